@@ -1,0 +1,156 @@
+/*
+ * sphb200.h -- C ABI of the B200-native SPH particle -> grid scatter library
+ * (libsphb200.so, built for sm_100a from sarracen_b200/csrc).
+ *
+ * This is the drop-in boundary for Sarracen's one data-parallel hot path.  Each
+ * entry point replaces one compiled routine behind the reference's backend
+ * interface `BaseBackend` (sarracen/interpolate/base_backend.py:7-177); the
+ * reference-side binding (a ctypes stub inside a `BaseBackend` subclass) is
+ * shown in INTEGRATION.md and implemented in sarracen_b200/backend.py.
+ *
+ * Conventions
+ *  - Every array pointer is a DEVICE pointer owned by the caller (PyTorch
+ *    tensors in practice).  The library never allocates or frees device
+ *    memory: scratch space is a caller-provided workspace.  Calls that need a
+ *    data-dependent amount report it through `ws_needed` and return
+ *    SPHB_ERR_WORKSPACE when `ws_bytes` is too small; the caller grows the
+ *    buffer and calls again.
+ *  - Particle columns are structure-of-arrays, all of one dtype (SPHB_F32 or
+ *    SPHB_F64).  SPHB_F64 computes and accumulates in double; SPHB_F32
+ *    computes in float with tile-local positions, accumulates float per tile
+ *    chunk and flushes into the double output.  Output images are always
+ *    float64, row-major [y][x] / [z][y][x], like the reference's
+ *    (cpu_backend.py:243).
+ *  - `stream` is a cudaStream_t passed as void*.  Work is stream-ordered;
+ *    the scatter calls synchronise the stream once (they read the bin count
+ *    back to size the sort), the others are fully asynchronous.
+ *  - Return value 0 on success, negative SPHB_ERR_* otherwise;
+ *    sphb_last_error() returns a thread-local message.
+ *  - No global mutable state; re-entrant across streams and devices.
+ */
+#ifndef SPHB200_H
+#define SPHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB_VERSION 100
+#define SPHB_MAX_WEIGHTS 4
+
+enum { SPHB_F32 = 0, SPHB_F64 = 1 };
+
+/* Weight functions.  The first three are the analytic kernels of
+ * sarracen/kernels/{cubic,quartic,quintic}_spline.py; SPHB_COLUMN_LUT is the
+ * tabulated column-integrated kernel evaluated by linear interpolation
+ * (sarracen/kernels/base_kernel.py:68-99). */
+enum { SPHB_CUBIC = 0, SPHB_QUARTIC = 1, SPHB_QUINTIC = 2, SPHB_COLUMN_LUT = 3 };
+
+enum {
+    SPHB_OK = 0,
+    SPHB_ERR_ARGUMENT = -1,  /* invalid argument */
+    SPHB_ERR_WORKSPACE = -2, /* workspace too small; *ws_needed holds the size */
+    SPHB_ERR_CUDA = -3,      /* CUDA runtime error; see sphb_last_error() */
+    SPHB_ERR_TOO_MANY = -4   /* more than 2^31-1 (particle, tile) pairs: split the particle set */
+};
+
+typedef void *sphb_stream;
+
+/* Particle columns (device pointers).  `z` may be NULL for 2-D data.  `w[k]`
+ * are the per-particle weights A m / rho (interpolate.py:448-472); one
+ * footprint walk accumulates all `n_weights` of them (the `_vec` methods and
+ * the normalisation pass of the reference are separate passes,
+ * cpu_backend.py:58-63, interpolate.py:587-594). */
+typedef struct sphb_particles {
+    int64_t n;
+    int dtype; /* SPHB_F32 | SPHB_F64, of x, y, z, h and w[] alike */
+    const void *x, *y, *z, *h;
+    int n_weights;
+    const void *w[SPHB_MAX_WEIGHTS];
+} sphb_particles;
+
+/* Weight function.  `ndim` is the exponent of h in the particle term
+ * w / h^ndim and the normalisation dimension of the analytic kernels
+ * (cpu_backend.py:251 and :34, :120, :168, :218).  For SPHB_COLUMN_LUT,
+ * `lut` is a device array of `lut_samples` float64 and `ndim` must be 2. */
+typedef struct sphb_kernel {
+    int kind;
+    int ndim;
+    double radius;
+    const double *lut;
+    int lut_samples;
+} sphb_kernel;
+
+/* Output raster: pixel (i, j[, k]) has its centre at x_min + (i + 1/2) pwx. */
+typedef struct sphb_raster {
+    int nx, ny, nz; /* nz = 1 for images */
+    double x_min, x_max, y_min, y_max, z_min, z_max;
+} sphb_raster;
+
+/* Optional counters filled by the scatter calls (host memory). */
+typedef struct sphb_stats {
+    int64_t n_pairs;      /* (particle, tile) pairs binned and sorted */
+    int64_t n_culled;     /* particles that touch no pixel */
+    int64_t n_tiles;      /* tiles in the raster */
+    int32_t tile_x, tile_y, tile_z;
+} sphb_stats;
+
+int sphb_version(void);
+const char *sphb_last_error(void);
+
+/* A4 -- column-integrated kernel table, sarracen/kernels/base_kernel.py:39-66
+ * and :102-117.  out: device float64[samples]. */
+int sphb_column_kernel(int kind, int samples, double *out, sphb_stream stream);
+
+/* B3 -- sampled scatter onto an image, replaces CPUBackend._fast_2d
+ * (cpu_backend.py:226-313) as used by interpolate_2d_render[_vec],
+ * interpolate_3d_projection[_vec] (use_z = 0) and interpolate_3d_cross[_vec]
+ * (use_z = 1: cull |z_slice - z| >= R h and add dz^2 to the distance).
+ * out[k]: device float64[ny * nx] per weight.  If `accumulate` is zero the
+ * images are cleared first, otherwise the result is added to them (for
+ * particle sets processed in several batches). */
+int sphb_scatter2d(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int use_z,
+                   double z_slice, int accumulate, double *const *out, void *ws, size_t ws_bytes,
+                   size_t *ws_needed, sphb_stats *stats, sphb_stream stream);
+
+/* B2/B3 -- sampled scatter onto a voxel grid in ONE pass over the particles,
+ * replaces the per-slice loop of CPUBackend.interpolate_3d_grid
+ * (cpu_backend.py:193-220).  out[k]: device float64[nz * ny * nx]. */
+int sphb_scatter3d(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int accumulate,
+                   double *const *out, void *ws, size_t ws_bytes, size_t *ws_needed,
+                   sphb_stats *stats, sphb_stream stream);
+
+/* B6 -- line cut through 2-D data, replaces CPUBackend._fast_2d_line
+ * (cpu_backend.py:450-538).  out[k]: device float64[pixels]. */
+int sphb_line2d(const sphb_particles *p, const sphb_kernel *k, int pixels, double x1, double x2,
+                double y1, double y2, int accumulate, double *const *out, sphb_stream stream);
+
+/* B7 -- line cut through 3-D data, replaces CPUBackend._fast_3d_line
+ * (cpu_backend.py:540-609). */
+int sphb_line3d(const sphb_particles *p, const sphb_kernel *k, int pixels, double x1, double x2,
+                double y1, double y2, double z1, double z2, int accumulate, double *const *out,
+                sphb_stream stream);
+
+/* B4 -- exact pixel-area integral of the 2-D cubic spline, replaces
+ * CPUBackend._exact_2d_render (cpu_backend.py:317-447) with the integrals of
+ * sarracen/kernels/cubic_spline_exact.py:7-217.  Float64 only. */
+int sphb_exact2d(const sphb_particles *p, const sphb_raster *r, int accumulate, double *const *out,
+                 sphb_stream stream);
+
+/* B5 -- exact column integral of the 3-D cubic spline, replaces
+ * CPUBackend._exact_3d_project (cpu_backend.py:611-720) with the integrals of
+ * sarracen/kernels/cubic_spline_exact.py:220-483.  Float64 only. */
+int sphb_exact3d_proj(const sphb_particles *p, const sphb_raster *r, int accumulate,
+                      double *const *out, sphb_stream stream);
+
+/* N5 -- out = nan_to_num(num / den) elementwise on the device
+ * (interpolate.py:594): 0/0 -> 0, +-inf -> +-DBL_MAX. */
+int sphb_normalize(double *num, const double *den, int64_t n, sphb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB200_H */

@@ -1,0 +1,76 @@
+"""Build libsphb200.so (CUDA, sm_100a) in-tree with nvcc.
+
+    python -m sarracen_b200.build [--force]
+
+The library is a plain C-ABI shared object (include/sphb200.h); it does not
+link against torch.  Objects are compiled in parallel, one nvcc per .cu file.
+"""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "lib")
+BUILD_DIR = os.path.join(HERE, "lib", "obj")
+LIB = os.path.join(OUT_DIR, "libsphb200.so")
+SOURCES = ["sphb_scatter.cu", "sphb_misc.cu", "sphb_exact.cu"]
+HEADERS = [os.path.join(CSRC, "sphb_common.cuh"),
+           os.path.join(os.path.dirname(HERE), "include", "sphb200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+              "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; libsphb200.so cannot be built")
+    return cand
+
+
+def _stale(target, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    jobs = []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
+        if force or _stale(obj, [path] + HEADERS):
+            jobs.append((path, obj))
+
+    def compile_one(job):
+        path, obj = job
+        cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-c", path, "-o", obj]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log = obj.replace(".o", ".ptxas.log")
+        with open(log, "w") as f:
+            f.write(res.stdout)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {path}:\n{res.stdout[-4000:]}")
+        return res.stdout
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            outs = list(ex.map(compile_one, jobs))
+        if verbose:
+            for o in outs:
+                print(o)
+    objs = [os.path.join(BUILD_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,185 @@
+// Shared device math and host helpers for libsphb200 (sm_100a).
+//
+// Kernel functions follow their mathematical definition in
+// sarracen/kernels/{cubic,quartic,quintic}_spline.py and the table lookup of
+// sarracen/kernels/base_kernel.py:89-97.  The normalisation constant is NOT
+// applied here: it is folded into the per-particle term w / h^ndim when a
+// particle is staged, so the per-contribution work is polynomial only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sphb200.h"
+
+namespace sphb {
+
+void set_error(const char *fmt, ...);
+
+#define SPHB_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            sphb::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call,                  \
+                            cudaGetErrorString(e_));                                     \
+            return SPHB_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+#define SPHB_LAUNCH_CHECK() SPHB_CUDA(cudaGetLastError())
+
+constexpr double kPi = 3.14159265358979323846;
+
+// sigma_d of each kernel (cubic_spline.py:15-17, quartic_spline.py:15-17,
+// quintic_spline.py:15-17); 1 for the already normalised column table.
+__host__ __device__ inline double kernel_norm(int kind, int ndim)
+{
+    switch (kind) {
+    case SPHB_CUBIC: return ndim == 1 ? 2.0 / 3.0 : ndim == 2 ? 10.0 / (7.0 * kPi) : 1.0 / kPi;
+    case SPHB_QUARTIC:
+        return ndim == 1 ? 1.0 / 24.0 : ndim == 2 ? 96.0 / (1199.0 * kPi) : 1.0 / (20.0 * kPi);
+    case SPHB_QUINTIC:
+        return ndim == 1 ? 1.0 / 120.0 : ndim == 2 ? 7.0 / (478.0 * kPi) : 1.0 / (120.0 * kPi);
+    default: return 1.0;
+    }
+}
+
+__host__ __device__ inline double kernel_default_radius(int kind)
+{
+    return kind == SPHB_CUBIC ? 2.0 : kind == SPHB_QUARTIC ? 2.5 : 3.0;
+}
+
+template <typename R> struct Real2;
+template <> struct Real2<float> { using type = float2; };
+template <> struct Real2<double> { using type = double2; };
+
+// Column table as the device sees it: entry i holds (T[i], T[i+1] - T[i]) so
+// one vector load serves the lerp T[i] + f (T[i+1] - T[i]).
+template <typename R> struct LutView {
+    const typename Real2<R>::type *tab;
+    R scale; // (S - 1) / radius
+    int last; // S - 1
+};
+
+// ---- square root -----------------------------------------------------------
+// double: MUFU.RSQ64H seed (2^-22.9) + one coupled Goldschmidt step + one
+// Heron correction -> ~1 ulp with 7 FMA-pipe ops and no slow-path branches.
+__device__ __forceinline__ double fast_sqrt(double a)
+{
+    a = fmax(a, 1e-290);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, g, a);
+    return fma(r, h, g);
+}
+__device__ __forceinline__ float fast_sqrt(float a)
+{
+    a = fmaxf(a, 1e-35f);
+    return a * rsqrtf(a);
+}
+
+// ---- unnormalised kernel shapes, valid for 0 <= q < radius ----------------
+template <int KIND, typename R> __device__ __forceinline__ R kernel_shape(R q)
+{
+    if (KIND == SPHB_CUBIC) {
+        R a = R(2) - q;
+        R w = R(0.25) * a * a * a;
+        R w1 = fma(q * q, fma(R(0.75), q, R(-1.5)), R(1));
+        return q < R(1) ? w1 : w;
+    } else if (KIND == SPHB_QUARTIC) {
+        R a = R(2.5) - q, b = R(1.5) - q, c = R(0.5) - q;
+        R a2 = a * a, b2 = b * b, c2 = c * c;
+        R w = a2 * a2;
+        if (q < R(1.5)) w = fma(R(-5), b2 * b2, w);
+        if (q < R(0.5)) w = fma(R(10), c2 * c2, w);
+        return w;
+    } else {
+        R a = R(3) - q, b = R(2) - q, c = R(1) - q;
+        R a2 = a * a, b2 = b * b, c2 = c * c;
+        R w = a2 * a2 * a;
+        if (q < R(2)) w = fma(R(-6), b2 * b2 * b, w);
+        if (q < R(1)) w = fma(R(15), c2 * c2 * c, w);
+        return w;
+    }
+}
+
+// floor(t) for 0 <= t < 2^22 without the conversion pipe: adding 2^52 (2^23)
+// leaves rint(t - 1/2) in the low mantissa bits.  When t is an exact integer
+// the index may come out one lower with f = 1, which evaluates to the same
+// table value.
+__device__ __forceinline__ int floor_nonneg(double t, double &f)
+{
+    double m = (t - 0.5) + 4503599627370496.0;
+    int i = __double2loint(m);
+    f = t - (m - 4503599627370496.0);
+    return i;
+}
+__device__ __forceinline__ int floor_nonneg(float t, float &f)
+{
+    float m = (t - 0.5f) + 8388608.0f;
+    int i = __float_as_int(m) & 0x7fffff;
+    f = t - (m - 8388608.0f);
+    return i;
+}
+
+// W(q) from q^2 (caller guarantees q^2 < radius^2).
+template <int KIND, typename R>
+__device__ __forceinline__ R kernel_eval_q2(R q2, const LutView<R> &lut)
+{
+    R q = fast_sqrt(q2);
+    if (KIND == SPHB_COLUMN_LUT) {
+        R f;
+        int i = floor_nonneg(q * lut.scale, f);
+        i = max(0, min(i, lut.last));
+        typename Real2<R>::type e = lut.tab[i];
+        return fma(f, e.y, e.x);
+    } else {
+        return kernel_shape<KIND>(q);
+    }
+}
+
+// W(q) for arbitrary q (line cuts: no q <= R guard in the reference,
+// cpu_backend.py:527-528, :598-599): zero outside [0, R).
+template <int KIND>
+__device__ __forceinline__ double kernel_eval_any(double q, double radius, const double *lut, int samples)
+{
+    if (KIND == SPHB_COLUMN_LUT) {
+        double t = q * (samples - 1) / radius;
+        double fl = floor(t);
+        int i0 = (int)fmin(fmax(fl, 0.0), (double)(samples - 1));
+        int i1 = (int)fmin(fmax(ceil(t), 0.0), (double)(samples - 1));
+        double f = t - (double)i0;
+        return fma(f, lut[i1] - lut[i0], lut[i0]);
+    } else {
+        if (!(q >= 0.0) || q >= radius) return 0.0;
+        return kernel_shape<KIND>(q);
+    }
+}
+
+// small exact int -> real without the conversion pipe
+__device__ __forceinline__ double int_to_real(int i, double)
+{
+    return __hiloint2double(0x43300000, i ^ 0x80000000) - 4503601774854144.0; // 2^52 + 2^31
+}
+__device__ __forceinline__ float int_to_real(int i, float)
+{
+    return __int_as_float(0x4B400000 + i) - 12582912.0f; // 1.5 * 2^23, |i| < 2^22
+}
+
+__device__ __forceinline__ void red_add(double *addr, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ double load_as_double(const void *base, int64_t i)
+{
+    return (double)__ldg(reinterpret_cast<const T *>(base) + i);
+}
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace sphb

@@ -1,0 +1,380 @@
+// Exact (pixel-integrated) cubic-spline rendering for B200 (sm_100a).
+//
+// Replaces CPUBackend._exact_2d_render (sarracen/interpolate/cpu_backend.py:
+// 317-447) and CPUBackend._exact_3d_project (:611-720).  The integrals are the
+// closed forms of Petkova, Laibe & Bonnell (2018) as the reference lays them
+// out in sarracen/kernels/cubic_spline_exact.py; they are restated here from
+// those formulas, in double precision (no fast-math), because the pixel value
+// is a difference of edge/face terms that cancel to many digits.
+//
+// Decomposition: these paths cost 10^3 - 10^4 double-precision operations per
+// (particle, pixel), so accumulation is not the bottleneck.  One warp takes 32
+// particles at a time, lanes are spread over the pixels of one particle's
+// bounding box, every lane evaluates its pixel's full boundary integral and
+// adds it to the image with red.global.add.f64.
+//
+//  - 2-D: the four edge integrals of a pixel are evaluated directly.  The
+//    reference evaluates each interior edge once and adds it to one pixel and
+//    subtracts it from the neighbour (:404-440); line_int is exactly
+//    antisymmetric under that swap, so both give the same four terms per pixel.
+//  - A particle whose clamped pixel range is empty contributes nothing; the
+//    reference's lone top-row / left-column edge terms for such a particle
+//    (:370, :387) and its out-of-bounds row write (:353) are not reproduced.
+#include "sphb_common.cuh"
+
+namespace sphb {
+
+namespace ex {
+
+__device__ __forceinline__ double log_tan_term(double phi) { return log(tan(0.5 * phi + 0.25 * kPi)); }
+
+// cubic_spline_exact.py:124-155 -- region 0 < q <= 1
+__device__ double f1_2d(double phi, double q0)
+{
+    double s, c;
+    sincos(phi, &s, &c);
+    const double c2 = c * c, tn = s / c;
+    const double logs = log_tan_term(phi);
+    const double i2 = tn;
+    const double i4 = (1.0 / 3.0) * tn * (2.0 + 1.0 / c2);
+    const double i5 = (1.0 / 16.0) * (0.5 * (11.0 * s + 3.0 * sin(3.0 * phi)) / c2 / c2 + 6.0 * logs);
+    const double q02 = q0 * q0;
+    return 5.0 / 7.0 * q02 / kPi * (i2 - 0.75 * q02 * i4 + 0.3 * q02 * q0 * i5);
+}
+
+// cubic_spline_exact.py:158-196 -- region 1 < q <= 2
+__device__ double f2_2d(double phi, double q0)
+{
+    double s, c;
+    sincos(phi, &s, &c);
+    const double c2 = c * c, tn = s / c;
+    const double q02 = q0 * q0, q03 = q02 * q0;
+    const double logs = log_tan_term(phi);
+    const double i0 = phi, i2 = tn;
+    const double i3 = 0.5 * (tn / c + logs);
+    const double i4 = (1.0 / 3.0) * tn * (2.0 + 1.0 / c2);
+    const double i5 = (1.0 / 16.0) * (0.5 * (11.0 * s + 3.0 * sin(3.0 * phi)) / c2 / c2 + 6.0 * logs);
+    return 5.0 / 7.0 * q02 / kPi *
+           (2.0 * i2 - 2.0 * q0 * i3 + 0.75 * q02 * i4 - 0.1 * q03 * i5 - 0.1 / q02 * i0);
+}
+
+// cubic_spline_exact.py:199-217 -- region q > 2
+__device__ __forceinline__ double f3_2d(double phi) { return 0.5 / kPi * phi; }
+
+// cubic_spline_exact.py:58-121
+__device__ double full_2d_mod(double phi, double q0)
+{
+    if (q0 <= 1.0) {
+        const double q = q0 / cos(phi);
+        if (q <= 1.0) return f1_2d(phi, q0);
+        const double pa = acos(q0);
+        if (q <= 2.0) return f2_2d(phi, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
+        const double pb = acos(0.5 * q0);
+        return f3_2d(phi) - f3_2d(pb) + f2_2d(pb, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
+    }
+    if (q0 <= 2.0) {
+        const double q = q0 / cos(phi);
+        if (q <= 2.0) return f2_2d(phi, q0);
+        const double pb = acos(0.5 * q0);
+        return f3_2d(phi) - f3_2d(pb) + f2_2d(pb, q0);
+    }
+    return f3_2d(phi);
+}
+
+// cubic_spline_exact.py:7-55
+__device__ double line_int(double r0, double d1, double d2, double h)
+{
+    if (r0 == 0.0) return 0.0;
+    const double sign = r0 > 0.0 ? 1.0 : -1.0, ar0 = fabs(r0);
+    const double q0 = ar0 / h;
+    const double pa = atan(fabs(d1) / ar0), pb = atan(fabs(d2) / ar0);
+    const double fa = full_2d_mod(pa, q0), fb = full_2d_mod(pb, q0);
+    if (d1 * d2 >= 0.0) return sign * (fa + fb);
+    if (fabs(d1) < fabs(d2)) return sign * (fb - fa);
+    return sign * (fa - fb);
+}
+
+// cubic_spline_exact.py:457-483
+struct ITerms {
+    double i0, i1, i2, i3, i4, i5;
+};
+
+__device__ __noinline__ ITerms get_i_terms(double cosp, double a2, double a)
+{
+    ITerms t;
+    const double cosp2 = cosp * cosp;
+    const double p = acos(cosp);
+    const double tn = sqrt(1.0 - cosp2) / cosp;
+    const double mu2_1 = 1.0 / (1.0 + cosp2 / a2);
+    const double u2 = (1.0 - cosp2) * mu2_1, u = sqrt(u2);
+    const double logs = log((1.0 + u) / (1.0 - u));
+    const double i1 = atan2(u, a);
+    const double fac = 1.0 / (1.0 - u2);
+    const double im1 = 0.5 * a * logs + i1;
+    const double im3 = im1 + a * 0.25 * (1.0 + a2) * (2.0 * u * fac + logs);
+    const double im5 = im3 + a * (1.0 + a2) * (1.0 + a2) / 16.0 * ((10.0 * u - 6.0 * u * u2) * fac * fac + 3.0 * logs);
+    t.i0 = p;
+    t.i1 = i1;
+    t.i2 = p + a2 * tn;
+    t.i3 = im3;
+    t.i4 = p + 2.0 * a2 * tn + (1.0 / 3.0) * a2 * a2 * tn * (2.0 + 1.0 / cosp2);
+    t.i5 = im5;
+    return t;
+}
+
+// cubic_spline_exact.py:353-454
+__device__ __noinline__ double full_integral_3d(double d, double r0, double r1, double h)
+{
+    const double r0h = r0 / h;
+    const double phi = atan(fabs(d) / r1);
+    if (fabs(r0h) == 0.0 || fabs(r1 / h) == 0.0 || fabs(phi) == 0.0) return 0.0;
+
+    const double h2 = h * h, r03 = r0 * r0 * r0;
+    const double r0h2 = r0h * r0h, r0h3 = r0h2 * r0h;
+    const double r0h_2 = 1.0 / r0h2, r0h_3 = 1.0 / r0h3;
+    double b1 = 0.0, b2 = 0.0, b3;
+    if (r0 > 2.0 * h) {
+        b3 = 0.25 * h2 * h;
+    } else if (r0 > h) {
+        b3 = 0.25 * r03 * (-4.0 / 3.0 + r0h - 0.3 * r0h2 + 1.0 / 30.0 * r0h3 - 1.0 / 15.0 * r0h_3 + 8.0 / 5.0 * r0h_2);
+        b2 = 0.25 * r03 * (-4.0 / 3.0 + r0h - 0.3 * r0h2 + 1.0 / 30.0 * r0h3 - 1.0 / 15.0 * r0h_3);
+    } else {
+        b3 = 0.25 * r03 * (-2.0 / 3.0 + 0.3 * r0h2 - 0.1 * r0h3 + 1.4 * r0h_2);
+        b2 = 0.25 * r03 * (-2.0 / 3.0 + 0.3 * r0h2 - 0.1 * r0h3 - 0.2 * r0h_2);
+        b1 = 0.25 * r03 * (-2.0 / 3.0 + 0.3 * r0h2 - 0.1 * r0h3);
+    }
+
+    const double a = r1 / r0, a2 = a * a;
+    const double linedist2 = r0 * r0 + r1 * r1;
+    const double cphi = cos(phi);
+    const double r_ = r1 / cphi;
+    const double r2 = r0 * r0 + r_ * r_;
+    double d2 = 0.0, d3 = 0.0;
+
+    if (linedist2 < h2) {
+        const ITerms t = get_i_terms(r1 / sqrt(h2 - r0 * r0), a2, a);
+        d2 = -1.0 / 6.0 * t.i2 + 0.25 * r0h * t.i3 - 0.15 * r0h2 * t.i4;
+        d2 += 1.0 / 30.0 * r0h3 * t.i5 - 1.0 / 60.0 * r0h_3 * t.i1;
+        d2 += (b1 - b2) / r03 * t.i0;
+    }
+    if (linedist2 < 4.0 * h2) {
+        const ITerms t = get_i_terms(r1 / sqrt(4.0 * h2 - r0 * r0), a2, a);
+        d3 = 1.0 / 3.0 * t.i2 - 0.25 * r0h * t.i3 + 3.0 / 40.0 * r0h2 * t.i4;
+        d3 += -1.0 / 120.0 * r0h3 * t.i5 + 4.0 / 15.0 * r0h_3 * t.i1;
+        d3 += (b2 - b3) / r03 * t.i0 + d2;
+    }
+    const ITerms t = get_i_terms(cphi, a2, a);
+    if (r2 <= h2)
+        return r0h3 / kPi * (1.0 / 6.0 * t.i2 - 3.0 / 40.0 * r0h2 * t.i4 + 1.0 / 40.0 * r0h3 * t.i5 + b1 / r03 * t.i0);
+    if (r2 <= 4.0 * h2)
+        return r0h3 / kPi *
+               (0.25 * (4.0 / 3.0 * t.i2 - (r0 / h) * t.i3 + 0.3 * r0h2 * t.i4 - 1.0 / 30.0 * r0h3 * t.i5 +
+                        1.0 / 15.0 * r0h_3 * t.i1) +
+                b2 / r03 * t.i0 + d2);
+    return r0h3 / kPi * (-0.25 * r0h_3 * t.i1 + b3 / r03 * t.i0 + d3);
+}
+
+// cubic_spline_exact.py:284-350 (its diagnostic prints are dropped)
+__device__ double line_int3d(double r0, double r1, double d1, double d2, double h)
+{
+    if (fabs(r0) == 0.0) return 0.0;
+    double sign = r0 > 0.0 ? 1.0 : -1.0;
+    const double ar0 = fabs(r0);
+    double ar1 = r1;
+    if (!(r1 > 0.0)) {
+        sign = -sign;
+        ar1 = -r1;
+    }
+    double int1 = full_integral_3d(d1, ar0, ar1, h);
+    double int2 = full_integral_3d(d2, ar0, ar1, h);
+    if (int1 < 0.0) int1 = 0.0;
+    if (int2 < 0.0) int2 = 0.0;
+    if (d1 * d2 >= 0.0) return sign * (int1 + int2);
+    if (fabs(d1) < fabs(d2)) return sign * (int2 - int1);
+    return sign * (int1 - int2);
+}
+
+// cubic_spline_exact.py:220-281
+__device__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx, double wy,
+                              double h)
+{
+    const double dx = x2 - x1, dy = y2 - y1;
+    double res = 0.0;
+    res += line_int3d(r0, 0.5 * wy + dy, 0.5 * wx - dx, 0.5 * wx + dx, h);
+    res += line_int3d(r0, 0.5 * wy - dy, 0.5 * wx + dx, 0.5 * wx - dx, h);
+    res += line_int3d(r0, 0.5 * wx + dx, 0.5 * wy + dy, 0.5 * wy - dy, h);
+    res += line_int3d(r0, 0.5 * wx - dx, 0.5 * wy - dy, 0.5 * wy + dy, h);
+    return res;
+}
+
+} // namespace ex
+
+struct ExactView {
+    int nx, ny;
+    double x_min, y_min, pwx, pwy;
+};
+
+constexpr int kExactWarps = 4;
+
+template <typename T, int NW, bool PROJ3D>
+__global__ void __launch_bounds__(kExactWarps * 32)
+exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
+             const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
+             const T *__restrict__ w3, int64_t n, double *o0, double *o1, double *o2, double *o3)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T *wsrc[4] = {w0, w1, w2, w3};
+    double *outs[4] = {o0, o1, o2, o3};
+    const int64_t warps_total = (int64_t)gridDim.x * kExactWarps;
+    for (int64_t base = ((int64_t)blockIdx.x * kExactWarps + warp) * 32; base < n; base += warps_total * 32) {
+        const int64_t p = base + lane;
+        int i0 = 0, i1 = 0, j0 = 0, j1 = 0;
+        double xp = 0, yp = 0, hp = 1, wv[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) wv[k] = 0.0;
+        if (p < n) {
+            xp = (double)__ldg(x + p);
+            yp = (double)__ldg(y + p);
+            hp = (double)__ldg(h + p);
+            if (hp > 0.0 && isfinite(hp) && isfinite(xp) && isfinite(yp)) {
+                // cpu_backend.py:343-363 / :639-664
+                const double rad = 2.0 * hp;
+                const double a0 = floor((xp - rad - v.x_min) / v.pwx), a1 = ceil((xp + rad - v.x_min) / v.pwx);
+                const double b0 = floor((yp - rad - v.y_min) / v.pwy), b1 = ceil((yp + rad - v.y_min) / v.pwy);
+                if (!(a1 < 0.0 || a0 >= v.nx || b1 < 0.0 || b0 >= v.ny)) {
+                    i0 = (int)fmax(a0, 0.0);
+                    i1 = (int)fmin(a1, (double)v.nx);
+                    j0 = (int)fmax(b0, 0.0);
+                    j1 = (int)fmin(b1, (double)v.ny);
+                }
+#pragma unroll
+                for (int k = 0; k < NW; k++) wv[k] = (double)__ldg(wsrc[k] + p);
+            }
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, i1 > i0 && j1 > j0);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int si0 = __shfl_sync(0xffffffffu, i0, src), si1 = __shfl_sync(0xffffffffu, i1, src);
+            const int sj0 = __shfl_sync(0xffffffffu, j0, src), sj1 = __shfl_sync(0xffffffffu, j1, src);
+            const double sx = __shfl_sync(0xffffffffu, xp, src), sy = __shfl_sync(0xffffffffu, yp, src);
+            const double sh = __shfl_sync(0xffffffffu, hp, src);
+            double sw[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) sw[k] = __shfl_sync(0xffffffffu, wv[k], src);
+            const int bw = si1 - si0, total = bw * (sj1 - sj0);
+            for (int e = lane; e < total; e += 32) {
+                const int jj = e / bw, ii = e - jj * bw;
+                const int i = si0 + ii, j = sj0 + jj;
+                const double xpix = v.x_min + (i + 0.5) * v.pwx, ypix = v.y_min + (j + 0.5) * v.pwy;
+                const double dx = xpix - sx, dy = ypix - sy;
+                double val;
+                if (PROJ3D) {
+                    // cpu_backend.py:673-713
+                    const double q2 = (dx * dx + dy * dy) / (sh * sh);
+                    if (!(q2 < 4.0 + 3.0 * v.pwx * v.pwy / (sh * sh))) continue;
+                    const double pwz = 4.0 * sh;
+                    double s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
+                    s += ex::surface_int(ypix - sy + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
+                    s += ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
+                    s += ex::surface_int(xpix - sx + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
+                    s += ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
+                    // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (:628-629)
+                    const double h3 = sh * sh * sh;
+                    val = s * (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
+                } else {
+                    // cpu_backend.py:365-440: top, left, bottom, right edge
+                    double s = ex::line_int(0.5 * v.pwy - dy, 0.5 * v.pwx + dx, 0.5 * v.pwx - dx, sh);
+                    s += ex::line_int(0.5 * v.pwx - dx, 0.5 * v.pwy - dy, 0.5 * v.pwy + dy, sh);
+                    s += ex::line_int(0.5 * v.pwy + dy, 0.5 * v.pwx - dx, 0.5 * v.pwx + dx, sh);
+                    s += ex::line_int(0.5 * v.pwx + dx, 0.5 * v.pwy + dy, 0.5 * v.pwy - dy, sh);
+                    // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (:333, :365)
+                    val = s * (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
+                }
+                if (val != 0.0) {
+#pragma unroll
+                    for (int k = 0; k < NW; k++) red_add(outs[k] + (size_t)j * v.nx + i, sw[k] * val);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int NW, bool PROJ3D>
+static int launch_exact(const ExactView &v, const sphb_particles *p, double *const *out, cudaStream_t stream)
+{
+    int grid = div_up(p->n, kExactWarps * 32);
+    grid = grid < 1 ? 1 : grid > 148 * 16 ? 148 * 16 : grid;
+    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NW; i++) {
+        w[i] = static_cast<const T *>(p->w[i]);
+        o[i] = out[i];
+    }
+    exact_kernel<T, NW, PROJ3D><<<grid, kExactWarps * 32, 0, stream>>>(
+        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), w[0],
+        w[1], w[2], w[3], p->n, o[0], o[1], o[2], o[3]);
+    SPHB_LAUNCH_CHECK();
+    return SPHB_OK;
+}
+
+template <typename T, bool PROJ3D>
+static int exact_nw(const ExactView &v, const sphb_particles *p, double *const *out, cudaStream_t stream)
+{
+    switch (p->n_weights) {
+    case 1: return launch_exact<T, 1, PROJ3D>(v, p, out, stream);
+    case 2: return launch_exact<T, 2, PROJ3D>(v, p, out, stream);
+    case 3: return launch_exact<T, 3, PROJ3D>(v, p, out, stream);
+    default: return launch_exact<T, 4, PROJ3D>(v, p, out, stream);
+    }
+}
+
+static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d, int accumulate,
+                      double *const *out, cudaStream_t stream)
+{
+    if (!p || !r || !out || p->n < 0 || p->n_weights < 1 || p->n_weights > SPHB_MAX_WEIGHTS ||
+        (p->dtype != SPHB_F32 && p->dtype != SPHB_F64) || r->nx <= 0 || r->ny <= 0 ||
+        !(r->x_max > r->x_min) || !(r->y_max > r->y_min)) {
+        set_error("invalid argument to exact render");
+        return SPHB_ERR_ARGUMENT;
+    }
+    for (int i = 0; i < p->n_weights; i++)
+        if (!out[i] || (p->n > 0 && !p->w[i])) {
+            set_error("missing weight or output %d", i);
+            return SPHB_ERR_ARGUMENT;
+        }
+    if (p->n > 0 && (!p->x || !p->y || !p->h)) {
+        set_error("missing particle column");
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (!accumulate)
+        for (int i = 0; i < p->n_weights; i++)
+            SPHB_CUDA(cudaMemsetAsync(out[i], 0, sizeof(double) * (size_t)r->nx * r->ny, stream));
+    if (p->n == 0) return SPHB_OK;
+    ExactView v;
+    v.nx = r->nx;
+    v.ny = r->ny;
+    v.x_min = r->x_min;
+    v.y_min = r->y_min;
+    v.pwx = (r->x_max - r->x_min) / r->nx;
+    v.pwy = (r->y_max - r->y_min) / r->ny;
+    if (p->dtype == SPHB_F32)
+        return proj3d ? exact_nw<float, true>(v, p, out, stream) : exact_nw<float, false>(v, p, out, stream);
+    return proj3d ? exact_nw<double, true>(v, p, out, stream) : exact_nw<double, false>(v, p, out, stream);
+}
+
+} // namespace sphb
+
+using namespace sphb;
+
+extern "C" int sphb_exact2d(const sphb_particles *p, const sphb_raster *r, int accumulate, double *const *out,
+                            sphb_stream stream)
+{
+    return exact_impl(p, r, false, accumulate, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sphb_exact3d_proj(const sphb_particles *p, const sphb_raster *r, int accumulate,
+                                 double *const *out, sphb_stream stream)
+{
+    return exact_impl(p, r, true, accumulate, out, static_cast<cudaStream_t>(stream));
+}

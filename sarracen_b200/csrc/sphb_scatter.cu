@@ -1,0 +1,655 @@
+// Sampled SPH scatter onto pixel / voxel rasters for B200 (sm_100a).
+//
+// Replaces CPUBackend._fast_2d (sarracen/interpolate/cpu_backend.py:226-313)
+// and the per-slice loop of CPUBackend.interpolate_3d_grid (:193-220):
+//
+//   out[j,i] = sum_p (w_p / h_p^d) W( |r_ij - r_p| / h_p )
+//
+// The bounding box the reference builds per particle is only a cull (every W
+// is exactly zero at and beyond its radius), so the result is the plain sum
+// over all pixel centres inside the support -- computed here in a different
+// order and a different decomposition:
+//
+//  1. bin    every particle is keyed by the raster tiles its support box
+//            covers (count -> exclusive scan -> emit (tile, particle) pairs),
+//  2. sort   cub::DeviceRadixSort on the tile key (only the bits in use),
+//  3. render the sorted pair list is cut into fixed chunks, one CTA per
+//            chunk.  A CTA walks the tile segments of its chunk; per tile it
+//            stages the particles' derived records into shared memory, and
+//            every warp owns an exclusive strip (2-D: rows, 3-D: z-planes) of
+//            the tile's shared-memory accumulator, so the footprint walk is a
+//            plain load-add-store without atomics.  Lanes are spread linearly
+//            over (footprint box ∩ strip).
+//  4. flush  a finished tile segment is added to the float64 output with
+//            red.global.add.f64 -- the only global atomics, once per tile
+//            segment, coalesced along x.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "sphb_common.cuh"
+
+namespace sphb {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kBatch = kThreads;  // particles staged per round, one per thread
+constexpr int kChunkPairs = 2048; // sorted pairs per CTA
+
+// Geometry of one call, shared by every kernel of the pipeline.
+struct View {
+    int nx, ny, nz;
+    int tx, ty, tz;    // tile size in pixels
+    int ntx, nty, ntz; // tiles per axis
+    double x_min, y_min, z_min;
+    double inv_pwx, inv_pwy, inv_pwz;
+    double pwx, pwy, pwz;
+    double radius;
+    double z_slice;
+    int use_z; // 2-D raster, particles carry a depth (cross-section)
+    int dim3;  // voxel raster
+    int ndim;  // exponent of h in the particle term
+    double norm;
+};
+
+struct TileBox {
+    int x0, x1, y0, y1, z0, z1; // tile index ranges, inclusive
+};
+
+__device__ __forceinline__ int clamp_to_int(double v, int lo, int hi)
+{
+    // also maps NaN to lo
+    return (int)fmin(fmax(v, (double)lo), (double)hi);
+}
+
+// Pixel box [lo, hi) that holds every pixel centre within rad of c.
+__device__ __forceinline__ void pixel_range(double c, double rad, double origin, double inv_pw, int n,
+                                            int &lo, int &hi)
+{
+    // centre of pixel i sits at origin + (i + 1/2) pw
+    lo = clamp_to_int(ceil((c - rad - origin) * inv_pw - 0.5), 0, n);
+    hi = clamp_to_int(floor((c + rad - origin) * inv_pw - 0.5) + 1.0, 0, n);
+}
+
+// Tiles covered by a particle's support box; false if it touches no pixel.
+template <typename T>
+__device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const T *y, const T *z,
+                                               const T *h, int64_t i, TileBox &b)
+{
+    double hp = (double)__ldg(h + i);
+    double xp = (double)__ldg(x + i), yp = (double)__ldg(y + i);
+    if (!(hp > 0.0) || !isfinite(hp) || !isfinite(xp) || !isfinite(yp)) return false;
+    double rad = v.radius * hp;
+    int lo, hi;
+    b.z0 = b.z1 = 0;
+    if (v.dim3) {
+        double zp = (double)__ldg(z + i);
+        if (!isfinite(zp)) return false;
+        pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, lo, hi);
+        if (hi <= lo) return false;
+        b.z0 = lo / v.tz;
+        b.z1 = (hi - 1) / v.tz;
+    } else if (v.use_z) {
+        double dz = v.z_slice - (double)__ldg(z + i);
+        if (!(fabs(dz) < rad)) return false; // cpu_backend.py:264
+    }
+    pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, lo, hi);
+    if (hi <= lo) return false;
+    b.x0 = lo / v.tx;
+    b.x1 = (hi - 1) / v.tx;
+    pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, lo, hi);
+    if (hi <= lo) return false;
+    b.y0 = lo / v.ty;
+    b.y1 = (hi - 1) / v.ty;
+    return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint64_t *counts)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    TileBox b;
+    uint64_t c = 0; // counts[n] = 0 so that the exclusive scan leaves the total there
+    if (i < n && particle_tiles(v, x, y, z, h, i, b))
+        c = (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) * (uint64_t)(b.z1 - b.z0 + 1);
+    counts[i] = c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n,
+                  const uint64_t *offsets, uint32_t *keys, uint32_t *vals)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TileBox b;
+    if (!particle_tiles(v, x, y, z, h, i, b)) return;
+    uint64_t o = offsets[i];
+    for (int tz = b.z0; tz <= b.z1; tz++)
+        for (int ty = b.y0; ty <= b.y1; ty++)
+            for (int tx = b.x0; tx <= b.x1; tx++) {
+                keys[o] = (uint32_t)((tz * v.nty + ty) * v.ntx + tx);
+                vals[o] = (uint32_t)i;
+                o++;
+            }
+}
+
+__global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t *tile_end)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    if (i == n_pairs - 1 || keys[i] != keys[i + 1]) tile_end[keys[i]] = (uint32_t)(i + 1);
+}
+
+// ---------------------------------------------------------------------------
+// Render.
+
+// Staged particle record, tile-local.  Coordinates are in pixel units with the
+// tile origin subtracted; in float mode the centre is split into the nearest
+// pixel (ic) and a fraction in [-1/2, 1/2] so that position differences keep
+// full float precision however large the raster is.
+template <typename R, int NW> struct Staged {
+    R fx[kBatch], fy[kBatch], fz[kBatch];    // centre (double mode) / fraction (float mode)
+    R sx[kBatch], sy[kBatch], sz[kBatch];    // (pixel width / h)^2 per axis
+    R c[kBatch];                             // dz^2 / h^2 of a cross-section, else 0
+    R term[NW][kBatch];                      // norm * w / h^ndim
+    int cx[kBatch], cy[kBatch], cz[kBatch];  // nearest pixel (float mode), else 0
+    uint32_t bx[kBatch], by[kBatch], bz[kBatch]; // footprint box ∩ tile: lo | hi << 16
+};
+
+template <typename R> struct Split;
+template <> struct Split<double> {
+    static __device__ __forceinline__ void apply(double u, double &f, int &ic)
+    {
+        f = u;
+        ic = 0;
+    }
+};
+template <> struct Split<float> {
+    static __device__ __forceinline__ void apply(double u, float &f, int &ic)
+    {
+        double r = rint(u);
+        r = fmin(fmax(r, -2097152.0), 2097152.0);
+        ic = (int)r;
+        f = (float)(u - r);
+    }
+};
+
+template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ>
+__global__ void __launch_bounds__(kThreads)
+render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+              const T *__restrict__ h, const T *__restrict__ w0, const T *__restrict__ w1,
+              const T *__restrict__ w2, const T *__restrict__ w3, const double *__restrict__ lut,
+              int lut_samples, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+              const uint32_t *__restrict__ tile_end, int64_t n_pairs, double *o0, double *o1, double *o2,
+              double *o3)
+{
+    using R2 = typename Real2<R>::type;
+    constexpr int SX = TX + 8;            // padded row stride (bank spread for narrow boxes)
+    constexpr int PLANE = SX * TY;        // elements per z-plane
+    constexpr int ACC = PLANE * TZ;       // elements per weight
+    constexpr int OWN = DIM3 ? TZ : TY;   // extent of the axis split among warps
+    constexpr int PER_WARP = OWN / kWarps;
+    static_assert(OWN % kWarps == 0, "strip split");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *acc = reinterpret_cast<R *>(smem_raw);
+    Staged<R, NW> *st = reinterpret_cast<Staged<R, NW> *>(acc + (size_t)ACC * NW);
+    R2 *lut_s = reinterpret_cast<R2 *>(st + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T *wsrc[4] = {w0, w1, w2, w3};
+    double *outs[4] = {o0, o1, o2, o3};
+
+    LutView<R> lv;
+    lv.tab = lut_s;
+    lv.scale = R(0);
+    lv.last = 0;
+    if (KIND == SPHB_COLUMN_LUT) {
+        for (int i = tid; i < lut_samples; i += kThreads) {
+            double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
+            R2 e;
+            e.x = (R)a;
+            e.y = (R)(b - a);
+            lut_s[i] = e;
+        }
+        lv.scale = (R)((double)(lut_samples - 1) / v.radius);
+        lv.last = lut_samples - 1;
+    }
+    for (int i = tid; i < ACC * NW; i += kThreads) acc[i] = R(0);
+    __syncthreads();
+
+    const R rad2 = (R)(v.radius * v.radius);
+    const int own_lo = warp * PER_WARP, own_hi = own_lo + PER_WARP;
+
+    const int64_t chunk_lo = (int64_t)blockIdx.x * kChunkPairs;
+    const int64_t chunk_hi = min(chunk_lo + (int64_t)kChunkPairs, n_pairs);
+    int64_t pos = chunk_lo;
+
+    while (pos < chunk_hi) {
+        const uint32_t tile = keys[pos];
+        const int64_t seg_hi = min((int64_t)tile_end[tile], chunk_hi);
+        const int ttx = tile % v.ntx, tty = (tile / v.ntx) % v.nty, ttz = tile / (v.ntx * v.nty);
+        const int ox = ttx * TX, oy = tty * TY, oz = ttz * TZ; // tile origin in pixels
+        const int lim_x = min(TX, v.nx - ox), lim_y = min(TY, v.ny - oy), lim_z = min(TZ, v.nz - oz);
+
+        for (int64_t base = pos; base < seg_hi; base += kBatch) {
+            const int nb = (int)min((int64_t)kBatch, seg_hi - base);
+            // ---- stage: one particle per thread --------------------------------
+            if (tid < nb) {
+                const int64_t p = vals[base + tid];
+                const double hp = (double)__ldg(h + p);
+                const double xp = (double)__ldg(x + p), yp = (double)__ldg(y + p);
+                const double rad = v.radius * hp;
+                const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
+                int lo, hi;
+                // pixel-unit coordinate in which pixel i has its centre at i
+                const double ux = (xp - v.x_min) * v.inv_pwx - 0.5 - ox;
+                const double uy = (yp - v.y_min) * v.inv_pwy - 0.5 - oy;
+                pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, lo, hi);
+                lo = max(lo - ox, 0);
+                hi = min(hi - ox, lim_x);
+                st->bx[tid] = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
+                pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, lo, hi);
+                lo = max(lo - oy, 0);
+                hi = min(hi - oy, lim_y);
+                st->by[tid] = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
+                Split<R>::apply(ux, st->fx[tid], st->cx[tid]);
+                Split<R>::apply(uy, st->fy[tid], st->cy[tid]);
+                st->sx[tid] = (R)(v.pwx * v.pwx * hinv2);
+                st->sy[tid] = (R)(v.pwy * v.pwy * hinv2);
+                double cc = 0.0;
+                if (DIM3) {
+                    const double zp = (double)__ldg(z + p);
+                    const double uz = (zp - v.z_min) * v.inv_pwz - 0.5 - oz;
+                    pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, lo, hi);
+                    lo = max(lo - oz, 0);
+                    hi = min(hi - oz, lim_z);
+                    st->bz[tid] = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
+                    Split<R>::apply(uz, st->fz[tid], st->cz[tid]);
+                    st->sz[tid] = (R)(v.pwz * v.pwz * hinv2);
+                } else if (v.use_z) {
+                    const double dz = v.z_slice - (double)__ldg(z + p);
+                    cc = dz * dz * hinv2;
+                }
+                st->c[tid] = (R)cc;
+                const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
+#pragma unroll
+                for (int k = 0; k < NW; k++) st->term[k][tid] = (R)((double)__ldg(wsrc[k] + p) * scale);
+            }
+            __syncthreads();
+
+            // ---- accumulate: each warp scans the batch for its strip ------------
+            for (int g = 0; g < nb; g += 32) {
+                const int me = g + lane;
+                bool hit = false;
+                if (me < nb) {
+                    const uint32_t b = DIM3 ? st->bz[me] : st->by[me];
+                    const int lo = (int)(b & 0xffff), hi = (int)(b >> 16);
+                    hit = max(lo, own_lo) < min(hi, own_hi);
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int s = g + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t bx = st->bx[s], by = st->by[s];
+                    int x0 = (int)(bx & 0xffff), x1 = (int)(bx >> 16);
+                    int y0 = (int)(by & 0xffff), y1 = (int)(by >> 16);
+                    int z0 = 0, z1 = 1;
+                    if (DIM3) {
+                        const uint32_t bz = st->bz[s];
+                        z0 = max((int)(bz & 0xffff), own_lo);
+                        z1 = min((int)(bz >> 16), own_hi);
+                    } else {
+                        y0 = max(y0, own_lo);
+                        y1 = min(y1, own_hi);
+                    }
+                    const int wx = x1 - x0, wy = y1 - y0;
+                    if (wx <= 0 || wy <= 0) continue;
+                    const int wxy = wx * wy, total = wxy * (z1 - z0);
+                    const unsigned inv_wx = 65536u / (unsigned)wx + 1u;
+                    const unsigned inv_wxy = DIM3 ? (1u << 20) / (unsigned)wxy + 1u : 0u;
+                    const R fx = st->fx[s], fy = st->fy[s], sx = st->sx[s], sy = st->sy[s];
+                    const R cc = st->c[s];
+                    const int cx = st->cx[s], cy = st->cy[s];
+                    R fz = R(0), sz = R(0);
+                    int cz = 0;
+                    if (DIM3) {
+                        fz = st->fz[s];
+                        sz = st->sz[s];
+                        cz = st->cz[s];
+                    }
+                    R term[NW];
+#pragma unroll
+                    for (int k = 0; k < NW; k++) term[k] = st->term[k][s];
+
+                    for (int e = lane; e < total; e += 32) {
+                        int iz = 0, rem = e;
+                        if (DIM3) {
+                            iz = (int)(((unsigned)e * inv_wxy) >> 20);
+                            rem = e - iz * wxy;
+                        }
+                        const int iy = (int)(((unsigned)rem * inv_wx) >> 16);
+                        const int ix = rem - iy * wx;
+                        const int px = x0 + ix, py = y0 + iy, pz = z0 + iz;
+                        const R dx = int_to_real(px - cx, R(0)) - fx;
+                        const R dy = int_to_real(py - cy, R(0)) - fy;
+                        R q2 = fma(dy * dy, sy, cc);
+                        if (DIM3) {
+                            const R dz = int_to_real(pz - cz, R(0)) - fz;
+                            q2 = fma(dz * dz, sz, q2);
+                        }
+                        q2 = fma(dx * dx, sx, q2);
+                        if (q2 < rad2) {
+                            const R wv = kernel_eval_q2<KIND, R>(q2, lv);
+                            R *a = acc + (pz * PLANE + py * SX + px);
+#pragma unroll
+                            for (int k = 0; k < NW; k++) a[k * ACC] = fma(term[k], wv, a[k * ACC]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- flush the tile segment and clear the accumulator ------------------
+        for (int i = tid; i < TX * TY * TZ; i += kThreads) {
+            const int ix = i % TX, iy = (i / TX) % TY, iz = i / (TX * TY);
+            if (ix < lim_x && iy < lim_y && iz < lim_z) {
+                const int a = iz * PLANE + iy * SX + ix;
+                const size_t o = ((size_t)(oz + iz) * v.ny + (oy + iy)) * v.nx + (ox + ix);
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const R val = acc[k * ACC + a];
+                    if (val != R(0)) {
+                        red_add(outs[k] + o, (double)val);
+                        acc[k * ACC + a] = R(0);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        pos = seg_hi;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Host side.
+
+struct Workspace {
+    unsigned char *base;
+    size_t used;
+    explicit Workspace(void *p) : base(static_cast<unsigned char *>(p)), used(0) {}
+    template <typename U> U *take(size_t count)
+    {
+        used = align_up(used, 256);
+        U *r = reinterpret_cast<U *>(base + used);
+        used += count * sizeof(U);
+        return r;
+    }
+};
+
+template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ>
+static int launch_render(const View &v, const sphb_particles *p, const sphb_kernel *k, const uint32_t *keys,
+                         const uint32_t *vals, const uint32_t *tile_end, int64_t n_pairs,
+                         double *const *out, cudaStream_t stream)
+{
+    using R2 = typename Real2<R>::type;
+    auto kern = render_kernel<T, R, KIND, NW, DIM3, TX, TY, TZ>;
+    size_t smem = sizeof(R) * (size_t)(TX + 8) * TY * TZ * NW + sizeof(Staged<R, NW>);
+    if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
+    if (smem > 227 * 1024) {
+        set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
+        return SPHB_ERR_ARGUMENT;
+    }
+    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = div_up(n_pairs, kChunkPairs);
+    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NW; i++) {
+        w[i] = static_cast<const T *>(p->w[i]);
+        o[i] = out[i];
+    }
+    kern<<<grid, kThreads, smem, stream>>>(v, static_cast<const T *>(p->x), static_cast<const T *>(p->y),
+                                           static_cast<const T *>(p->z), static_cast<const T *>(p->h),
+                                           w[0], w[1], w[2], w[3], k->lut, k->lut_samples, keys, vals,
+                                           tile_end, n_pairs, o[0], o[1], o[2], o[3]);
+    SPHB_LAUNCH_CHECK();
+    return SPHB_OK;
+}
+
+template <typename T, typename R, int KIND, bool DIM3, int TX, int TY, int TZ, typename... A>
+static int dispatch_nw(int nw, A &&...a)
+{
+    switch (nw) {
+    case 1: return launch_render<T, R, KIND, 1, DIM3, TX, TY, TZ>(a...);
+    case 2: return launch_render<T, R, KIND, 2, DIM3, TX, TY, TZ>(a...);
+    case 3: return launch_render<T, R, KIND, 3, DIM3, TX, TY, TZ>(a...);
+    default: return launch_render<T, R, KIND, 4, DIM3, TX, TY, TZ>(a...);
+    }
+}
+
+template <typename T, typename R, bool DIM3, int TX, int TY, int TZ, typename... A>
+static int dispatch_kind(int kind, int nw, A &&...a)
+{
+    switch (kind) {
+    case SPHB_CUBIC: return dispatch_nw<T, R, SPHB_CUBIC, DIM3, TX, TY, TZ>(nw, a...);
+    case SPHB_QUARTIC: return dispatch_nw<T, R, SPHB_QUARTIC, DIM3, TX, TY, TZ>(nw, a...);
+    case SPHB_QUINTIC: return dispatch_nw<T, R, SPHB_QUINTIC, DIM3, TX, TY, TZ>(nw, a...);
+    default: return dispatch_nw<T, R, SPHB_COLUMN_LUT, DIM3, TX, TY, TZ>(nw, a...);
+    }
+}
+
+constexpr int kTile2X = 32, kTile2Y = 32;
+constexpr int kTile3X = 16, kTile3Y = 16, kTile3Z = 8;
+
+static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
+                    int use_z, double *const *out)
+{
+    if (!p || !k || !r || !out) {
+        set_error("null argument");
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (p->n < 0 || p->n > 0xffffffffLL) {
+        set_error("particle count %lld out of range", (long long)p->n);
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (p->dtype != SPHB_F32 && p->dtype != SPHB_F64) {
+        set_error("dtype must be SPHB_F32 or SPHB_F64");
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (p->n_weights < 1 || p->n_weights > SPHB_MAX_WEIGHTS) {
+        set_error("n_weights must be 1..%d", SPHB_MAX_WEIGHTS);
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (p->n > 0 && (!p->x || !p->y || !p->h || ((dim3 || use_z) && !p->z))) {
+        set_error("missing particle column");
+        return SPHB_ERR_ARGUMENT;
+    }
+    for (int i = 0; i < p->n_weights; i++)
+        if (!out[i] || (p->n > 0 && !p->w[i])) {
+            set_error("missing weight or output %d", i);
+            return SPHB_ERR_ARGUMENT;
+        }
+    if (r->nx <= 0 || r->ny <= 0 || (dim3 && r->nz <= 0) || !(r->x_max > r->x_min) ||
+        !(r->y_max > r->y_min) || (dim3 && !(r->z_max > r->z_min))) {
+        set_error("invalid raster");
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (k->kind < SPHB_CUBIC || k->kind > SPHB_COLUMN_LUT || !(k->radius > 0.0)) {
+        set_error("invalid kernel");
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (k->kind == SPHB_COLUMN_LUT && (!k->lut || k->lut_samples < 2)) {
+        set_error("column table needs >= 2 samples");
+        return SPHB_ERR_ARGUMENT;
+    }
+    if (k->ndim != 2 && k->ndim != 3) {
+        set_error("kernel ndim must be 2 or 3");
+        return SPHB_ERR_ARGUMENT;
+    }
+    return SPHB_OK;
+}
+
+template <typename T>
+static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
+                        int use_z, double z_slice, int accumulate, double *const *out, void *ws,
+                        size_t ws_bytes, size_t *ws_needed, sphb_stats *stats, cudaStream_t stream)
+{
+    View v;
+    v.nx = r->nx;
+    v.ny = r->ny;
+    v.nz = dim3 ? r->nz : 1;
+    v.tx = dim3 ? kTile3X : kTile2X;
+    v.ty = dim3 ? kTile3Y : kTile2Y;
+    v.tz = dim3 ? kTile3Z : 1;
+    v.ntx = div_up(v.nx, v.tx);
+    v.nty = div_up(v.ny, v.ty);
+    v.ntz = div_up(v.nz, v.tz);
+    v.x_min = r->x_min;
+    v.y_min = r->y_min;
+    v.z_min = dim3 ? r->z_min : 0.0;
+    v.pwx = (r->x_max - r->x_min) / r->nx;
+    v.pwy = (r->y_max - r->y_min) / r->ny;
+    v.pwz = dim3 ? (r->z_max - r->z_min) / r->nz : 1.0;
+    v.inv_pwx = 1.0 / v.pwx;
+    v.inv_pwy = 1.0 / v.pwy;
+    v.inv_pwz = 1.0 / v.pwz;
+    v.radius = k->radius;
+    v.z_slice = z_slice;
+    v.use_z = use_z;
+    v.dim3 = dim3 ? 1 : 0;
+    v.ndim = k->ndim;
+    v.norm = kernel_norm(k->kind, k->ndim);
+    const int64_t n_tiles = (int64_t)v.ntx * v.nty * v.ntz;
+    if (n_tiles > 0x7fffffffLL) {
+        set_error("raster has too many tiles");
+        return SPHB_ERR_ARGUMENT;
+    }
+    const int64_t n = p->n;
+    const size_t n_out = (size_t)v.nx * v.ny * v.nz;
+
+    if (!accumulate)
+        for (int i = 0; i < p->n_weights; i++)
+            SPHB_CUDA(cudaMemsetAsync(out[i], 0, n_out * sizeof(double), stream));
+    if (stats) {
+        stats->n_pairs = 0;
+        stats->n_culled = n;
+        stats->n_tiles = n_tiles;
+        stats->tile_x = v.tx;
+        stats->tile_y = v.ty;
+        stats->tile_z = v.tz;
+    }
+    if (ws_needed) *ws_needed = 0;
+    if (n == 0) return SPHB_OK;
+
+    // ---- phase A: count and scan ------------------------------------------
+    size_t scan_tmp = 0;
+    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                            n + 1, stream));
+    Workspace a(ws);
+    uint64_t *offsets = a.take<uint64_t>(n + 1); // counts, scanned in place
+    unsigned char *scan_ws = a.take<unsigned char>(scan_tmp);
+    const size_t need_a = align_up(a.used, 256);
+    if (ws_needed) *ws_needed = need_a;
+    if (!ws || ws_bytes < need_a) {
+        set_error("workspace of %zu bytes needed for binning, %zu given", need_a, ws_bytes);
+        return SPHB_ERR_WORKSPACE;
+    }
+    const T *x = static_cast<const T *>(p->x), *y = static_cast<const T *>(p->y);
+    const T *z = static_cast<const T *>(p->z), *h = static_cast<const T *>(p->h);
+    const int blocks = div_up(n + 1, 256);
+    count_tiles_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets);
+    SPHB_LAUNCH_CHECK();
+    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
+    uint64_t total = 0;
+    SPHB_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    SPHB_CUDA(cudaStreamSynchronize(stream));
+    if (stats) stats->n_pairs = (int64_t)total;
+    if (total == 0) return SPHB_OK;
+    if (total > 0x7fffffffULL) {
+        set_error("%llu (particle, tile) pairs exceed 2^31-1: split the particle set",
+                  (unsigned long long)total);
+        if (ws_needed) *ws_needed = 0;
+        return SPHB_ERR_TOO_MANY;
+    }
+    const int64_t n_pairs = (int64_t)total;
+
+    // ---- phase B: emit, sort, segment ------------------------------------
+    int end_bit = 1;
+    while ((1LL << end_bit) < n_tiles) end_bit++;
+    size_t sort_tmp = 0;
+    SPHB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                              (uint32_t *)nullptr, (uint32_t *)nullptr, n_pairs, 0,
+                                              end_bit, stream));
+    uint32_t *keys_a = a.take<uint32_t>(n_pairs);
+    uint32_t *vals_a = a.take<uint32_t>(n_pairs);
+    uint32_t *keys_b = a.take<uint32_t>(n_pairs);
+    uint32_t *vals_b = a.take<uint32_t>(n_pairs);
+    uint32_t *tile_end = a.take<uint32_t>(n_tiles);
+    unsigned char *sort_ws = a.take<unsigned char>(sort_tmp);
+    const size_t need_b = align_up(a.used, 256);
+    if (ws_needed) *ws_needed = need_b;
+    if (ws_bytes < need_b) {
+        set_error("workspace of %zu bytes needed for %lld pairs, %zu given", need_b, (long long)n_pairs,
+                  ws_bytes);
+        return SPHB_ERR_WORKSPACE;
+    }
+    emit_pairs_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets, keys_a, vals_a);
+    SPHB_LAUNCH_CHECK();
+    SPHB_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sort_tmp, keys_a, keys_b, vals_a, vals_b, n_pairs, 0,
+                                              end_bit, stream));
+    tile_end_kernel<<<div_up(n_pairs, 256), 256, 0, stream>>>(keys_b, n_pairs, tile_end);
+    SPHB_LAUNCH_CHECK();
+
+    // ---- phase C: render ---------------------------------------------------
+    const bool f32 = p->dtype == SPHB_F32;
+    int rc;
+    if (dim3) {
+        if (f32)
+            rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z>(
+                k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_pairs, out, stream);
+        else
+            rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z>(
+                k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_pairs, out, stream);
+    } else {
+        if (f32)
+            rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
+                                                                    vals_b, tile_end, n_pairs, out, stream);
+        else
+            rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
+                                                                     vals_b, tile_end, n_pairs, out, stream);
+    }
+    return rc;
+}
+
+} // namespace sphb
+
+using namespace sphb;
+
+extern "C" int sphb_scatter2d(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int use_z,
+                              double z_slice, int accumulate, double *const *out, void *ws, size_t ws_bytes,
+                              size_t *ws_needed, sphb_stats *stats, sphb_stream stream)
+{
+    int rc = validate(p, k, r, false, use_z, out);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (p->dtype == SPHB_F32)
+        return scatter_impl<float>(p, k, r, false, use_z, z_slice, accumulate, out, ws, ws_bytes, ws_needed,
+                                   stats, s);
+    return scatter_impl<double>(p, k, r, false, use_z, z_slice, accumulate, out, ws, ws_bytes, ws_needed,
+                                stats, s);
+}
+
+extern "C" int sphb_scatter3d(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r,
+                              int accumulate, double *const *out, void *ws, size_t ws_bytes,
+                              size_t *ws_needed, sphb_stats *stats, sphb_stream stream)
+{
+    int rc = validate(p, k, r, true, 0, out);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (p->dtype == SPHB_F32)
+        return scatter_impl<float>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, s);
+    return scatter_impl<double>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, s);
+}

@@ -1,0 +1,269 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out.
+
+Thin host code over the C ABI of libsphb200.so (include/sphb200.h).  PyTorch is
+used for device memory, streams and nothing else: every function here hands raw
+device pointers to a hand-written CUDA kernel.  There is no CPU path -- a
+missing library or a non-CUDA tensor raises.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SphbKernel, SphbParticles, SphbRaster, SphbStats
+
+_KIND = {"cubic": _lib.SPHB_CUBIC, "quartic": _lib.SPHB_QUARTIC, "quintic": _lib.SPHB_QUINTIC,
+         "lut": _lib.SPHB_COLUMN_LUT}
+
+# Workspace handling: one growing byte buffer per device.  A call whose bin
+# list would not fit in `max_workspace_fraction` of the free memory is split
+# into particle batches that accumulate into the same output.
+_workspaces = {}
+max_workspace_fraction = 0.6
+last_stats = {}
+
+
+@dataclass
+class Raster:
+    nx: int
+    ny: int
+    x_min: float
+    x_max: float
+    y_min: float
+    y_max: float
+    nz: int = 1
+    z_min: float = 0.0
+    z_max: float = 1.0
+
+    def c(self) -> SphbRaster:
+        return SphbRaster(int(self.nx), int(self.ny), int(self.nz), float(self.x_min), float(self.x_max),
+                          float(self.y_min), float(self.y_max), float(self.z_min), float(self.z_max))
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (sarracen_b200 has no CPU path)")
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = str(device)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            del _workspaces[key]
+            del ws
+        ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def _particles(x, y, z, h, weights: Sequence[torch.Tensor], lo: int = 0, hi: Optional[int] = None):
+    """Pack column tensors (one dtype, contiguous, same device) into the C struct."""
+    cols = [x, y, h] + list(weights) + ([z] if z is not None else [])
+    for i, t in enumerate(cols):
+        _require_cuda(t, f"particle column {i}")
+    dtype, device, n = x.dtype, x.device, x.numel()
+    if dtype not in (torch.float32, torch.float64):
+        raise TypeError("particle columns must be float32 or float64")
+    for t in cols:
+        if t.dtype != dtype or t.device != device or t.numel() != n or not t.is_contiguous() or t.dim() != 1:
+            raise ValueError("particle columns must be contiguous 1-D tensors of one dtype, length and device")
+    if not 1 <= len(weights) <= _lib.SPHB_MAX_WEIGHTS:
+        raise ValueError(f"1..{_lib.SPHB_MAX_WEIGHTS} weight columns are supported per call")
+    hi = n if hi is None else hi
+    item = x.element_size()
+    p = SphbParticles()
+    p.n = hi - lo
+    p.dtype = _lib.SPHB_F64 if dtype == torch.float64 else _lib.SPHB_F32
+    p.x = x.data_ptr() + lo * item
+    p.y = y.data_ptr() + lo * item
+    p.z = (z.data_ptr() + lo * item) if z is not None else None
+    p.h = h.data_ptr() + lo * item
+    p.n_weights = len(weights)
+    for i, w in enumerate(weights):
+        p.w[i] = w.data_ptr() + lo * item
+    return p
+
+
+def _kernel(weight_function, radius: float, ndim: int, device):
+    kind = getattr(weight_function, "kind", None)
+    if kind not in _KIND:
+        raise TypeError("weight_function must be a sarracen_b200.kernels.WeightFunction "
+                        "(or a Sarracen kernel function resolved by sarracen_b200.backend)")
+    k = SphbKernel()
+    k.kind = _KIND[kind]
+    k.ndim = int(ndim)
+    k.radius = float(radius)
+    keep = None
+    if kind == "lut":
+        keep = weight_function.lut_on(device)
+        k.lut = keep.data_ptr()
+        k.lut_samples = keep.numel()
+        k.ndim = 2
+    return k, keep
+
+
+def _out_ptrs(outs: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * len(outs))()
+    for i, o in enumerate(outs):
+        arr[i] = o.data_ptr()
+    return arr
+
+
+def column_kernel(kind: str, samples: int, device=None) -> torch.Tensor:
+    """A4: column-integrated kernel table on the device (base_kernel.py:39-66)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty(int(samples), dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().sphb_column_kernel(_KIND[kind], int(samples), ctypes.c_void_p(out.data_ptr()),
+                                                  _stream(device)))
+    return out
+
+
+def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, raster: Raster, use_z=False,
+             z_slice=0.0, out: Optional[List[torch.Tensor]] = None, accumulate=False) -> List[torch.Tensor]:
+    lib = _lib.load()
+    device = x.device
+    n = x.numel()
+    shape = (raster.nz, raster.ny, raster.nx) if dim3 else (raster.ny, raster.nx)
+    if out is None:
+        out = [torch.empty(shape, dtype=torch.float64, device=device) for _ in weights]
+        accumulate = False
+    for o in out:
+        _require_cuda(o, "output")
+        if o.dtype != torch.float64 or tuple(o.shape) != shape or not o.is_contiguous():
+            raise ValueError(f"outputs must be contiguous float64 tensors of shape {shape}")
+    kern, _keep = _kernel(weight_function, radius, ndim, device)
+    rast = raster.c()
+    optr = _out_ptrs(out)
+    stats = SphbStats()
+    total_pairs = 0
+    with torch.cuda.device(device):
+        stream = _stream(device)
+        free, _total = torch.cuda.mem_get_info(device)
+        held = _workspaces[str(device)].numel() if str(device) in _workspaces else 0
+        budget = int((free + held) * max_workspace_fraction)
+        todo = [(0, n)]
+        done_any = False
+        while todo:
+            lo, hi = todo.pop()
+            part = _particles(x, y, z, h, weights, lo, hi)
+            # the first batch clears the outputs (inside the library), later ones add to them
+            acc = 1 if (accumulate or done_any) else 0
+            need = ctypes.c_size_t(0)
+            ws = _workspaces.get(str(device))
+            while True:
+                wptr = ctypes.c_void_p(ws.data_ptr()) if ws is not None else None
+                wlen = ws.numel() if ws is not None else 0
+                if dim3:
+                    rc = lib.sphb_scatter3d(ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast), acc, optr,
+                                            wptr, wlen, ctypes.byref(need), ctypes.byref(stats), stream)
+                else:
+                    rc = lib.sphb_scatter2d(ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast),
+                                            1 if use_z else 0, float(z_slice), acc, optr, wptr, wlen,
+                                            ctypes.byref(need), ctypes.byref(stats), stream)
+                if rc == _lib.SPHB_ERR_WORKSPACE and need.value <= budget:
+                    ws = None  # drop our reference so the old buffer is freed before growing
+                    ws = _workspace(device, need.value)
+                    continue
+                break
+            if rc in (_lib.SPHB_ERR_WORKSPACE, _lib.SPHB_ERR_TOO_MANY) and hi - lo > 1:
+                mid = (lo + hi) // 2  # bin list too large for this device: halve the batch
+                todo.append((mid, hi))
+                todo.append((lo, mid))
+                continue
+            _lib.check(rc)
+            done_any = True
+            total_pairs += stats.n_pairs
+    last_stats.clear()
+    last_stats.update(n_pairs=int(total_pairs), n_tiles=int(stats.n_tiles),
+                      tile=(int(stats.tile_x), int(stats.tile_y), int(stats.tile_z)))
+    return out
+
+
+def scatter2d(x, y, h, weights, weight_function, radius, ndim, raster: Raster, z=None, z_slice=None,
+              out=None, accumulate=False) -> List[torch.Tensor]:
+    """B3: sampled scatter onto an image (cpu_backend.py:226-313).
+
+    z/z_slice given -> cross-section (cull |z_slice - z| >= R h, distance
+    includes dz); omitted -> 2-D render or column projection.  One pass
+    accumulates every weight column.  Returns float64 (ny, nx) tensors.
+    """
+    use_z = z is not None and z_slice is not None
+    return _scatter(False, x, y, z if use_z else None, h, weights, weight_function, radius, ndim, raster,
+                    use_z, 0.0 if z_slice is None else z_slice, out, accumulate)
+
+
+def scatter3d(x, y, z, h, weights, weight_function, radius, raster: Raster, out=None,
+              accumulate=False) -> List[torch.Tensor]:
+    """B2/B3: sampled scatter onto a voxel grid in one pass (cpu_backend.py:193-220)."""
+    return _scatter(True, x, y, z, h, weights, weight_function, radius, 3, raster, False, 0.0, out, accumulate)
+
+
+def line2d(x, y, h, weights, weight_function, radius, pixels, x1, x2, y1, y2) -> List[torch.Tensor]:
+    """B6: line cut through 2-D data (cpu_backend.py:450-538)."""
+    device = x.device
+    out = [torch.empty(int(pixels), dtype=torch.float64, device=device) for _ in weights]
+    kern, _keep = _kernel(weight_function, radius, 2, device)
+    part = _particles(x, y, None, h, weights)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().sphb_line2d(ctypes.byref(part), ctypes.byref(kern), int(pixels), float(x1), float(x2),
+                                           float(y1), float(y2), 0, _out_ptrs(out), _stream(device)))
+    return out
+
+
+def line3d(x, y, z, h, weights, weight_function, radius, pixels, x1, x2, y1, y2, z1, z2) -> List[torch.Tensor]:
+    """B7: line cut through 3-D data (cpu_backend.py:540-609)."""
+    device = x.device
+    out = [torch.empty(int(pixels), dtype=torch.float64, device=device) for _ in weights]
+    kern, _keep = _kernel(weight_function, radius, 3, device)
+    part = _particles(x, y, z, h, weights)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().sphb_line3d(ctypes.byref(part), ctypes.byref(kern), int(pixels), float(x1), float(x2),
+                                           float(y1), float(y2), float(z1), float(z2), 0, _out_ptrs(out),
+                                           _stream(device)))
+    return out
+
+
+def _exact(fn_name, x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
+    device = x.device
+    out = [torch.empty((raster.ny, raster.nx), dtype=torch.float64, device=device) for _ in weights]
+    part = _particles(x, y, None, h, weights)
+    rast = raster.c()
+    with torch.cuda.device(device):
+        fn = getattr(_lib.load(), fn_name)
+        _lib.check(fn(ctypes.byref(part), ctypes.byref(rast), 0, _out_ptrs(out), _stream(device)))
+    return out
+
+
+def exact2d(x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
+    """B4: exact pixel integrals of the 2-D cubic spline (cpu_backend.py:317-447)."""
+    return _exact("sphb_exact2d", x, y, h, weights, raster)
+
+
+def exact3d_proj(x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
+    """B5: exact column integrals of the 3-D cubic spline (cpu_backend.py:611-720)."""
+    return _exact("sphb_exact3d_proj", x, y, h, weights, raster)
+
+
+def normalize_(num: torch.Tensor, den: torch.Tensor) -> torch.Tensor:
+    """N5: num <- nan_to_num(num / den) in place on the device (interpolate.py:594)."""
+    _require_cuda(num, "num")
+    _require_cuda(den, "den")
+    if num.dtype != torch.float64 or den.dtype != torch.float64 or num.shape != den.shape \
+            or not num.is_contiguous() or not den.is_contiguous():
+        raise ValueError("normalize_ needs contiguous float64 tensors of one shape")
+    with torch.cuda.device(num.device):
+        _lib.check(_lib.load().sphb_normalize(ctypes.c_void_p(num.data_ptr()), ctypes.c_void_p(den.data_ptr()),
+                                              num.numel(), _stream(num.device)))
+    return num

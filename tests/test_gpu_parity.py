@@ -1,0 +1,233 @@
+"""Parity of the CUDA path (through the C ABI) with the reference.
+
+Every test calls `B200Backend` -- ctypes -> libsphb200.so -> sm_100a kernels --
+and compares with (a) the committed golden outputs of the unmodified reference
+CPU backend and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): relative L2 and max error of 1e-10 for
+float64 inputs and 1e-5 for float32 inputs (the reference given the same
+float32 arrays), per function.
+"""
+import numpy as np
+import pytest
+from conftest import assert_parity, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-10
+TOL32 = 1e-5
+KINDS = ["cubic", "quartic", "quintic"]
+
+
+@pytest.fixture(scope="module")
+def B():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device")
+    from sarracen_b200 import B200Backend
+    return B200Backend
+
+
+def _kernel(kind):
+    import sarracen_b200 as s
+    return {"cubic": s.CubicSplineKernel, "quartic": s.QuarticSplineKernel,
+            "quintic": s.QuinticSplineKernel}[kind]()
+
+
+def test_library_is_loaded():
+    from sarracen_b200 import _lib
+    assert _lib.load().sphb_version() == 100
+
+
+def test_column_table_on_device():
+    g = load_golden("kernels")
+    for kind in KINDS:
+        for s in (1000, 64, 2):
+            tab = _kernel(kind).get_column_kernel(s)
+            np.testing.assert_allclose(tab, g[f"column_{kind}_{s}"], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_sampled_paths_float64(B, kind):
+    g = load_golden("sampled")
+    x, y, z, h, w = (g[k] for k in "xyzhw")
+    nx, ny, lim, zs = int(g["nx"]), int(g["ny"]), g["lim"], float(g["z_slice"])
+    k = _kernel(kind)
+    R = k.get_radius()
+    out = B.interpolate_2d_render(x, y, w, h, k.w, R, nx, ny, *lim, False)
+    assert_parity(out, g[f"render2d_{kind}"], TOL64, "render2d")
+    out = B.interpolate_3d_cross(x, y, z, zs, w, h, k.w, R, nx, ny, *lim)
+    assert_parity(out, g[f"cross_{kind}"], TOL64, "cross")
+    out = B.interpolate_3d_projection(x, y, w, h, k.get_column_kernel_func(1000), R, nx, ny, *lim, False)
+    assert_parity(out, g[f"proj_{kind}"], TOL64, "proj")
+
+
+def test_vec_paths_share_one_walk(B):
+    g = load_golden("sampled")
+    x, y, z, h, w, w2 = (g[k] for k in ("x", "y", "z", "h", "w", "w2"))
+    nx, ny, lim, zs = int(g["nx"]), int(g["ny"]), g["lim"], float(g["z_slice"])
+    k = _kernel("cubic")
+    a, b = B.interpolate_3d_projection_vec(x, y, w, w2, h, k.get_column_kernel_func(1000), 2, nx, ny, *lim,
+                                           False)
+    assert_parity(a, g["projvec_a"], TOL64)
+    assert_parity(b, g["projvec_b"], TOL64)
+    a, b = B.interpolate_3d_cross_vec(x, y, z, zs, w, w2, h, k.w, 2, nx, ny, *lim)
+    assert_parity(a, g["crossvec_a"], TOL64)
+    assert_parity(b, g["crossvec_b"], TOL64)
+    a, b = B.interpolate_2d_render_vec(x, y, w, w2, h, k.w, 2, nx, ny, *lim, False)
+    assert_parity(a, g["render2dvec_a"], TOL64)
+    assert_parity(b, g["render2dvec_b"], TOL64)
+
+
+def test_sampled_paths_float32(B):
+    g = load_golden("sampled")
+    x, y, z, h, w = (g[k].astype(np.float32) for k in "xyzhw")
+    nx, ny, lim, zs = int(g["nx"]), int(g["ny"]), g["lim"], float(np.float32(g["z_slice"]))
+    out = B.interpolate_2d_render(x, y, w, h, _kernel("cubic").w, 2, nx, ny, *lim, False)
+    assert_parity(out, g["render2d_cubic_f32"], TOL32, "render2d f32")
+    out = B.interpolate_3d_cross(x, y, z, zs, w, h, _kernel("cubic").w, 2, nx, ny, *lim)
+    assert_parity(out, g["cross_cubic_f32"], TOL32, "cross f32")
+    out = B.interpolate_3d_projection(x, y, w, h, _kernel("quintic").get_column_kernel_func(1000), 3, nx, ny,
+                                      *lim, False)
+    assert_parity(out, g["proj_quintic_f32"], TOL32, "proj f32")
+
+
+def test_small_smoothing_lengths(B):
+    g = load_golden("small_h")
+    out = B.interpolate_2d_render(g["x"], g["y"], g["w"], g["h"], _kernel("cubic").w, 2, int(g["nx"]),
+                                  int(g["ny"]), 0.0, 1.0, 0.0, 1.0, False)
+    assert_parity(out, g["render2d_cubic"], TOL64)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_grid(B, kind):
+    g = load_golden("grid")
+    k = _kernel(kind)
+    out = B.interpolate_3d_grid(g["x"], g["y"], g["z"], g["w"], g["h"], k.w, k.get_radius(), int(g["nx"]),
+                                int(g["ny"]), int(g["nz"]), *g["lim"])
+    assert_parity(out, g[f"grid_{kind}"], TOL64)
+    out = B.interpolate_3d_grid(*(g[c].astype(np.float32) for c in "xyzwh"), k.w, k.get_radius(),
+                                int(g["nx"]), int(g["ny"]), int(g["nz"]), *g["lim"])
+    assert_parity(out, g[f"grid_{kind}"], TOL32, "grid f32")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_lines(B, kind):
+    g = load_golden("lines")
+    x, y, z, h, w = (g[k] for k in "xyzhw")
+    px = int(g["pixels"])
+    k = _kernel(kind)
+    for i, c in enumerate(g["cuts2"]):
+        out = B.interpolate_2d_line(x, y, w, h, k.w, k.get_radius(), px, *c)
+        assert_parity(out, g[f"line2d_{kind}_{i}"], TOL64, f"line2d {i}")
+    for i, c in enumerate(g["cuts3"]):
+        out = B.interpolate_3d_line(x, y, z, w, h, k.w, k.get_radius(), px, *c)
+        assert_parity(out, g[f"line3d_{kind}_{i}"], TOL64, f"line3d {i}")
+
+
+def test_exact_paths(B):
+    g = load_golden("exact")
+    x, y, h, w = (g[k] for k in "xyhw")
+    nx, ny, lim = int(g["nx"]), int(g["ny"]), g["lim"]
+    k = _kernel("cubic")
+    out = B.interpolate_2d_render(x, y, w, h, k.w, 2, nx, ny, *lim, True)
+    assert_parity(out, g["exact2d"], TOL64, "exact2d")
+    out = B.interpolate_3d_projection(x, y, w, h, k.w, 2, nx, ny, *lim, True)
+    assert_parity(out, g["exact3dproj"], TOL64, "exact3dproj")
+
+
+# ---- larger seeded cases against the oracle (sizes it finishes in seconds) ----
+
+def _plummer(rng, n, a=1.0, rmax=10.0):
+    u = rng.uniform(0, (1 + a * a / rmax ** 2) ** -1.5, n)
+    r = a / np.sqrt(u ** (-2 / 3) - 1)
+    ct = rng.uniform(-1, 1, n)
+    ph = rng.uniform(0, 2 * np.pi, n)
+    st = np.sqrt(1 - ct * ct)
+    rho = 3 / (4 * np.pi * a ** 3) * (1 + r * r / (a * a)) ** -2.5
+    h = 1.2 * ((1.0 / n) / rho) ** (1 / 3)
+    return r * st * np.cos(ph), r * st * np.sin(ph), r * ct, h, rho
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_projection_plummer_vs_oracle(B, dtype, tol):
+    """BASELINE config 2 at reduced N: Plummer sphere, quintic column table."""
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(1002)
+    n = 20000
+    x, y, z, h, rho = _plummer(rng, n)
+    w = rng.uniform(0, 1, n) * (1.0 / n) / rho
+    x, y, h, w = (a.astype(dtype) for a in (x, y, h, w))
+    nx = ny = 256
+    lim = (-2.0, 2.0, -2.0, 2.0)
+    k = _kernel("quintic")
+    out = B.interpolate_3d_projection(x, y, w, h, k.get_column_kernel_func(1000), 3, nx, ny, *lim, False)
+    ref = OracleBackend.interpolate_3d_projection(x, y, w, h, OracleKernel.column("quintic", 1000), 3, nx, ny,
+                                                  *lim, False)
+    assert_parity(out, ref, tol, "plummer projection")
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_grid_uniform_vs_oracle(B, dtype, tol):
+    """BASELINE config 4 at reduced N (same 2h / voxel = 2.44)."""
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(1004)
+    n = 1 << 15
+    x, y, z = rng.uniform(0, 1, (3, n))
+    h = np.full(n, 1.2 * n ** (-1 / 3))
+    w = rng.uniform(0, 1, n) / n
+    x, y, z, h, w = (a.astype(dtype) for a in (x, y, z, h, w))
+    m = 32
+    k = _kernel("cubic")
+    out = B.interpolate_3d_grid(x, y, z, w, h, k.w, 2, m, m, m, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+    ref = OracleBackend.interpolate_3d_grid(x, y, z, w, h, OracleKernel("cubic"), 2, m, m, m, 0.0, 1.0, 0.0, 1.0,
+                                            0.0, 1.0)
+    assert_parity(out, ref, tol, "uniform grid")
+
+
+def test_single_particle_every_function(B):
+    """After sarracen/tests/interpolate/test_interpolate.py:36-147: one particle,
+    every pixel equals w / h^d * W(r / h)."""
+    from oracle import OracleKernel, kernel_w
+    k = _kernel("cubic")
+    x, y, z = np.array([0.0]), np.array([0.0]), np.array([0.0])
+    h, w = np.array([0.9]), np.array([0.35])
+    n = 25
+    lim = (-1.0, 1.0, -1.0, 1.0)
+    c = -1.0 + (np.arange(n) + 0.5) * (2.0 / n)
+    r2 = c[None, :] ** 2 + c[:, None] ** 2
+    img = B.interpolate_2d_render(x, y, w, h, k.w, 2, n, n, *lim, False)
+    exp = np.vectorize(lambda q: kernel_w("cubic", q, 2))(np.sqrt(r2) / 0.9) * 0.35 / 0.9 ** 2
+    np.testing.assert_allclose(img, exp, rtol=1e-12, atol=1e-15)
+    col = OracleKernel.column("cubic", 1000)
+    img = B.interpolate_3d_projection(x, y, w, h, k.get_column_kernel_func(1000), 2, n, n, *lim, False)
+    exp = np.vectorize(lambda q: col(q, 3))(np.sqrt(r2) / 0.9) * 0.35 / 0.9 ** 2
+    np.testing.assert_allclose(img, exp, rtol=1e-11, atol=1e-15)
+    img = B.interpolate_3d_cross(x, y, z, 0.0, w, h, k.w, 2, n, n, *lim)
+    exp = np.vectorize(lambda q: kernel_w("cubic", q, 3))(np.sqrt(r2) / 0.9) * 0.35 / 0.9 ** 3
+    np.testing.assert_allclose(img, exp, rtol=1e-12, atol=1e-15)
+    grid = B.interpolate_3d_grid(x, y, z, w, h, k.w, 2, n, n, n, *lim, -1.0, 1.0)
+    r3 = np.sqrt(r2[None, :, :] + c[:, None, None] ** 2)
+    exp = np.vectorize(lambda q: kernel_w("cubic", q, 3))(r3 / 0.9) * 0.35 / 0.9 ** 3
+    np.testing.assert_allclose(grid, exp, rtol=1e-12, atol=1e-15)
+
+
+def test_repeated_particle_has_no_races(B):
+    """After test_interpolate.py:150-270: the same particle 10 000 times."""
+    k = _kernel("quintic")
+    n = 10000
+    x, y = np.zeros(n), np.zeros(n)
+    h, w = np.full(n, 0.7), np.full(n, 1e-4)
+    one = B.interpolate_2d_render(x[:1], y[:1], w[:1], h[:1], k.w, 3, 31, 29, -1, 1, -1, 1, False)
+    many = B.interpolate_2d_render(x, y, w, h, k.w, 3, 31, 29, -1, 1, -1, 1, False)
+    np.testing.assert_allclose(many, one * n, rtol=1e-11)
+
+
+def test_empty_and_out_of_view(B):
+    k = _kernel("cubic")
+    e = np.zeros(0)
+    assert not B.interpolate_2d_render(e, e, e, e, k.w, 2, 8, 6, 0, 1, 0, 1, False).any()
+    assert B.interpolate_3d_grid(e, e, e, e, e, k.w, 2, 4, 5, 6, 0, 1, 0, 1, 0, 1).shape == (6, 5, 4)
+    far = np.array([50.0])
+    img = B.interpolate_2d_render(far, far, np.ones(1), np.array([0.1]), k.w, 2, 8, 6, 0, 1, 0, 1, False)
+    assert img.shape == (6, 8) and not img.any()
