@@ -92,10 +92,15 @@ typedef struct sphb_raster {
 
 /* Optional counters filled by the scatter calls (host memory). */
 typedef struct sphb_stats {
-    int64_t n_pairs;      /* (particle, tile) pairs binned and sorted */
-    int64_t n_culled;     /* particles that touch no pixel */
-    int64_t n_tiles;      /* tiles in the raster */
-    int32_t tile_x, tile_y, tile_z;
+    int64_t n_pairs;      /* out: (particle, tile) pairs binned and sorted */
+    int64_t n_tiles;      /* out: tiles in the raster */
+    int32_t tile_x, tile_y, tile_z; /* out: tile size in pixels */
+    int32_t time_phases;  /* in: non-zero -> bracket the phases with CUDA events on `stream`
+                             and synchronise at the end of the call to read them */
+    float ms_bin;         /* out: count + scan + emit kernels */
+    float ms_sort;        /* out: radix sort + segment boundaries */
+    float ms_render;      /* out: the tile render kernel alone */
+    int32_t launches;     /* out: kernels of this library launched by the call (CUB's not counted) */
 } sphb_stats;
 
 int sphb_version(void);
@@ -145,6 +150,13 @@ int sphb_exact2d(const sphb_particles *p, const sphb_raster *r, int accumulate, 
  * sarracen/kernels/cubic_spline_exact.py:220-483.  Float64 only. */
 int sphb_exact3d_proj(const sphb_particles *p, const sphb_raster *r, int accumulate,
                       double *const *out, sphb_stream stream);
+
+/* Measurement aid: the number of (particle, pixel) pairs for which
+ * the reference evaluates the weight function and accumulates, i.e. pixel
+ * centres with q <= R.  nz > 1 counts voxels.  out: device uint64 (one value,
+ * overwritten). */
+int sphb_count_contributions(const sphb_particles *p, double radius, const sphb_raster *r, int use_z,
+                             double z_slice, unsigned long long *out, sphb_stream stream);
 
 /* N5 -- out = nan_to_num(num / den) elementwise on the device
  * (interpolate.py:594): 0/0 -> 0, +-inf -> +-DBL_MAX. */

@@ -15,7 +15,8 @@ SPHB_CUBIC, SPHB_QUARTIC, SPHB_QUINTIC, SPHB_COLUMN_LUT = 0, 1, 2, 3
 SPHB_OK, SPHB_ERR_ARGUMENT, SPHB_ERR_WORKSPACE, SPHB_ERR_CUDA, SPHB_ERR_TOO_MANY = 0, -1, -2, -3, -4
 
 EXPORTS = ["sphb_version", "sphb_last_error", "sphb_column_kernel", "sphb_scatter2d", "sphb_scatter3d",
-           "sphb_line2d", "sphb_line3d", "sphb_exact2d", "sphb_exact3d_proj", "sphb_normalize"]
+           "sphb_line2d", "sphb_line3d", "sphb_exact2d", "sphb_exact3d_proj", "sphb_normalize",
+           "sphb_count_contributions"]
 
 
 class SphbParticles(ctypes.Structure):
@@ -38,8 +39,10 @@ class SphbRaster(ctypes.Structure):
 
 
 class SphbStats(ctypes.Structure):
-    _fields_ = [("n_pairs", ctypes.c_int64), ("n_culled", ctypes.c_int64), ("n_tiles", ctypes.c_int64),
-                ("tile_x", ctypes.c_int32), ("tile_y", ctypes.c_int32), ("tile_z", ctypes.c_int32)]
+    _fields_ = [("n_pairs", ctypes.c_int64), ("n_tiles", ctypes.c_int64),
+                ("tile_x", ctypes.c_int32), ("tile_y", ctypes.c_int32), ("tile_z", ctypes.c_int32),
+                ("time_phases", ctypes.c_int32), ("ms_bin", ctypes.c_float), ("ms_sort", ctypes.c_float),
+                ("ms_render", ctypes.c_float), ("launches", ctypes.c_int32)]
 
 
 class SphbError(RuntimeError):
@@ -78,6 +81,7 @@ def load():
     lib.sphb_exact2d.argtypes = [P, R, c_int, outs, c_vp]
     lib.sphb_exact3d_proj.argtypes = [P, R, c_int, outs, c_vp]
     lib.sphb_normalize.argtypes = [c_vp, c_vp, ctypes.c_int64, c_vp]
+    lib.sphb_count_contributions.argtypes = [P, c_dbl, R, c_int, c_dbl, c_vp, c_vp]
     for name in EXPORTS:
         if name != "sphb_last_error":
             getattr(lib, name).restype = c_int

@@ -106,22 +106,25 @@ template <int KIND, typename R> __device__ __forceinline__ R kernel_shape(R q)
     }
 }
 
-// floor(t) for 0 <= t < 2^22 without the conversion pipe: adding 2^52 (2^23)
-// leaves rint(t - 1/2) in the low mantissa bits.  When t is an exact integer
-// the index may come out one lower with f = 1, which evaluates to the same
-// table value.
+// floor(t) for 0 <= t < 2^22 without the conversion pipe: adding 1.5 * 2^52
+// (1.5 * 2^23) leaves rint(t - 1/2) in the low mantissa bits.  The 1.5 keeps
+// the sum inside one binade (unit spacing) even when t - 1/2 is negative.
+// When t is an exact integer the index may come out one lower with f = 1,
+// which evaluates to the same table value.
 __device__ __forceinline__ int floor_nonneg(double t, double &f)
 {
-    double m = (t - 0.5) + 4503599627370496.0;
+    const double magic = 6755399441055744.0;
+    double m = (t - 0.5) + magic;
     int i = __double2loint(m);
-    f = t - (m - 4503599627370496.0);
+    f = t - (m - magic);
     return i;
 }
 __device__ __forceinline__ int floor_nonneg(float t, float &f)
 {
-    float m = (t - 0.5f) + 8388608.0f;
-    int i = __float_as_int(m) & 0x7fffff;
-    f = t - (m - 8388608.0f);
+    const float magic = 12582912.0f;
+    float m = (t - 0.5f) + magic;
+    int i = __float_as_int(m) & 0x3fffff;
+    f = t - (m - magic);
     return i;
 }
 

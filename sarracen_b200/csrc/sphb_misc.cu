@@ -268,6 +268,69 @@ static int line_impl(const sphb_particles *p, const sphb_kernel *k, bool dim3, i
 }
 
 // ---------------------------------------------------------------------------
+// Measurement aid: exact number of pixel centres with q <= R, summed over the
+// particles.  One thread per particle walks the rows of its support box and
+// counts the centres inside the row's chord.
+struct CountView {
+    int nx, ny, nz;
+    double x_min, y_min, z_min, pwx, pwy, pwz, radius, z_slice;
+    int use_z, dim3;
+};
+
+__device__ __forceinline__ void centre_range(double c, double rad, double origin, double pw, int n, int &lo,
+                                             int &hi)
+{
+    lo = (int)fmin(fmax(ceil((c - rad - origin) / pw - 0.5), 0.0), (double)n);
+    hi = (int)fmin(fmax(floor((c + rad - origin) / pw - 0.5) + 1.0, 0.0), (double)n);
+}
+
+template <typename T>
+__global__ void count_contributions_kernel(CountView v, const T *x, const T *y, const T *z, const T *h,
+                                           int64_t n, unsigned long long *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (i < n) {
+        const double hp = (double)h[i], xp = (double)x[i], yp = (double)y[i];
+        const double rad = v.radius * hp;
+        if (hp > 0.0 && isfinite(hp) && isfinite(xp) && isfinite(yp)) {
+            double r2 = rad * rad;
+            int k0 = 0, k1 = 1;
+            double zp = 0.0;
+            bool ok = true;
+            if (v.dim3) {
+                zp = (double)z[i];
+                centre_range(zp, rad, v.z_min, v.pwz, v.nz, k0, k1);
+            } else if (v.use_z) {
+                const double dz = v.z_slice - (double)z[i];
+                ok = fabs(dz) < rad;
+                r2 -= dz * dz;
+            }
+            for (int k = k0; ok && k < k1; k++) {
+                double rr = r2;
+                if (v.dim3) {
+                    const double dz = v.z_min + (k + 0.5) * v.pwz - zp;
+                    rr -= dz * dz;
+                }
+                if (rr < 0.0) continue;
+                int j0, j1;
+                centre_range(yp, sqrt(rr), v.y_min, v.pwy, v.ny, j0, j1);
+                for (int j = j0; j < j1; j++) {
+                    const double dy = v.y_min + (j + 0.5) * v.pwy - yp;
+                    const double rx = rr - dy * dy;
+                    if (rx < 0.0) continue;
+                    int i0, i1;
+                    centre_range(xp, sqrt(rx), v.x_min, v.pwx, v.nx, i0, i1);
+                    if (i1 > i0) c += (unsigned long long)(i1 - i0);
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// ---------------------------------------------------------------------------
 // N5: num <- nan_to_num(num / den)   (interpolate.py:594)
 __global__ void normalize_kernel(double *num, const double *den, int64_t n)
 {
@@ -320,6 +383,44 @@ extern "C" int sphb_line3d(const sphb_particles *p, const sphb_kernel *k, int pi
 {
     return line_impl(p, k, true, pixels, x1, x2, y1, y2, z1, z2, accumulate, out,
                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sphb_count_contributions(const sphb_particles *p, double radius, const sphb_raster *r, int use_z,
+                                        double z_slice, unsigned long long *out, sphb_stream stream)
+{
+    if (!p || !r || !out || p->n < 0 || (p->dtype != SPHB_F32 && p->dtype != SPHB_F64) || r->nx <= 0 ||
+        r->ny <= 0 || r->nz <= 0 || !(radius > 0.0)) {
+        set_error("invalid argument to count_contributions");
+        return SPHB_ERR_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SPHB_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long), s));
+    if (p->n == 0) return SPHB_OK;
+    CountView v;
+    v.nx = r->nx; v.ny = r->ny; v.nz = r->nz;
+    v.x_min = r->x_min; v.y_min = r->y_min; v.z_min = r->z_min;
+    v.pwx = (r->x_max - r->x_min) / r->nx;
+    v.pwy = (r->y_max - r->y_min) / r->ny;
+    v.pwz = r->nz > 1 ? (r->z_max - r->z_min) / r->nz : 1.0;
+    v.radius = radius;
+    v.z_slice = z_slice;
+    v.use_z = use_z;
+    v.dim3 = r->nz > 1;
+    if ((v.dim3 || use_z) && !p->z) {
+        set_error("missing z column");
+        return SPHB_ERR_ARGUMENT;
+    }
+    const int grid = div_up(p->n, 256);
+    if (p->dtype == SPHB_F32)
+        count_contributions_kernel<float><<<grid, 256, 0, s>>>(
+            v, static_cast<const float *>(p->x), static_cast<const float *>(p->y),
+            static_cast<const float *>(p->z), static_cast<const float *>(p->h), p->n, out);
+    else
+        count_contributions_kernel<double><<<grid, 256, 0, s>>>(
+            v, static_cast<const double *>(p->x), static_cast<const double *>(p->y),
+            static_cast<const double *>(p->z), static_cast<const double *>(p->h), p->n, out);
+    SPHB_LAUNCH_CHECK();
+    return SPHB_OK;
 }
 
 extern "C" int sphb_normalize(double *num, const double *den, int64_t n, sphb_stream stream)

@@ -533,14 +533,27 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     if (!accumulate)
         for (int i = 0; i < p->n_weights; i++)
             SPHB_CUDA(cudaMemsetAsync(out[i], 0, n_out * sizeof(double), stream));
+    const bool timed = stats && stats->time_phases;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (stats) {
         stats->n_pairs = 0;
-        stats->n_culled = n;
         stats->n_tiles = n_tiles;
         stats->tile_x = v.tx;
         stats->tile_y = v.ty;
         stats->tile_z = v.tz;
+        stats->ms_bin = stats->ms_sort = stats->ms_render = 0.f;
+        stats->launches = 0;
     }
+    struct EventGuard {
+        cudaEvent_t *e;
+        ~EventGuard()
+        {
+            for (int i = 0; i < 4; i++)
+                if (e[i]) cudaEventDestroy(e[i]);
+        }
+    } guard{ev};
+    if (timed)
+        for (int i = 0; i < 4; i++) SPHB_CUDA(cudaEventCreate(&ev[i]));
     if (ws_needed) *ws_needed = 0;
     if (n == 0) return SPHB_OK;
 
@@ -560,6 +573,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     const T *x = static_cast<const T *>(p->x), *y = static_cast<const T *>(p->y);
     const T *z = static_cast<const T *>(p->z), *h = static_cast<const T *>(p->h);
     const int blocks = div_up(n + 1, 256);
+    if (timed) SPHB_CUDA(cudaEventRecord(ev[0], stream));
     count_tiles_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets);
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
@@ -598,12 +612,14 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     }
     emit_pairs_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets, keys_a, vals_a);
     SPHB_LAUNCH_CHECK();
+    if (timed) SPHB_CUDA(cudaEventRecord(ev[1], stream));
     SPHB_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sort_tmp, keys_a, keys_b, vals_a, vals_b, n_pairs, 0,
                                               end_bit, stream));
     tile_end_kernel<<<div_up(n_pairs, 256), 256, 0, stream>>>(keys_b, n_pairs, tile_end);
     SPHB_LAUNCH_CHECK();
 
     // ---- phase C: render ---------------------------------------------------
+    if (timed) SPHB_CUDA(cudaEventRecord(ev[2], stream));
     const bool f32 = p->dtype == SPHB_F32;
     int rc;
     if (dim3) {
@@ -621,7 +637,16 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
             rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
                                                                      vals_b, tile_end, n_pairs, out, stream);
     }
-    return rc;
+    if (rc) return rc;
+    if (stats) stats->launches = 4; // count, emit, tile_end, render
+    if (timed) {
+        SPHB_CUDA(cudaEventRecord(ev[3], stream));
+        SPHB_CUDA(cudaEventSynchronize(ev[3]));
+        SPHB_CUDA(cudaEventElapsedTime(&stats->ms_bin, ev[0], ev[1]));
+        SPHB_CUDA(cudaEventElapsedTime(&stats->ms_sort, ev[1], ev[2]));
+        SPHB_CUDA(cudaEventElapsedTime(&stats->ms_render, ev[2], ev[3]));
+    }
+    return SPHB_OK;
 }
 
 } // namespace sphb

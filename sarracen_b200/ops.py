@@ -23,6 +23,7 @@ _KIND = {"cubic": _lib.SPHB_CUBIC, "quartic": _lib.SPHB_QUARTIC, "quintic": _lib
 _workspaces = {}
 max_workspace_fraction = 0.6
 last_stats = {}
+time_phases = False  # bench/profiling: bracket the pipeline phases with CUDA events (adds a sync)
 
 
 @dataclass
@@ -147,7 +148,10 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
     rast = raster.c()
     optr = _out_ptrs(out)
     stats = SphbStats()
+    stats.time_phases = 1 if time_phases else 0
     total_pairs = 0
+    ms = [0.0, 0.0, 0.0]
+    launches = 0
     with torch.cuda.device(device):
         stream = _stream(device)
         free, _total = torch.cuda.mem_get_info(device)
@@ -185,9 +189,12 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
             _lib.check(rc)
             done_any = True
             total_pairs += stats.n_pairs
+            launches += stats.launches
+            ms = [ms[0] + stats.ms_bin, ms[1] + stats.ms_sort, ms[2] + stats.ms_render]
     last_stats.clear()
     last_stats.update(n_pairs=int(total_pairs), n_tiles=int(stats.n_tiles),
-                      tile=(int(stats.tile_x), int(stats.tile_y), int(stats.tile_z)))
+                      tile=(int(stats.tile_x), int(stats.tile_y), int(stats.tile_z)),
+                      ms_bin=ms[0], ms_sort=ms[1], ms_render=ms[2], launches=launches)
     return out
 
 
@@ -254,6 +261,20 @@ def exact2d(x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
 def exact3d_proj(x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
     """B5: exact column integrals of the 3-D cubic spline (cpu_backend.py:611-720)."""
     return _exact("sphb_exact3d_proj", x, y, h, weights, raster)
+
+
+def count_contributions(x, y, h, radius, raster: Raster, z=None, z_slice=None) -> int:
+    """Exact number of (particle, pixel) pairs with q <= R (SURVEY 8(d) 'pixel-contribution')."""
+    device = x.device
+    use_z = z is not None and z_slice is not None and raster.nz == 1
+    part = _particles(x, y, z if (use_z or raster.nz > 1) else None, h, [h])
+    out = torch.zeros(1, dtype=torch.int64, device=device)
+    rast = raster.c()
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().sphb_count_contributions(ctypes.byref(part), float(radius), ctypes.byref(rast),
+                                                        1 if use_z else 0, float(z_slice or 0.0),
+                                                        ctypes.c_void_p(out.data_ptr()), _stream(device)))
+    return int(out.item())
 
 
 def normalize_(num: torch.Tensor, den: torch.Tensor) -> torch.Tensor:
