@@ -98,42 +98,49 @@ def make_workload(name, n_override, rank, dtype):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region, sampled through NVML
+    (a light in-process query; spawning nvidia-smi every 200 ms perturbs the run)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.samples = []
+    def __init__(self, gpu_index, period=0.2):
+        self.period = period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
         self.stop_flag = threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() \
+                else gpu_index
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.handle = None
 
     def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.reasons |= {k for k, bit in names.items() if mask & bit}
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(self.period)
 
     def start(self):
-        self.thread.start()
+        if self.handle is not None:
+            self.thread.start()
 
     def stop(self):
         self.stop_flag.set()
-        self.thread.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4)
-                          if len(s) >= 6 and s[2 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.handle is not None:
+            self.thread.join(timeout=3)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle port)

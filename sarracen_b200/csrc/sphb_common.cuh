@@ -65,7 +65,7 @@ template <typename R> struct LutView {
 // Heron correction -> ~1 ulp with 7 FMA-pipe ops and no slow-path branches.
 __device__ __forceinline__ double fast_sqrt(double a)
 {
-    a = fmax(a, 1e-290);
+    a += 1e-290; // a >= 0: keeps rsqrt finite at a == 0 and changes no other value
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     double g = a * y, h = 0.5 * y;
@@ -77,7 +77,7 @@ __device__ __forceinline__ double fast_sqrt(double a)
 }
 __device__ __forceinline__ float fast_sqrt(float a)
 {
-    a = fmaxf(a, 1e-35f);
+    a += 1e-35f;
     return a * rsqrtf(a);
 }
 

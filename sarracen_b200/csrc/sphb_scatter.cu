@@ -176,6 +176,30 @@ template <> struct Split<float> {
     }
 };
 
+// One evaluation of a staged particle at one pixel, given q^2.
+template <int KIND, typename R, int NW>
+__device__ __forceinline__ void add_contribution(R q2, R rad2, const LutView<R> &lv, const R (&term)[NW],
+                                                 R (&dst)[NW])
+{
+    if (q2 < rad2) {
+        const R wv = kernel_eval_q2<KIND, R>(q2, lv);
+#pragma unroll
+        for (int k = 0; k < NW; k++) dst[k] = fma(term[k], wv, dst[k]);
+    }
+}
+
+// Tile render.  Work split inside a CTA of kWarps warps:
+//   2-D tile TX x TY pixels: warp w owns the strip of rows [w TY/8, (w+1) TY/8);
+//   3-D tile TX x TY x TZ voxels with TZ == kWarps: warp w owns z-plane w.
+// Ownership is exclusive, so accumulation needs no atomics.  Per (warp,
+// particle) hit there are two code paths:
+//   wide   (footprint box wider than TX/2 inside the tile): lanes sit on fixed
+//          pixels of the warp's box -- column lane % TX, rows lane / TX + k RI --
+//          and accumulate in REGISTERS (K values per lane and weight);
+//   narrow lanes are laid over the footprint box as LW x (32 / LW) pixels, LW the
+//          power of two >= box width, and accumulate into the warp's part of the
+//          shared-memory tile (plain load / fma / store).
+// Registers and shared memory are merged when the tile segment is flushed.
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ>
 __global__ void __launch_bounds__(kThreads)
 render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
@@ -186,12 +210,15 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
               double *o3)
 {
     using R2 = typename Real2<R>::type;
-    constexpr int SX = TX + 8;            // padded row stride (bank spread for narrow boxes)
-    constexpr int PLANE = SX * TY;        // elements per z-plane
-    constexpr int ACC = PLANE * TZ;       // elements per weight
-    constexpr int OWN = DIM3 ? TZ : TY;   // extent of the axis split among warps
-    constexpr int PER_WARP = OWN / kWarps;
-    static_assert(OWN % kWarps == 0, "strip split");
+    constexpr int SX = TX + 8;                    // padded row stride
+    constexpr int PLANE = SX * TY;                // elements per z-plane
+    constexpr int ACC = PLANE * TZ;               // elements per weight
+    constexpr int ROWS = DIM3 ? TY : TY / kWarps; // rows of the warp's box
+    constexpr int RI = 32 / TX;                   // rows one warp iteration covers in the wide path
+    constexpr int K = ROWS / RI;                  // register accumulators per lane and weight
+    static_assert(!DIM3 || TZ == kWarps, "one z-plane per warp");
+    static_assert(DIM3 || TY % kWarps == 0, "strip split");
+    static_assert(32 % TX == 0 && ROWS % RI == 0, "lane layout");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *acc = reinterpret_cast<R *>(smem_raw);
@@ -221,7 +248,18 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
     __syncthreads();
 
     const R rad2 = (R)(v.radius * v.radius);
-    const int own_lo = warp * PER_WARP, own_hi = own_lo + PER_WARP;
+    // the warp's box inside the tile
+    const int own_y0 = DIM3 ? 0 : warp * ROWS;
+    const int own_lo = DIM3 ? warp : own_y0, own_hi = DIM3 ? warp + 1 : own_y0 + ROWS;
+    R *const my_acc = acc + (DIM3 ? warp * PLANE : 0);
+    // wide-path lane position
+    const int lx = lane % TX, ly = lane / TX;
+
+    R racc[NW][K];
+#pragma unroll
+    for (int k = 0; k < NW; k++)
+#pragma unroll
+        for (int r = 0; r < K; r++) racc[k][r] = R(0);
 
     const int64_t chunk_lo = (int64_t)blockIdx.x * kChunkPairs;
     const int64_t chunk_hi = min(chunk_lo + (int64_t)kChunkPairs, n_pairs);
@@ -280,7 +318,7 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
             }
             __syncthreads();
 
-            // ---- accumulate: each warp scans the batch for its strip ------------
+            // ---- accumulate: each warp scans the batch for its box --------------
             for (int g = 0; g < nb; g += 32) {
                 const int me = g + lane;
                 bool hit = false;
@@ -294,66 +332,100 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                     const int s = g + __ffs(mask) - 1;
                     mask &= mask - 1;
                     const uint32_t bx = st->bx[s], by = st->by[s];
-                    int x0 = (int)(bx & 0xffff), x1 = (int)(bx >> 16);
-                    int y0 = (int)(by & 0xffff), y1 = (int)(by >> 16);
-                    int z0 = 0, z1 = 1;
-                    if (DIM3) {
-                        const uint32_t bz = st->bz[s];
-                        z0 = max((int)(bz & 0xffff), own_lo);
-                        z1 = min((int)(bz >> 16), own_hi);
-                    } else {
-                        y0 = max(y0, own_lo);
-                        y1 = min(y1, own_hi);
-                    }
-                    const int wx = x1 - x0, wy = y1 - y0;
-                    if (wx <= 0 || wy <= 0) continue;
-                    const int wxy = wx * wy, total = wxy * (z1 - z0);
-                    const unsigned inv_wx = 65536u / (unsigned)wx + 1u;
-                    const unsigned inv_wxy = DIM3 ? (1u << 20) / (unsigned)wxy + 1u : 0u;
+                    const int x0 = (int)(bx & 0xffff), x1 = (int)(bx >> 16);
+                    const int y0 = max((int)(by & 0xffff), own_y0), y1 = min((int)(by >> 16), own_y0 + ROWS);
+                    const int wx = x1 - x0;
+                    if (wx <= 0 || y1 <= y0) continue;
                     const R fx = st->fx[s], fy = st->fy[s], sx = st->sx[s], sy = st->sy[s];
-                    const R cc = st->c[s];
                     const int cx = st->cx[s], cy = st->cy[s];
-                    R fz = R(0), sz = R(0);
-                    int cz = 0;
+                    R cc = st->c[s];
                     if (DIM3) {
-                        fz = st->fz[s];
-                        sz = st->sz[s];
-                        cz = st->cz[s];
+                        const R dz = int_to_real(warp - st->cz[s], R(0)) - st->fz[s];
+                        cc = dz * dz * st->sz[s];
                     }
                     R term[NW];
 #pragma unroll
                     for (int k = 0; k < NW; k++) term[k] = st->term[k][s];
 
-                    for (int e = lane; e < total; e += 32) {
-                        int iz = 0, rem = e;
-                        if (DIM3) {
-                            iz = (int)(((unsigned)e * inv_wxy) >> 20);
-                            rem = e - iz * wxy;
-                        }
-                        const int iy = (int)(((unsigned)rem * inv_wx) >> 16);
-                        const int ix = rem - iy * wx;
-                        const int px = x0 + ix, py = y0 + iy, pz = z0 + iz;
-                        const R dx = int_to_real(px - cx, R(0)) - fx;
-                        const R dy = int_to_real(py - cy, R(0)) - fy;
-                        R q2 = fma(dy * dy, sy, cc);
-                        if (DIM3) {
-                            const R dz = int_to_real(pz - cz, R(0)) - fz;
-                            q2 = fma(dz * dz, sz, q2);
-                        }
-                        q2 = fma(dx * dx, sx, q2);
-                        if (q2 < rad2) {
-                            const R wv = kernel_eval_q2<KIND, R>(q2, lv);
-                            R *a = acc + (pz * PLANE + py * SX + px);
+                    if (wx > TX / 2) {
+                        // ---- wide: fixed pixels, register accumulators -------------
+                        // Rows are handled G at a time without branches inside a group
+                        // (rejected lanes evaluate W(0) and add zero), so the G
+                        // dependent square-root / table chains overlap; a group no lane
+                        // of which lies inside the support is skipped by a warp vote.
+                        const R dx = int_to_real(lx - cx, R(0)) - fx;
+                        const R qx = fma(dx * dx, sx, cc);
+                        const bool in_x = lx >= x0 && lx < x1;
+                        const R dy0 = int_to_real(own_y0 + ly - cy, R(0)) - fy;
+                        constexpr int G = K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1);
 #pragma unroll
-                            for (int k = 0; k < NW; k++) a[k * ACC] = fma(term[k], wv, a[k * ACC]);
+                        for (int r0 = 0; r0 < K; r0 += G) {
+                            R q2[G];
+                            bool ok[G];
+                            bool any = false;
+#pragma unroll
+                            for (int j = 0; j < G; j++) {
+                                const int row = own_y0 + ly + (r0 + j) * RI;
+                                const R dy = dy0 + R((r0 + j) * RI);
+                                q2[j] = fma(dy * dy, sy, qx);
+                                ok[j] = in_x && row >= y0 && row < y1 && q2[j] < rad2;
+                                any = any || ok[j];
+                            }
+                            if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                                for (int j = 0; j < G; j++) {
+                                    const R wv = kernel_eval_q2<KIND, R>(ok[j] ? q2[j] : R(0), lv);
+#pragma unroll
+                                    for (int k = 0; k < NW; k++)
+                                        racc[k][r0 + j] = fma(ok[j] ? term[k] : R(0), wv, racc[k][r0 + j]);
+                                }
+                            }
                         }
+                    } else {
+                        // ---- narrow: lanes over the footprint box, shared memory ----
+                        int lw_log = 0;
+                        while ((1 << lw_log) < wx) lw_log++;
+                        const int rows_per_it = 32 >> lw_log;
+                        const int px = x0 + (lane & ((1 << lw_log) - 1));
+                        const int pr = lane >> lw_log;
+                        const bool in_x = px < x1;
+                        const R dx = int_to_real(px - cx, R(0)) - fx;
+                        const R qx = fma(dx * dx, sx, cc);
+                        R dy = int_to_real(y0 + pr - cy, R(0)) - fy;
+                        const R dstep = int_to_real(rows_per_it, R(0));
+                        R *a = my_acc + ((y0 + pr) * SX + px);
+                        for (int py = y0 + pr; py < y1; py += rows_per_it) {
+                            if (in_x) {
+                                const R q2 = fma(dy * dy, sy, qx);
+                                if (q2 < rad2) {
+                                    const R wv = kernel_eval_q2<KIND, R>(q2, lv);
+#pragma unroll
+                                    for (int k = 0; k < NW; k++) a[k * ACC] = fma(term[k], wv, a[k * ACC]);
+                                }
+                            }
+                            dy += dstep;
+                            a += rows_per_it * SX;
+                        }
+                        __syncwarp();
                     }
                 }
             }
             __syncthreads();
         }
 
-        // ---- flush the tile segment and clear the accumulator ------------------
+        // ---- merge registers into the tile, flush it, clear both ---------------
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+            R *a = my_acc + ((own_y0 + ly + r * RI) * SX + lx);
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                if (racc[k][r] != R(0)) {
+                    a[k * ACC] += racc[k][r];
+                    racc[k][r] = R(0);
+                }
+            }
+        }
+        __syncthreads();
         for (int i = tid; i < TX * TY * TZ; i += kThreads) {
             const int ix = i % TX, iy = (i / TX) % TY, iz = i / (TX * TY);
             if (ix < lim_x && iy < lim_y && iz < lim_z) {
@@ -441,7 +513,7 @@ static int dispatch_kind(int kind, int nw, A &&...a)
     }
 }
 
-constexpr int kTile2X = 32, kTile2Y = 32;
+constexpr int kTile2X = 32, kTile2Y = 64;
 constexpr int kTile3X = 16, kTile3Y = 16, kTile3Z = 8;
 
 static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
