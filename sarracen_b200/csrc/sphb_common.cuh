@@ -61,8 +61,24 @@ template <typename R> struct LutView {
 };
 
 // ---- square root -----------------------------------------------------------
-// double: MUFU.RSQ64H seed (2^-22.9) + one coupled Goldschmidt step + one
-// Heron correction -> ~1 ulp with 7 FMA-pipe ops and no slow-path branches.
+// double: MUFU.RSQ64H seed (reads the high word only: relative error < 2^-19.9)
+// followed by one coupled Goldschmidt step -> relative error < 1.5 * 2^-39.8
+// ~ 1.6e-12, far inside the 1e-10 parity budget (it moves W by < |W'| q 1.6e-12).
+// `fast_sqrt` adds a Heron correction for ~1 ulp.  Arguments must be > 0: callers
+// add sqrt_guard() once per particle so that a == 0 cannot reach rsqrt.
+__device__ __forceinline__ double sqrt_guard(double) { return 1e-290; }
+__device__ __forceinline__ float sqrt_guard(float) { return 1e-35f; }
+
+__device__ __forceinline__ double sqrt_pos(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    return fma(g, r, g);
+}
+__device__ __forceinline__ float sqrt_pos(float a) { return a * rsqrtf(a); }
+
 __device__ __forceinline__ double fast_sqrt(double a)
 {
     a += 1e-290; // a >= 0: keeps rsqrt finite at a == 0 and changes no other value
@@ -141,6 +157,25 @@ __device__ __forceinline__ R kernel_eval_q2(R q2, const LutView<R> &lut)
         return fma(f, e.y, e.x);
     } else {
         return kernel_shape<KIND>(q);
+    }
+}
+
+// W(q) from q^2 > 0 with no caller-side range test: zero for q >= radius.  The
+// table path needs no test at all -- the index clamps to the last entry, which
+// is (0, 0) because every kernel vanishes at its radius.
+template <int KIND, typename R>
+__device__ __forceinline__ R kernel_eval_unguarded(R q2, R rad2, const LutView<R> &lut)
+{
+    R q = sqrt_pos(q2);
+    if (KIND == SPHB_COLUMN_LUT) {
+        R f;
+        int i = floor_nonneg(q * lut.scale, f);
+        i = min(i, lut.last);
+        typename Real2<R>::type e = lut.tab[i];
+        return fma(f, e.y, e.x);
+    } else {
+        R w = kernel_shape<KIND>(q);
+        return q2 < rad2 ? w : R(0);
     }
 }
 

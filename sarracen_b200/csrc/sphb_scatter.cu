@@ -239,6 +239,8 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
             R2 e;
             e.x = (R)a;
             e.y = (R)(b - a);
+            // the clamp target of out-of-support lookups: W(q >= R) = 0
+            if (i == lut_samples - 1) e.x = e.y = R(0);
             lut_s[i] = e;
         }
         lv.scale = (R)((double)(lut_samples - 1) / v.radius);
@@ -349,35 +351,39 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
 
                     if (wx > TX / 2) {
                         // ---- wide: fixed pixels, register accumulators -------------
-                        // Rows are handled G at a time without branches inside a group
-                        // (rejected lanes evaluate W(0) and add zero), so the G
-                        // dependent square-root / table chains overlap; a group no lane
-                        // of which lies inside the support is skipped by a warp vote.
+                        // Every lane evaluates its own pixels: a pixel outside the
+                        // footprint box has q >= R and W(q) = 0 there (the table is
+                        // clamped to its zero last entry, the analytic shapes are
+                        // selected to 0), so no box tests are needed.  q^2 runs down
+                        // the lane's rows by second differences.  Rows are handled G at
+                        // a time without branches so the G dependent square-root /
+                        // table chains overlap; a group with no lane inside the support
+                        // is skipped by a warp vote.
                         const R dx = int_to_real(lx - cx, R(0)) - fx;
-                        const R qx = fma(dx * dx, sx, cc);
-                        const bool in_x = lx >= x0 && lx < x1;
+                        const R qx = fma(dx * dx, sx, cc) + sqrt_guard(R(0));
                         const R dy0 = int_to_real(own_y0 + ly - cy, R(0)) - fy;
+                        R q2 = fma(dy0 * dy0, sy, qx);
+                        R d1 = sy * fma(R(2 * RI), dy0, R(RI * RI));
+                        const R d2 = sy * R(2 * RI * RI);
                         constexpr int G = K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1);
 #pragma unroll
                         for (int r0 = 0; r0 < K; r0 += G) {
-                            R q2[G];
-                            bool ok[G];
+                            R q[G];
                             bool any = false;
 #pragma unroll
                             for (int j = 0; j < G; j++) {
-                                const int row = own_y0 + ly + (r0 + j) * RI;
-                                const R dy = dy0 + R((r0 + j) * RI);
-                                q2[j] = fma(dy * dy, sy, qx);
-                                ok[j] = in_x && row >= y0 && row < y1 && q2[j] < rad2;
-                                any = any || ok[j];
+                                q[j] = q2;
+                                any = any || (q2 < rad2);
+                                q2 += d1;
+                                d1 += d2;
                             }
                             if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
                                 for (int j = 0; j < G; j++) {
-                                    const R wv = kernel_eval_q2<KIND, R>(ok[j] ? q2[j] : R(0), lv);
+                                    const R wv = kernel_eval_unguarded<KIND, R>(q[j], rad2, lv);
 #pragma unroll
                                     for (int k = 0; k < NW; k++)
-                                        racc[k][r0 + j] = fma(ok[j] ? term[k] : R(0), wv, racc[k][r0 + j]);
+                                        racc[k][r0 + j] = fma(term[k], wv, racc[k][r0 + j]);
                                 }
                             }
                         }
@@ -419,10 +425,9 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
             R *a = my_acc + ((own_y0 + ly + r * RI) * SX + lx);
 #pragma unroll
             for (int k = 0; k < NW; k++) {
-                if (racc[k][r] != R(0)) {
-                    a[k * ACC] += racc[k][r];
-                    racc[k][r] = R(0);
-                }
+                // lanes beyond the raster edge hold values of pixels that do not exist
+                if (racc[k][r] != R(0) && lx < lim_x && own_y0 + ly + r * RI < lim_y) a[k * ACC] += racc[k][r];
+                racc[k][r] = R(0);
             }
         }
         __syncthreads();

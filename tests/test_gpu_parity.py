@@ -198,18 +198,18 @@ def test_single_particle_every_function(B):
     r2 = c[None, :] ** 2 + c[:, None] ** 2
     img = B.interpolate_2d_render(x, y, w, h, k.w, 2, n, n, *lim, False)
     exp = np.vectorize(lambda q: kernel_w("cubic", q, 2))(np.sqrt(r2) / 0.9) * 0.35 / 0.9 ** 2
-    np.testing.assert_allclose(img, exp, rtol=1e-12, atol=1e-15)
+    assert_parity(img, exp, 1e-11)
     col = OracleKernel.column("cubic", 1000)
     img = B.interpolate_3d_projection(x, y, w, h, k.get_column_kernel_func(1000), 2, n, n, *lim, False)
     exp = np.vectorize(lambda q: col(q, 3))(np.sqrt(r2) / 0.9) * 0.35 / 0.9 ** 2
-    np.testing.assert_allclose(img, exp, rtol=1e-11, atol=1e-15)
+    assert_parity(img, exp, 1e-11)
     img = B.interpolate_3d_cross(x, y, z, 0.0, w, h, k.w, 2, n, n, *lim)
     exp = np.vectorize(lambda q: kernel_w("cubic", q, 3))(np.sqrt(r2) / 0.9) * 0.35 / 0.9 ** 3
-    np.testing.assert_allclose(img, exp, rtol=1e-12, atol=1e-15)
+    assert_parity(img, exp, 1e-11)
     grid = B.interpolate_3d_grid(x, y, z, w, h, k.w, 2, n, n, n, *lim, -1.0, 1.0)
     r3 = np.sqrt(r2[None, :, :] + c[:, None, None] ** 2)
     exp = np.vectorize(lambda q: kernel_w("cubic", q, 3))(r3 / 0.9) * 0.35 / 0.9 ** 3
-    np.testing.assert_allclose(grid, exp, rtol=1e-12, atol=1e-15)
+    assert_parity(grid, exp, 1e-11)
 
 
 def test_repeated_particle_has_no_races(B):
