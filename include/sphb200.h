@@ -92,7 +92,8 @@ typedef struct sphb_raster {
 
 /* Optional counters filled by the scatter calls (host memory). */
 typedef struct sphb_stats {
-    int64_t n_pairs;      /* out: (particle, tile) pairs binned and sorted */
+    int64_t n_pairs;      /* out: (particle, tile) pairs binned and sorted (tile path) */
+    int64_t n_direct;     /* out: small-footprint particles rendered by the direct path */
     int64_t n_tiles;      /* out: tiles in the raster */
     int32_t tile_x, tile_y, tile_z; /* out: tile size in pixels */
     int32_t time_phases;  /* in: non-zero -> bracket the phases with CUDA events on `stream`
@@ -100,6 +101,7 @@ typedef struct sphb_stats {
     float ms_bin;         /* out: count + scan + emit kernels */
     float ms_sort;        /* out: radix sort + segment boundaries */
     float ms_render;      /* out: the tile render kernel alone */
+    float ms_direct;      /* out: the direct (small-footprint) kernel alone */
     int32_t launches;     /* out: kernels of this library launched by the call (CUB's not counted) */
 } sphb_stats;
 

@@ -160,6 +160,23 @@ __device__ __forceinline__ R kernel_eval_q2(R q2, const LutView<R> &lut)
     }
 }
 
+// W(q) from 0 < q^2 < radius^2 (the caller has tested the range and added
+// sqrt_guard()).
+template <int KIND, typename R>
+__device__ __forceinline__ R kernel_eval_pos(R q2, const LutView<R> &lut)
+{
+    R q = sqrt_pos(q2);
+    if (KIND == SPHB_COLUMN_LUT) {
+        R f;
+        int i = floor_nonneg(q * lut.scale, f);
+        i = min(i, lut.last);
+        typename Real2<R>::type e = lut.tab[i];
+        return fma(f, e.y, e.x);
+    } else {
+        return kernel_shape<KIND>(q);
+    }
+}
+
 // W(q) from q^2 > 0 with no caller-side range test: zero for q >= radius.  The
 // table path needs no test at all -- the index clamps to the last entry, which
 // is (0, 0) because every kernel vanishes at its radius.

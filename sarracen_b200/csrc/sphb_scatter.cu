@@ -26,6 +26,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
+
 #include "sphb_common.cuh"
 
 namespace sphb {
@@ -49,6 +51,8 @@ struct View {
     int dim3;  // voxel raster
     int ndim;  // exponent of h in the particle term
     double norm;
+    int small_edge;    // footprint boxes with every edge <= this many pixels take the direct path
+    uint32_t flag_bit; // key bit that marks a direct-path particle (sorts after all tile pairs)
 };
 
 struct TileBox {
@@ -71,15 +75,18 @@ __device__ __forceinline__ void pixel_range(double c, double rad, double origin,
 }
 
 // Tiles covered by a particle's support box; false if it touches no pixel.
+// `small` is set when the whole box is at most small_edge pixels along every
+// axis: such a particle is not binned per tile but listed once (under the tile
+// of its box origin) for the direct path.
 template <typename T>
 __device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const T *y, const T *z,
-                                               const T *h, int64_t i, TileBox &b)
+                                               const T *h, int64_t i, TileBox &b, bool &small)
 {
     double hp = (double)__ldg(h + i);
     double xp = (double)__ldg(x + i), yp = (double)__ldg(y + i);
     if (!(hp > 0.0) || !isfinite(hp) || !isfinite(xp) || !isfinite(yp)) return false;
     double rad = v.radius * hp;
-    int lo, hi;
+    int lo, hi, edge = 0;
     b.z0 = b.z1 = 0;
     if (v.dim3) {
         double zp = (double)__ldg(z + i);
@@ -88,6 +95,7 @@ __device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const 
         if (hi <= lo) return false;
         b.z0 = lo / v.tz;
         b.z1 = (hi - 1) / v.tz;
+        edge = hi - lo;
     } else if (v.use_z) {
         double dz = v.z_slice - (double)__ldg(z + i);
         if (!(fabs(dz) < rad)) return false; // cpu_backend.py:264
@@ -96,24 +104,31 @@ __device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const 
     if (hi <= lo) return false;
     b.x0 = lo / v.tx;
     b.x1 = (hi - 1) / v.tx;
+    edge = max(edge, hi - lo);
     pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, lo, hi);
     if (hi <= lo) return false;
     b.y0 = lo / v.ty;
     b.y1 = (hi - 1) / v.ty;
+    edge = max(edge, hi - lo);
+    small = edge <= v.small_edge;
     return true;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint64_t *counts)
+count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint64_t *counts,
+                   unsigned long long *n_small)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
     TileBox b;
     uint64_t c = 0; // counts[n] = 0 so that the exclusive scan leaves the total there
-    if (i < n && particle_tiles(v, x, y, z, h, i, b))
-        c = (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) * (uint64_t)(b.z1 - b.z0 + 1);
-    counts[i] = c;
+    bool small = false;
+    if (i < n && particle_tiles(v, x, y, z, h, i, b, small))
+        c = small ? 1
+                  : (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) * (uint64_t)(b.z1 - b.z0 + 1);
+    if (i <= n) counts[i] = c;
+    const unsigned m = __ballot_sync(0xffffffffu, small && c);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_small, (unsigned long long)__popc(m));
 }
 
 template <typename T>
@@ -124,8 +139,14 @@ emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     TileBox b;
-    if (!particle_tiles(v, x, y, z, h, i, b)) return;
+    bool small;
+    if (!particle_tiles(v, x, y, z, h, i, b, small)) return;
     uint64_t o = offsets[i];
+    if (small) {
+        keys[o] = (uint32_t)((b.z0 * v.nty + b.y0) * v.ntx + b.x0) | v.flag_bit;
+        vals[o] = (uint32_t)i;
+        return;
+    }
     for (int tz = b.z0; tz <= b.z1; tz++)
         for (int ty = b.y0; ty <= b.y1; ty++)
             for (int tx = b.x0; tx <= b.x1; tx++) {
@@ -452,6 +473,169 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
 }
 
 // ---------------------------------------------------------------------------
+// Direct path for small footprints.
+//
+// A particle whose support box is at most small_edge pixels along every axis
+// covers a handful of pixels; binning it per tile, staging it per tile and
+// scanning it per warp costs far more than its few kernel evaluations.  Such
+// particles are listed once (sorted by the tile of their box origin, so that
+// consecutive particles touch the same few kilobytes of the raster and the
+// reductions are served by L2) and rendered here: one warp takes 32 of them,
+// every lane works out the record of one, then sub-groups of LPP lanes -- LPP
+// the power of two >= the largest in-plane box area in the batch -- walk one
+// particle each, a lane per in-plane pixel and a loop over z, adding each
+// contribution to the float64 raster with red.global.add.f64.
+constexpr int kDirectWarps = 8;
+
+template <typename R, int NW> struct DirectRec {
+    R fx[32], fy[32], fz[32]; // centre in pixel units relative to the box origin
+    R sx[32], sy[32], sz[32];
+    R cq[32];                 // dz^2 / h^2 of a cross-section + sqrt guard
+    R term[NW][32];
+    int ox[32], oy[32], oz[32]; // box origin in raster pixels
+    uint32_t dims[32];        // wx | wy << 8 | wz << 16 ; 0 = nothing to do
+};
+
+template <typename T, typename R, int KIND, int NW, bool DIM3>
+__global__ void __launch_bounds__(kDirectWarps * 32)
+direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+              const T *__restrict__ h, const T *__restrict__ w0, const T *__restrict__ w1,
+              const T *__restrict__ w2, const T *__restrict__ w3, const double *__restrict__ lut,
+              int lut_samples, const uint32_t *__restrict__ order, int64_t n_small, double *o0, double *o1,
+              double *o2, double *o3)
+{
+    using R2 = typename Real2<R>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DirectRec<R, NW> *recs = reinterpret_cast<DirectRec<R, NW> *>(smem_raw);
+    R2 *lut_s = reinterpret_cast<R2 *>(recs + kDirectWarps);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DirectRec<R, NW> &rec = recs[warp];
+    const T *wsrc[4] = {w0, w1, w2, w3};
+    double *outs[4] = {o0, o1, o2, o3};
+
+    LutView<R> lv;
+    lv.tab = lut_s;
+    lv.scale = R(0);
+    lv.last = 0;
+    if (KIND == SPHB_COLUMN_LUT) {
+        for (int i = tid; i < lut_samples; i += kDirectWarps * 32) {
+            double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
+            R2 e;
+            e.x = (R)a;
+            e.y = (R)(b - a);
+            if (i == lut_samples - 1) e.x = e.y = R(0);
+            lut_s[i] = e;
+        }
+        lv.scale = (R)((double)(lut_samples - 1) / v.radius);
+        lv.last = lut_samples - 1;
+        __syncthreads();
+    }
+    const R rad2 = (R)(v.radius * v.radius);
+    const int64_t warps_total = (int64_t)gridDim.x * kDirectWarps;
+
+    for (int64_t base = ((int64_t)blockIdx.x * kDirectWarps + warp) * 32; base < n_small;
+         base += warps_total * 32) {
+        // ---- every lane prepares one particle --------------------------------
+        int area = 0;
+        {
+            uint32_t dims = 0;
+            if (base + lane < n_small) {
+                const int64_t p = order[base + lane];
+                const double hp = (double)__ldg(h + p);
+                const double xp = (double)__ldg(x + p), yp = (double)__ldg(y + p);
+                const double rad = v.radius * hp;
+                const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
+                int x0, x1, y0, y1, z0 = 0, z1 = 1;
+                pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, x0, x1);
+                pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, y0, y1);
+                rec.fx[lane] = (R)((xp - v.x_min) * v.inv_pwx - 0.5 - x0);
+                rec.fy[lane] = (R)((yp - v.y_min) * v.inv_pwy - 0.5 - y0);
+                rec.sx[lane] = (R)(v.pwx * v.pwx * hinv2);
+                rec.sy[lane] = (R)(v.pwy * v.pwy * hinv2);
+                double cc = 0.0;
+                if (DIM3) {
+                    const double zp = (double)__ldg(z + p);
+                    pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, z0, z1);
+                    rec.fz[lane] = (R)((zp - v.z_min) * v.inv_pwz - 0.5 - z0);
+                    rec.sz[lane] = (R)(v.pwz * v.pwz * hinv2);
+                } else if (v.use_z) {
+                    const double dz = v.z_slice - (double)__ldg(z + p);
+                    cc = dz * dz * hinv2;
+                }
+                rec.cq[lane] = (R)cc + sqrt_guard(R(0));
+                const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
+#pragma unroll
+                for (int k = 0; k < NW; k++) rec.term[k][lane] = (R)((double)__ldg(wsrc[k] + p) * scale);
+                rec.ox[lane] = x0;
+                rec.oy[lane] = y0;
+                rec.oz[lane] = z0;
+                const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
+                if (wx > 0 && wy > 0 && wz > 0) {
+                    dims = (uint32_t)wx | ((uint32_t)wy << 8) | ((uint32_t)wz << 16);
+                    area = wx * wy;
+                }
+            }
+            rec.dims[lane] = dims;
+        }
+        // largest in-plane area of the batch -> lanes per particle
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) area = max(area, __shfl_xor_sync(0xffffffffu, area, o));
+        __syncwarp();
+        if (area == 0) continue;
+        int lpp_log = 0;
+        while ((1 << lpp_log) < area && lpp_log < 5) lpp_log++;
+        const int lpp = 1 << lpp_log, sub = lane & (lpp - 1), grp = lane >> lpp_log;
+
+        for (int g = 0; g < 32; g += 32 >> lpp_log) {
+            const int s = g + grp;
+            const uint32_t dims = rec.dims[s];
+            if (dims) {
+                const int wx = (int)(dims & 0xff), wy = (int)((dims >> 8) & 0xff), wz = (int)(dims >> 16);
+                const int x0 = rec.ox[s], y0 = rec.oy[s], z0 = rec.oz[s];
+                const R fx = rec.fx[s], fy = rec.fy[s], sx = rec.sx[s], sy = rec.sy[s], cq = rec.cq[s];
+                R fz = R(0), sz = R(0);
+                if (DIM3) {
+                    fz = rec.fz[s];
+                    sz = rec.sz[s];
+                }
+                R term[NW];
+#pragma unroll
+                for (int k = 0; k < NW; k++) term[k] = rec.term[k][s];
+                const unsigned inv_wx = 65536u / (unsigned)wx + 1u;
+                for (int e = sub; e < wx * wy; e += lpp) {
+                    const int iy = (int)(((unsigned)e * inv_wx) >> 16), ix = e - iy * wx;
+                    const R dx = int_to_real(ix, R(0)) - fx, dy = int_to_real(iy, R(0)) - fy;
+                    const R qxy = fma(dy * dy, sy, fma(dx * dx, sx, cq));
+                    const size_t o = ((size_t)z0 * v.ny + (size_t)(y0 + iy)) * v.nx + (size_t)(x0 + ix);
+                    if (DIM3) {
+                        // q^2 along z by second differences
+                        R q2 = fma(fz * fz, sz, qxy);
+                        R d1 = sz * fma(R(-2), fz, R(1));
+                        const R d2 = sz + sz;
+                        size_t oo = o;
+                        for (int iz = 0; iz < wz; iz++) {
+                            if (q2 < rad2) {
+                                const R wv = kernel_eval_pos<KIND, R>(q2, lv);
+#pragma unroll
+                                for (int k = 0; k < NW; k++) red_add(outs[k] + oo, (double)(term[k] * wv));
+                            }
+                            q2 += d1;
+                            d1 += d2;
+                            oo += (size_t)v.ny * v.nx;
+                        }
+                    } else if (qxy < rad2) {
+                        const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
+#pragma unroll
+                        for (int k = 0; k < NW; k++) red_add(outs[k] + o, (double)(term[k] * wv));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Host side.
 
 struct Workspace {
@@ -496,6 +680,56 @@ static int launch_render(const View &v, const sphb_particles *p, const sphb_kern
     return SPHB_OK;
 }
 
+template <typename T, typename R, int KIND, int NW, bool DIM3>
+static int launch_direct(const View &v, const sphb_particles *p, const sphb_kernel *k, const uint32_t *order,
+                         int64_t n_small, double *const *out, cudaStream_t stream)
+{
+    using R2 = typename Real2<R>::type;
+    auto kern = direct_kernel<T, R, KIND, NW, DIM3>;
+    size_t smem = sizeof(DirectRec<R, NW>) * kDirectWarps;
+    if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
+    if (smem > 227 * 1024) {
+        set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
+        return SPHB_ERR_ARGUMENT;
+    }
+    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = div_up(n_small, kDirectWarps * 32);
+    grid = grid > 148 * 64 ? 148 * 64 : grid;
+    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NW; i++) {
+        w[i] = static_cast<const T *>(p->w[i]);
+        o[i] = out[i];
+    }
+    kern<<<grid, kDirectWarps * 32, smem, stream>>>(
+        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->z),
+        static_cast<const T *>(p->h), w[0], w[1], w[2], w[3], k->lut, k->lut_samples, order, n_small, o[0],
+        o[1], o[2], o[3]);
+    SPHB_LAUNCH_CHECK();
+    return SPHB_OK;
+}
+
+template <typename T, typename R, int KIND, bool DIM3, typename... A>
+static int direct_nw(int nw, A &&...a)
+{
+    switch (nw) {
+    case 1: return launch_direct<T, R, KIND, 1, DIM3>(a...);
+    case 2: return launch_direct<T, R, KIND, 2, DIM3>(a...);
+    case 3: return launch_direct<T, R, KIND, 3, DIM3>(a...);
+    default: return launch_direct<T, R, KIND, 4, DIM3>(a...);
+    }
+}
+
+template <typename T, typename R, bool DIM3, typename... A> static int direct_kind(int kind, int nw, A &&...a)
+{
+    switch (kind) {
+    case SPHB_CUBIC: return direct_nw<T, R, SPHB_CUBIC, DIM3>(nw, a...);
+    case SPHB_QUARTIC: return direct_nw<T, R, SPHB_QUARTIC, DIM3>(nw, a...);
+    case SPHB_QUINTIC: return direct_nw<T, R, SPHB_QUINTIC, DIM3>(nw, a...);
+    default: return direct_nw<T, R, SPHB_COLUMN_LUT, DIM3>(nw, a...);
+    }
+}
+
 template <typename T, typename R, int KIND, bool DIM3, int TX, int TY, int TZ, typename... A>
 static int dispatch_nw(int nw, A &&...a)
 {
@@ -519,6 +753,19 @@ static int dispatch_kind(int kind, int nw, A &&...a)
 }
 
 constexpr int kTile2X = 32, kTile2Y = 64;
+
+// Footprint boxes up to this many pixels per edge take the direct path.  The
+// default can be overridden with SPHB_SMALL_EDGE (0 sends everything through
+// the tile path) for experiments.
+static int small_edge_setting()
+{
+    const char *e = getenv("SPHB_SMALL_EDGE");
+    if (e && *e) {
+        int val = atoi(e);
+        return val < 0 ? 0 : val > 15 ? 15 : val;
+    }
+    return 8;
+}
 constexpr int kTile3X = 16, kTile3Y = 16, kTile3Z = 8;
 
 static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
@@ -599,11 +846,16 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     v.dim3 = dim3 ? 1 : 0;
     v.ndim = k->ndim;
     v.norm = kernel_norm(k->kind, k->ndim);
+    v.small_edge = small_edge_setting();
     const int64_t n_tiles = (int64_t)v.ntx * v.nty * v.ntz;
-    if (n_tiles > 0x7fffffffLL) {
+    if (n_tiles > 0x3fffffffLL) {
         set_error("raster has too many tiles");
         return SPHB_ERR_ARGUMENT;
     }
+    int end_bit = 1;
+    while ((1LL << end_bit) < n_tiles) end_bit++;
+    v.flag_bit = 1u << end_bit; // direct-path entries sort behind every tile pair
+    end_bit++;
     const int64_t n = p->n;
     const size_t n_out = (size_t)v.nx * v.ny * v.nz;
 
@@ -611,26 +863,27 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         for (int i = 0; i < p->n_weights; i++)
             SPHB_CUDA(cudaMemsetAsync(out[i], 0, n_out * sizeof(double), stream));
     const bool timed = stats && stats->time_phases;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (stats) {
         stats->n_pairs = 0;
         stats->n_tiles = n_tiles;
         stats->tile_x = v.tx;
         stats->tile_y = v.ty;
         stats->tile_z = v.tz;
-        stats->ms_bin = stats->ms_sort = stats->ms_render = 0.f;
+        stats->ms_bin = stats->ms_sort = stats->ms_render = stats->ms_direct = 0.f;
+        stats->n_direct = 0;
         stats->launches = 0;
     }
     struct EventGuard {
         cudaEvent_t *e;
         ~EventGuard()
         {
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < 5; i++)
                 if (e[i]) cudaEventDestroy(e[i]);
         }
     } guard{ev};
     if (timed)
-        for (int i = 0; i < 4; i++) SPHB_CUDA(cudaEventCreate(&ev[i]));
+        for (int i = 0; i < 5; i++) SPHB_CUDA(cudaEventCreate(&ev[i]));
     if (ws_needed) *ws_needed = 0;
     if (n == 0) return SPHB_OK;
 
@@ -640,6 +893,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
                                             n + 1, stream));
     Workspace a(ws);
     uint64_t *offsets = a.take<uint64_t>(n + 1); // counts, scanned in place
+    unsigned long long *n_small_dev = a.take<unsigned long long>(1);
     unsigned char *scan_ws = a.take<unsigned char>(scan_tmp);
     const size_t need_a = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_a;
@@ -651,13 +905,19 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     const T *z = static_cast<const T *>(p->z), *h = static_cast<const T *>(p->h);
     const int blocks = div_up(n + 1, 256);
     if (timed) SPHB_CUDA(cudaEventRecord(ev[0], stream));
-    count_tiles_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets);
+    SPHB_CUDA(cudaMemsetAsync(n_small_dev, 0, sizeof(unsigned long long), stream));
+    count_tiles_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets, n_small_dev);
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
     uint64_t total = 0;
+    unsigned long long n_small_host = 0;
     SPHB_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    SPHB_CUDA(cudaMemcpyAsync(&n_small_host, n_small_dev, sizeof(n_small_host), cudaMemcpyDeviceToHost, stream));
     SPHB_CUDA(cudaStreamSynchronize(stream));
-    if (stats) stats->n_pairs = (int64_t)total;
+    if (stats) {
+        stats->n_pairs = (int64_t)total - (int64_t)n_small_host;
+        stats->n_direct = (int64_t)n_small_host;
+    }
     if (total == 0) return SPHB_OK;
     if (total > 0x7fffffffULL) {
         set_error("%llu (particle, tile) pairs exceed 2^31-1: split the particle set",
@@ -665,11 +925,11 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         if (ws_needed) *ws_needed = 0;
         return SPHB_ERR_TOO_MANY;
     }
-    const int64_t n_pairs = (int64_t)total;
+    const int64_t n_pairs = (int64_t)total;                     // entries in the sorted list
+    const int64_t n_small = (int64_t)n_small_host;              // its tail: direct-path particles
+    const int64_t n_large = n_pairs - n_small;                  // its head: (tile, particle) pairs
 
     // ---- phase B: emit, sort, segment ------------------------------------
-    int end_bit = 1;
-    while ((1LL << end_bit) < n_tiles) end_bit++;
     size_t sort_tmp = 0;
     SPHB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                               (uint32_t *)nullptr, (uint32_t *)nullptr, n_pairs, 0,
@@ -692,36 +952,52 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     if (timed) SPHB_CUDA(cudaEventRecord(ev[1], stream));
     SPHB_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sort_tmp, keys_a, keys_b, vals_a, vals_b, n_pairs, 0,
                                               end_bit, stream));
-    tile_end_kernel<<<div_up(n_pairs, 256), 256, 0, stream>>>(keys_b, n_pairs, tile_end);
-    SPHB_LAUNCH_CHECK();
+    if (n_large > 0) {
+        tile_end_kernel<<<div_up(n_large, 256), 256, 0, stream>>>(keys_b, n_large, tile_end);
+        SPHB_LAUNCH_CHECK();
+    }
 
     // ---- phase C: render ---------------------------------------------------
     if (timed) SPHB_CUDA(cudaEventRecord(ev[2], stream));
     const bool f32 = p->dtype == SPHB_F32;
-    int rc;
-    if (dim3) {
-        if (f32)
-            rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z>(
-                k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_pairs, out, stream);
+    int rc = SPHB_OK;
+    if (n_large > 0) {
+        if (dim3) {
+            if (f32)
+                rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z>(
+                    k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_large, out, stream);
+            else
+                rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z>(
+                    k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_large, out, stream);
+        } else {
+            if (f32)
+                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
+                                                                        vals_b, tile_end, n_large, out, stream);
+            else
+                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
+                                                                         vals_b, tile_end, n_large, out, stream);
+        }
+        if (rc) return rc;
+    }
+    if (timed) SPHB_CUDA(cudaEventRecord(ev[4], stream));
+    if (n_small > 0) {
+        const uint32_t *order = vals_b + n_large;
+        if (dim3)
+            rc = f32 ? direct_kind<T, float, true>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream)
+                     : direct_kind<T, double, true>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream);
         else
-            rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z>(
-                k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_pairs, out, stream);
-    } else {
-        if (f32)
-            rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
-                                                                    vals_b, tile_end, n_pairs, out, stream);
-        else
-            rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
-                                                                     vals_b, tile_end, n_pairs, out, stream);
+            rc = f32 ? direct_kind<T, float, false>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream)
+                     : direct_kind<T, double, false>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream);
     }
     if (rc) return rc;
-    if (stats) stats->launches = 4; // count, emit, tile_end, render
+    if (stats) stats->launches = 2 + (n_large > 0 ? 2 : 0) + (n_small > 0 ? 1 : 0); // count, emit, tile_end, render, direct
     if (timed) {
         SPHB_CUDA(cudaEventRecord(ev[3], stream));
         SPHB_CUDA(cudaEventSynchronize(ev[3]));
         SPHB_CUDA(cudaEventElapsedTime(&stats->ms_bin, ev[0], ev[1]));
         SPHB_CUDA(cudaEventElapsedTime(&stats->ms_sort, ev[1], ev[2]));
-        SPHB_CUDA(cudaEventElapsedTime(&stats->ms_render, ev[2], ev[3]));
+        SPHB_CUDA(cudaEventElapsedTime(&stats->ms_render, ev[2], ev[4]));
+        SPHB_CUDA(cudaEventElapsedTime(&stats->ms_direct, ev[4], ev[3]));
     }
     return SPHB_OK;
 }

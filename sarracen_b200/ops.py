@@ -150,7 +150,8 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
     stats = SphbStats()
     stats.time_phases = 1 if time_phases else 0
     total_pairs = 0
-    ms = [0.0, 0.0, 0.0]
+    total_direct = 0
+    ms = [0.0, 0.0, 0.0, 0.0]
     launches = 0
     with torch.cuda.device(device):
         stream = _stream(device)
@@ -189,12 +190,13 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
             _lib.check(rc)
             done_any = True
             total_pairs += stats.n_pairs
+            total_direct += stats.n_direct
             launches += stats.launches
-            ms = [ms[0] + stats.ms_bin, ms[1] + stats.ms_sort, ms[2] + stats.ms_render]
+            ms = [ms[0] + stats.ms_bin, ms[1] + stats.ms_sort, ms[2] + stats.ms_render, ms[3] + stats.ms_direct]
     last_stats.clear()
-    last_stats.update(n_pairs=int(total_pairs), n_tiles=int(stats.n_tiles),
+    last_stats.update(n_pairs=int(total_pairs), n_direct=int(total_direct), n_tiles=int(stats.n_tiles),
                       tile=(int(stats.tile_x), int(stats.tile_y), int(stats.tile_z)),
-                      ms_bin=ms[0], ms_sort=ms[1], ms_render=ms[2], launches=launches)
+                      ms_bin=ms[0], ms_sort=ms[1], ms_render=ms[2], ms_direct=ms[3], launches=launches)
     return out
 
 
