@@ -171,7 +171,7 @@ def cpu_baseline(wl, budget_s=15.0):
         scale = max(1.0, min(budget_s / max(t, 1e-3), wl["n"] / ns))
         ns2 = int(ns * scale)
         t2 = run(ns2) if ns2 > ns else t
-        return {"value": ns2 / t2, "unit": "particles/s", "cores": threads, "kind": "port",
+        return {"value": ns2 / t2, "unit": "particles/s", "cores": threads, "kind": "port", "seconds": t2,
                 "sample": f"first {ns2} of {wl['n']} particles of the same set, same {wl['nx']}x{wl['ny']} raster, "
                           f"{t2:.2f} s, oracle/sph_oracle.c with {threads} OpenMP threads"}
     # voxel grid: the reference makes nz full passes over the particles (cpu_backend.py:213-218), far too
@@ -192,7 +192,7 @@ def cpu_baseline(wl, budget_s=15.0):
             t = run(ns, m)
     finally:
         cols["h"] = saved
-    return {"value": ns / t, "unit": "particles/s", "cores": threads, "kind": "port",
+    return {"value": ns / t, "unit": "particles/s", "cores": threads, "kind": "port", "seconds": t,
             "sample": f"{ns} particles -> {m}^3 voxels with the same 2h/voxel ({t:.2f} s); the reference does nz "
                       f"full passes so particles/s falls as 1/nz: at {wl['nx']}^3 expect x{m / wl['nx']:.3f}, "
                       f"oracle/sph_oracle.c with {threads} OpenMP threads"}
@@ -204,16 +204,18 @@ def run_reference(args):
     if rank != 0:
         return
     wl = make_workload(args.workload, args.particles, 0, args.dtype)
-    per_step = []
+    per_step, secs = [], []
     base = None
     for i in range(args.warmup + args.steps):
         base = cpu_baseline(wl, budget_s=max(2.0, 60.0 / (args.warmup + args.steps)))
         if i >= args.warmup:
             per_step.append(base["value"])
+            secs.append(base["seconds"])
     value = float(np.mean(per_step))
     base["value"] = value
     line = {"impl": "reference", "metric": "particles/sec", "value": value, "unit": "particles/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(secs)) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "config": {"workload": wl["desc"]}, "cpu_baseline": base,
             "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
