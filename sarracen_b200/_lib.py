@@ -78,8 +78,8 @@ def load():
     lib.sphb_scatter3d.argtypes = [P, K, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), S, c_vp]
     lib.sphb_line2d.argtypes = [P, K, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_int, outs, c_vp]
     lib.sphb_line3d.argtypes = [P, K, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_int, outs, c_vp]
-    lib.sphb_exact2d.argtypes = [P, R, c_int, outs, c_vp]
-    lib.sphb_exact3d_proj.argtypes = [P, R, c_int, outs, c_vp]
+    lib.sphb_exact2d.argtypes = [P, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), c_vp]
+    lib.sphb_exact3d_proj.argtypes = [P, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), c_vp]
     lib.sphb_normalize.argtypes = [c_vp, c_vp, ctypes.c_int64, c_vp]
     lib.sphb_count_contributions.argtypes = [P, c_dbl, R, c_int, c_dbl, c_vp, c_vp]
     for name in EXPORTS:

@@ -8,10 +8,12 @@
 // is a difference of edge/face terms that cancel to many digits.
 //
 // Decomposition: these paths cost 10^3 - 10^4 double-precision operations per
-// (particle, pixel), so accumulation is not the bottleneck.  One warp takes 32
-// particles at a time, lanes are spread over the pixels of one particle's
-// bounding box, every lane evaluates its pixel's full boundary integral and
-// adds it to the image with red.global.add.f64.
+// (particle, pixel), so accumulation is not the bottleneck but load balance is
+// (boxes range from 1 to thousands of pixels).  The work is flattened into
+// units of 32 consecutive pixels of one particle's box (count -> exclusive
+// scan); warps take units grid-stride, find the particle by binary search in
+// the scanned offsets, every lane evaluates its pixel's full boundary integral
+// and adds it to the image with red.global.add.f64.
 //
 //  - 2-D: the four edge integrals of a pixel are evaluated directly.  The
 //    reference evaluates each interior edge once and adds it to one pixel and
@@ -20,40 +22,73 @@
 //  - A particle whose clamped pixel range is empty contributes nothing; the
 //    reference's lone top-row / left-column edge terms for such a particle
 //    (:370, :387) and its out-of-bounds row write (:353) are not reproduced.
+#include <cub/device/device_scan.cuh>
+
 #include "sphb_common.cuh"
 
 namespace sphb {
 
 namespace ex {
 
-__device__ __forceinline__ double log_tan_term(double phi) { return log(tan(0.5 * phi + 0.25 * kPi)); }
+// The closed forms below need sin, cos and tan of an angle phi plus
+// L = ln tan(phi/2 + pi/4) and, in two of the three regions, phi itself.  Every
+// angle on this path is either atan(t) of a known tangent t (segment end
+// points) or acos(c) of a known cosine c (where the segment crosses q = 1 or
+// q = 2), so the trigonometric values are algebraic in t resp. c:
+//   cos = 1/sqrt(1+t^2), sin = t cos, L = ln((1 + sin)/cos) = ln(t + sqrt(1+t^2)),
+//   sin 3phi = 3 sin - 4 sin^3.
+// Only atan / acos (for phi) and one log per angle remain -- the same numbers
+// the reference gets from cos(atan(t)) etc., to rounding.
+struct Angle {
+    double s, c, tn, logs, phi;
+};
+
+__device__ __forceinline__ Angle angle_from_tan(double t)
+{
+    Angle a;
+    t = fmin(t, 1e150);
+    const double r = sqrt(fma(t, t, 1.0));
+    a.c = 1.0 / r;
+    a.s = t * a.c;
+    a.tn = t;
+    a.logs = log(t + r);
+    a.phi = atan(t);
+    return a;
+}
+
+__device__ __forceinline__ Angle angle_from_cos(double c)
+{
+    Angle a;
+    a.c = c;
+    a.s = sqrt(fmax(1.0 - c * c, 0.0));
+    a.tn = a.s / c;
+    a.logs = log((1.0 + a.s) / c);
+    a.phi = acos(c);
+    return a;
+}
 
 // cubic_spline_exact.py:124-155 -- region 0 < q <= 1
-__device__ double f1_2d(double phi, double q0)
+__device__ __forceinline__ double f1_2d(const Angle &a, double q0)
 {
-    double s, c;
-    sincos(phi, &s, &c);
-    const double c2 = c * c, tn = s / c;
-    const double logs = log_tan_term(phi);
-    const double i2 = tn;
-    const double i4 = (1.0 / 3.0) * tn * (2.0 + 1.0 / c2);
-    const double i5 = (1.0 / 16.0) * (0.5 * (11.0 * s + 3.0 * sin(3.0 * phi)) / c2 / c2 + 6.0 * logs);
+    const double ic2 = 1.0 / (a.c * a.c);
+    const double i2 = a.tn;
+    const double i4 = (1.0 / 3.0) * a.tn * (2.0 + ic2);
+    const double s3 = a.s * (20.0 - 12.0 * a.s * a.s); // 11 sin + 3 sin 3phi
+    const double i5 = (1.0 / 16.0) * (0.5 * s3 * ic2 * ic2 + 6.0 * a.logs);
     const double q02 = q0 * q0;
     return 5.0 / 7.0 * q02 / kPi * (i2 - 0.75 * q02 * i4 + 0.3 * q02 * q0 * i5);
 }
 
 // cubic_spline_exact.py:158-196 -- region 1 < q <= 2
-__device__ double f2_2d(double phi, double q0)
+__device__ __forceinline__ double f2_2d(const Angle &a, double q0)
 {
-    double s, c;
-    sincos(phi, &s, &c);
-    const double c2 = c * c, tn = s / c;
+    const double ic = 1.0 / a.c, ic2 = ic * ic;
     const double q02 = q0 * q0, q03 = q02 * q0;
-    const double logs = log_tan_term(phi);
-    const double i0 = phi, i2 = tn;
-    const double i3 = 0.5 * (tn / c + logs);
-    const double i4 = (1.0 / 3.0) * tn * (2.0 + 1.0 / c2);
-    const double i5 = (1.0 / 16.0) * (0.5 * (11.0 * s + 3.0 * sin(3.0 * phi)) / c2 / c2 + 6.0 * logs);
+    const double i0 = a.phi, i2 = a.tn;
+    const double i3 = 0.5 * (a.tn * ic + a.logs);
+    const double i4 = (1.0 / 3.0) * a.tn * (2.0 + ic2);
+    const double s3 = a.s * (20.0 - 12.0 * a.s * a.s);
+    const double i5 = (1.0 / 16.0) * (0.5 * s3 * ic2 * ic2 + 6.0 * a.logs);
     return 5.0 / 7.0 * q02 / kPi *
            (2.0 * i2 - 2.0 * q0 * i3 + 0.75 * q02 * i4 - 0.1 * q03 * i5 - 0.1 / q02 * i0);
 }
@@ -61,24 +96,24 @@ __device__ double f2_2d(double phi, double q0)
 // cubic_spline_exact.py:199-217 -- region q > 2
 __device__ __forceinline__ double f3_2d(double phi) { return 0.5 / kPi * phi; }
 
-// cubic_spline_exact.py:58-121
-__device__ double full_2d_mod(double phi, double q0)
+// cubic_spline_exact.py:58-121; `t` is tan(phi) of the segment end point
+__device__ double full_2d_mod(double t, double q0)
 {
+    const Angle e = angle_from_tan(t);
+    const double q = q0 / e.c;
     if (q0 <= 1.0) {
-        const double q = q0 / cos(phi);
-        if (q <= 1.0) return f1_2d(phi, q0);
-        const double pa = acos(q0);
-        if (q <= 2.0) return f2_2d(phi, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
-        const double pb = acos(0.5 * q0);
-        return f3_2d(phi) - f3_2d(pb) + f2_2d(pb, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
+        if (q <= 1.0) return f1_2d(e, q0);
+        const Angle pa = angle_from_cos(q0);
+        if (q <= 2.0) return f2_2d(e, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
+        const Angle pb = angle_from_cos(0.5 * q0);
+        return f3_2d(e.phi) - f3_2d(pb.phi) + f2_2d(pb, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
     }
     if (q0 <= 2.0) {
-        const double q = q0 / cos(phi);
-        if (q <= 2.0) return f2_2d(phi, q0);
-        const double pb = acos(0.5 * q0);
-        return f3_2d(phi) - f3_2d(pb) + f2_2d(pb, q0);
+        if (q <= 2.0) return f2_2d(e, q0);
+        const Angle pb = angle_from_cos(0.5 * q0);
+        return f3_2d(e.phi) - f3_2d(pb.phi) + f2_2d(pb, q0);
     }
-    return f3_2d(phi);
+    return f3_2d(e.phi);
 }
 
 // cubic_spline_exact.py:7-55
@@ -87,8 +122,7 @@ __device__ double line_int(double r0, double d1, double d2, double h)
     if (r0 == 0.0) return 0.0;
     const double sign = r0 > 0.0 ? 1.0 : -1.0, ar0 = fabs(r0);
     const double q0 = ar0 / h;
-    const double pa = atan(fabs(d1) / ar0), pb = atan(fabs(d2) / ar0);
-    const double fa = full_2d_mod(pa, q0), fb = full_2d_mod(pb, q0);
+    const double fa = full_2d_mod(fabs(d1) / ar0, q0), fb = full_2d_mod(fabs(d2) / ar0, q0);
     if (d1 * d2 >= 0.0) return sign * (fa + fb);
     if (fabs(d1) < fabs(d2)) return sign * (fb - fa);
     return sign * (fa - fb);
@@ -216,95 +250,114 @@ struct ExactView {
 
 constexpr int kExactWarps = 4;
 
+// Pixel box of a particle (cpu_backend.py:343-363 / :639-664); false if empty.
+template <typename T>
+__device__ __forceinline__ bool exact_box(const ExactView &v, const T *x, const T *y, const T *h, int64_t p,
+                                          double &xp, double &yp, double &hp, int &i0, int &i1, int &j0, int &j1)
+{
+    xp = (double)__ldg(x + p);
+    yp = (double)__ldg(y + p);
+    hp = (double)__ldg(h + p);
+    if (!(hp > 0.0) || !isfinite(hp) || !isfinite(xp) || !isfinite(yp)) return false;
+    const double rad = 2.0 * hp;
+    const double a0 = floor((xp - rad - v.x_min) / v.pwx), a1 = ceil((xp + rad - v.x_min) / v.pwx);
+    const double b0 = floor((yp - rad - v.y_min) / v.pwy), b1 = ceil((yp + rad - v.y_min) / v.pwy);
+    if (a1 < 0.0 || a0 >= v.nx || b1 < 0.0 || b0 >= v.ny) return false;
+    i0 = (int)fmax(a0, 0.0);
+    i1 = (int)fmin(a1, (double)v.nx);
+    j0 = (int)fmax(b0, 0.0);
+    j1 = (int)fmin(b1, (double)v.ny);
+    return i1 > i0 && j1 > j0;
+}
+
+// Work units: 32 consecutive pixels of one particle's box.  units[p] = number
+// of units of particle p (units[n] = 0 so the exclusive scan leaves the total
+// in units[n]).
+template <typename T>
+__global__ void exact_units_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
+                                   unsigned long long *units)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n) return;
+    unsigned long long c = 0;
+    double xp, yp, hp;
+    int i0, i1, j0, j1;
+    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1))
+        c = (unsigned long long)(((int64_t)(i1 - i0) * (j1 - j0) + 31) / 32);
+    units[p] = c;
+}
+
+// One warp per work unit (grid-stride): the unit's particle is found by binary
+// search in the scanned unit offsets; the lanes take the unit's 32 pixels.
 template <typename T, int NW, bool PROJ3D>
 __global__ void __launch_bounds__(kExactWarps * 32)
 exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
              const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
-             const T *__restrict__ w3, int64_t n, double *o0, double *o1, double *o2, double *o3)
+             const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets, double *o0,
+             double *o1, double *o2, double *o3)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const T *wsrc[4] = {w0, w1, w2, w3};
     double *outs[4] = {o0, o1, o2, o3};
-    const int64_t warps_total = (int64_t)gridDim.x * kExactWarps;
-    for (int64_t base = ((int64_t)blockIdx.x * kExactWarps + warp) * 32; base < n; base += warps_total * 32) {
-        const int64_t p = base + lane;
-        int i0 = 0, i1 = 0, j0 = 0, j1 = 0;
-        double xp = 0, yp = 0, hp = 1, wv[NW];
-#pragma unroll
-        for (int k = 0; k < NW; k++) wv[k] = 0.0;
-        if (p < n) {
-            xp = (double)__ldg(x + p);
-            yp = (double)__ldg(y + p);
-            hp = (double)__ldg(h + p);
-            if (hp > 0.0 && isfinite(hp) && isfinite(xp) && isfinite(yp)) {
-                // cpu_backend.py:343-363 / :639-664
-                const double rad = 2.0 * hp;
-                const double a0 = floor((xp - rad - v.x_min) / v.pwx), a1 = ceil((xp + rad - v.x_min) / v.pwx);
-                const double b0 = floor((yp - rad - v.y_min) / v.pwy), b1 = ceil((yp + rad - v.y_min) / v.pwy);
-                if (!(a1 < 0.0 || a0 >= v.nx || b1 < 0.0 || b0 >= v.ny)) {
-                    i0 = (int)fmax(a0, 0.0);
-                    i1 = (int)fmin(a1, (double)v.nx);
-                    j0 = (int)fmax(b0, 0.0);
-                    j1 = (int)fmin(b1, (double)v.ny);
-                }
-#pragma unroll
-                for (int k = 0; k < NW; k++) wv[k] = (double)__ldg(wsrc[k] + p);
-            }
+    const unsigned long long total = offsets[n];
+    const unsigned long long stride = (unsigned long long)gridDim.x * kExactWarps;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * kExactWarps + warp; u < total; u += stride) {
+        // largest p with offsets[p] <= u
+        int64_t lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (offsets[mid] <= u)
+                lo = mid;
+            else
+                hi = mid;
         }
-        unsigned mask = __ballot_sync(0xffffffffu, i1 > i0 && j1 > j0);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int si0 = __shfl_sync(0xffffffffu, i0, src), si1 = __shfl_sync(0xffffffffu, i1, src);
-            const int sj0 = __shfl_sync(0xffffffffu, j0, src), sj1 = __shfl_sync(0xffffffffu, j1, src);
-            const double sx = __shfl_sync(0xffffffffu, xp, src), sy = __shfl_sync(0xffffffffu, yp, src);
-            const double sh = __shfl_sync(0xffffffffu, hp, src);
-            double sw[NW];
+        const int64_t p = lo;
+        double sx, sy, sh;
+        int si0, si1, sj0, sj1;
+        if (!exact_box(v, x, y, h, p, sx, sy, sh, si0, si1, sj0, sj1)) continue;
+        const int bw = si1 - si0, total_px = bw * (sj1 - sj0);
+        const int e = (int)(u - offsets[p]) * 32 + lane;
+        if (e >= total_px) continue;
+        const int jj = e / bw, ii = e - jj * bw;
+        const int i = si0 + ii, j = sj0 + jj;
+        const double xpix = v.x_min + (i + 0.5) * v.pwx, ypix = v.y_min + (j + 0.5) * v.pwy;
+        const double dx = xpix - sx, dy = ypix - sy;
+        double val;
+        if (PROJ3D) {
+            // cpu_backend.py:673-713
+            const double q2 = (dx * dx + dy * dy) / (sh * sh);
+            if (!(q2 < 4.0 + 3.0 * v.pwx * v.pwy / (sh * sh))) continue;
+            const double pwz = 4.0 * sh;
+            double s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
+            s += ex::surface_int(ypix - sy + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
+            s += ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
+            s += ex::surface_int(xpix - sx + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
+            s += ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
+            // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (:628-629)
+            const double h3 = sh * sh * sh;
+            val = s * (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
+        } else {
+            // cpu_backend.py:365-440: top, left, bottom, right edge
+            double s = ex::line_int(0.5 * v.pwy - dy, 0.5 * v.pwx + dx, 0.5 * v.pwx - dx, sh);
+            s += ex::line_int(0.5 * v.pwx - dx, 0.5 * v.pwy - dy, 0.5 * v.pwy + dy, sh);
+            s += ex::line_int(0.5 * v.pwy + dy, 0.5 * v.pwx - dx, 0.5 * v.pwx + dx, sh);
+            s += ex::line_int(0.5 * v.pwx + dx, 0.5 * v.pwy + dy, 0.5 * v.pwy - dy, sh);
+            // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (:333, :365)
+            val = s * (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
+        }
+        if (val != 0.0) {
 #pragma unroll
-            for (int k = 0; k < NW; k++) sw[k] = __shfl_sync(0xffffffffu, wv[k], src);
-            const int bw = si1 - si0, total = bw * (sj1 - sj0);
-            for (int e = lane; e < total; e += 32) {
-                const int jj = e / bw, ii = e - jj * bw;
-                const int i = si0 + ii, j = sj0 + jj;
-                const double xpix = v.x_min + (i + 0.5) * v.pwx, ypix = v.y_min + (j + 0.5) * v.pwy;
-                const double dx = xpix - sx, dy = ypix - sy;
-                double val;
-                if (PROJ3D) {
-                    // cpu_backend.py:673-713
-                    const double q2 = (dx * dx + dy * dy) / (sh * sh);
-                    if (!(q2 < 4.0 + 3.0 * v.pwx * v.pwy / (sh * sh))) continue;
-                    const double pwz = 4.0 * sh;
-                    double s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
-                    s += ex::surface_int(ypix - sy + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
-                    s += ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
-                    s += ex::surface_int(xpix - sx + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
-                    s += ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
-                    // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (:628-629)
-                    const double h3 = sh * sh * sh;
-                    val = s * (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
-                } else {
-                    // cpu_backend.py:365-440: top, left, bottom, right edge
-                    double s = ex::line_int(0.5 * v.pwy - dy, 0.5 * v.pwx + dx, 0.5 * v.pwx - dx, sh);
-                    s += ex::line_int(0.5 * v.pwx - dx, 0.5 * v.pwy - dy, 0.5 * v.pwy + dy, sh);
-                    s += ex::line_int(0.5 * v.pwy + dy, 0.5 * v.pwx - dx, 0.5 * v.pwx + dx, sh);
-                    s += ex::line_int(0.5 * v.pwx + dx, 0.5 * v.pwy + dy, 0.5 * v.pwy - dy, sh);
-                    // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (:333, :365)
-                    val = s * (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
-                }
-                if (val != 0.0) {
-#pragma unroll
-                    for (int k = 0; k < NW; k++) red_add(outs[k] + (size_t)j * v.nx + i, sw[k] * val);
-                }
-            }
+            for (int k = 0; k < NW; k++)
+                red_add(outs[k] + (size_t)j * v.nx + i, (double)__ldg(wsrc[k] + p) * val);
         }
     }
 }
 
 template <typename T, int NW, bool PROJ3D>
-static int launch_exact(const ExactView &v, const sphb_particles *p, double *const *out, cudaStream_t stream)
+static int launch_exact(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
+                        double *const *out, cudaStream_t stream)
 {
-    int grid = div_up(p->n, kExactWarps * 32);
-    grid = grid < 1 ? 1 : grid > 148 * 16 ? 148 * 16 : grid;
+    const int grid = 148 * 32; // grid-stride over the work units
     const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) {
@@ -313,24 +366,49 @@ static int launch_exact(const ExactView &v, const sphb_particles *p, double *con
     }
     exact_kernel<T, NW, PROJ3D><<<grid, kExactWarps * 32, 0, stream>>>(
         v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), w[0],
-        w[1], w[2], w[3], p->n, o[0], o[1], o[2], o[3]);
+        w[1], w[2], w[3], p->n, offsets, o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }
 
 template <typename T, bool PROJ3D>
-static int exact_nw(const ExactView &v, const sphb_particles *p, double *const *out, cudaStream_t stream)
+static int exact_nw(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
+                    double *const *out, cudaStream_t stream)
 {
     switch (p->n_weights) {
-    case 1: return launch_exact<T, 1, PROJ3D>(v, p, out, stream);
-    case 2: return launch_exact<T, 2, PROJ3D>(v, p, out, stream);
-    case 3: return launch_exact<T, 3, PROJ3D>(v, p, out, stream);
-    default: return launch_exact<T, 4, PROJ3D>(v, p, out, stream);
+    case 1: return launch_exact<T, 1, PROJ3D>(v, p, offsets, out, stream);
+    case 2: return launch_exact<T, 2, PROJ3D>(v, p, offsets, out, stream);
+    case 3: return launch_exact<T, 3, PROJ3D>(v, p, offsets, out, stream);
+    default: return launch_exact<T, 4, PROJ3D>(v, p, offsets, out, stream);
     }
 }
 
+template <typename T>
+static int exact_typed(const ExactView &v, const sphb_particles *p, bool proj3d, double *const *out, void *ws,
+                       size_t ws_bytes, size_t *ws_needed, cudaStream_t stream)
+{
+    const int64_t n = p->n;
+    size_t scan_tmp = 0;
+    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned long long *)nullptr,
+                                            (unsigned long long *)nullptr, n + 1, stream));
+    const size_t off_bytes = align_up(sizeof(unsigned long long) * (size_t)(n + 1), 256);
+    const size_t need = off_bytes + align_up(scan_tmp, 256);
+    if (ws_needed) *ws_needed = need;
+    if (!ws || ws_bytes < need) {
+        set_error("workspace of %zu bytes needed, %zu given", need, ws_bytes);
+        return SPHB_ERR_WORKSPACE;
+    }
+    unsigned long long *offsets = static_cast<unsigned long long *>(ws);
+    void *scan_ws = static_cast<unsigned char *>(ws) + off_bytes;
+    exact_units_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(
+        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), n, offsets);
+    SPHB_LAUNCH_CHECK();
+    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
+    return proj3d ? exact_nw<T, true>(v, p, offsets, out, stream) : exact_nw<T, false>(v, p, offsets, out, stream);
+}
+
 static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d, int accumulate,
-                      double *const *out, cudaStream_t stream)
+                      double *const *out, void *ws, size_t ws_bytes, size_t *ws_needed, cudaStream_t stream)
 {
     if (!p || !r || !out || p->n < 0 || p->n_weights < 1 || p->n_weights > SPHB_MAX_WEIGHTS ||
         (p->dtype != SPHB_F32 && p->dtype != SPHB_F64) || r->nx <= 0 || r->ny <= 0 ||
@@ -347,6 +425,7 @@ static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d
         set_error("missing particle column");
         return SPHB_ERR_ARGUMENT;
     }
+    if (ws_needed) *ws_needed = 0;
     if (!accumulate)
         for (int i = 0; i < p->n_weights; i++)
             SPHB_CUDA(cudaMemsetAsync(out[i], 0, sizeof(double) * (size_t)r->nx * r->ny, stream));
@@ -358,9 +437,8 @@ static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d
     v.y_min = r->y_min;
     v.pwx = (r->x_max - r->x_min) / r->nx;
     v.pwy = (r->y_max - r->y_min) / r->ny;
-    if (p->dtype == SPHB_F32)
-        return proj3d ? exact_nw<float, true>(v, p, out, stream) : exact_nw<float, false>(v, p, out, stream);
-    return proj3d ? exact_nw<double, true>(v, p, out, stream) : exact_nw<double, false>(v, p, out, stream);
+    if (p->dtype == SPHB_F32) return exact_typed<float>(v, p, proj3d, out, ws, ws_bytes, ws_needed, stream);
+    return exact_typed<double>(v, p, proj3d, out, ws, ws_bytes, ws_needed, stream);
 }
 
 } // namespace sphb
@@ -368,13 +446,14 @@ static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d
 using namespace sphb;
 
 extern "C" int sphb_exact2d(const sphb_particles *p, const sphb_raster *r, int accumulate, double *const *out,
-                            sphb_stream stream)
+                            void *ws, size_t ws_bytes, size_t *ws_needed, sphb_stream stream)
 {
-    return exact_impl(p, r, false, accumulate, out, static_cast<cudaStream_t>(stream));
+    return exact_impl(p, r, false, accumulate, out, ws, ws_bytes, ws_needed, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sphb_exact3d_proj(const sphb_particles *p, const sphb_raster *r, int accumulate,
-                                 double *const *out, sphb_stream stream)
+                                 double *const *out, void *ws, size_t ws_bytes, size_t *ws_needed,
+                                 sphb_stream stream)
 {
-    return exact_impl(p, r, true, accumulate, out, static_cast<cudaStream_t>(stream));
+    return exact_impl(p, r, true, accumulate, out, ws, ws_bytes, ws_needed, static_cast<cudaStream_t>(stream));
 }

@@ -251,7 +251,17 @@ def _exact(fn_name, x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
     rast = raster.c()
     with torch.cuda.device(device):
         fn = getattr(_lib.load(), fn_name)
-        _lib.check(fn(ctypes.byref(part), ctypes.byref(rast), 0, _out_ptrs(out), _stream(device)))
+        need = ctypes.c_size_t(0)
+        ws = _workspaces.get(str(device))
+        for _attempt in range(2):
+            rc = fn(ctypes.byref(part), ctypes.byref(rast), 0, _out_ptrs(out),
+                    ctypes.c_void_p(ws.data_ptr()) if ws is not None else None,
+                    ws.numel() if ws is not None else 0, ctypes.byref(need), _stream(device))
+            if rc != _lib.SPHB_ERR_WORKSPACE:
+                break
+            ws = None
+            ws = _workspace(device, need.value)
+        _lib.check(rc)
     return out
 
 

@@ -231,3 +231,67 @@ def test_empty_and_out_of_view(B):
     far = np.array([50.0])
     img = B.interpolate_2d_render(far, far, np.ones(1), np.array([0.1]), k.w, 2, 8, 6, 0, 1, 0, 1, False)
     assert img.shape == (6, 8) and not img.any()
+
+
+def test_four_weights_in_one_walk_and_accumulate(B):
+    """ops level: up to 4 weight columns per footprint walk; accumulate adds to the raster."""
+    import torch
+    from sarracen_b200 import ops
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(11)
+    n = 4000
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    h = np.exp(rng.uniform(np.log(0.004), np.log(0.2), n))
+    ws = [rng.normal(size=n) * h ** 2 for _ in range(4)]
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    r = ops.Raster(70, 45, 0.0, 1.0, 0.1, 0.8)
+    k = _kernel("quartic")
+    outs = ops.scatter2d(t(x), t(y), t(h), [t(w) for w in ws], k.w, 2.5, 2, r)
+    for w, o in zip(ws, outs):
+        ref = OracleBackend.interpolate_2d_render(x, y, w, h, OracleKernel("quartic"), 2.5, 70, 45, 0.0, 1.0, 0.1, 0.8,
+                                                  False)
+        assert_parity(o.cpu().numpy(), ref, TOL64, "4 weights")
+    # second call accumulates into the first output
+    ops.scatter2d(t(x), t(y), t(h), [t(ws[1])], k.w, 2.5, 2, r, out=[outs[0]], accumulate=True)
+    ref = OracleBackend.interpolate_2d_render(x, y, ws[0] + ws[1], h, OracleKernel("quartic"), 2.5, 70, 45, 0.0, 1.0,
+                                              0.1, 0.8, False)
+    assert_parity(outs[0].cpu().numpy(), ref, TOL64, "accumulate")
+
+
+def test_particle_set_is_split_when_the_bin_list_does_not_fit(B, monkeypatch):
+    """A workspace budget too small for the whole bin list forces batches that accumulate."""
+    from sarracen_b200 import ops
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(12)
+    n = 30000
+    x, y, z = rng.uniform(0, 1, (3, n))
+    h = np.exp(rng.uniform(np.log(0.01), np.log(0.15), n))
+    w = rng.uniform(0.1, 1, n) * h ** 3
+    k = _kernel("cubic")
+    ops.release_workspaces()
+    monkeypatch.setattr(ops, "max_workspace_fraction", 4e-6)   # ~ 0.7 MB of a 180 GB device
+    out = B.interpolate_3d_grid(x, y, z, w, h, k.w, 2, 40, 36, 28, 0, 1, 0, 1, 0, 1)
+    monkeypatch.undo()
+    ops.release_workspaces()
+    ref = OracleBackend.interpolate_3d_grid(x, y, z, w, h, OracleKernel("cubic"), 2, 40, 36, 28, 0, 1, 0, 1, 0, 1)
+    assert_parity(out, ref, TOL64, "split batches")
+
+
+def test_mixed_footprints_use_both_paths(B):
+    """h from far below to far above the pixel size: direct path and tile path in one call."""
+    from sarracen_b200 import ops
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(13)
+    n = 20000
+    x, y = rng.uniform(-0.05, 1.05, n), rng.uniform(-0.05, 1.05, n)
+    pw = 1.0 / 300
+    h = np.exp(rng.uniform(np.log(pw / 10), np.log(40 * pw), n))
+    w = rng.uniform(0.1, 1, n) * h ** 2
+    k = _kernel("quintic")
+    for dtype, tol in ((np.float64, TOL64), (np.float32, TOL32)):
+        a = [v.astype(dtype) for v in (x, y, w, h)]
+        out = B.interpolate_2d_render(*a, k.w, 3, 300, 217, 0, 1, 0, 1, False)
+        assert ops.last_stats["n_direct"] > 0 and ops.last_stats["n_pairs"] > 0
+        ref = OracleBackend.interpolate_2d_render(*a, OracleKernel("quintic"), 3, 300, 217, 0, 1, 0, 1, False)
+        assert_parity(out, ref, tol, f"mixed footprints {np.dtype(dtype).name}")
