@@ -101,7 +101,7 @@ class ClockSampler:
     """SM clock and throttle reasons during the timed region, sampled through NVML
     (a light in-process query; spawning nvidia-smi every 200 ms perturbs the run)."""
 
-    def __init__(self, gpu_index, period=0.2):
+    def __init__(self, gpu_index, period=0.5):
         self.period = period
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self.stop_flag = threading.Event()
@@ -134,10 +134,11 @@ class ClockSampler:
     def start(self):
         if self.handle is not None:
             self.thread.start()
+            self.started = True
 
     def stop(self):
         self.stop_flag.set()
-        if self.handle is not None:
+        if getattr(self, "started", False):
             self.thread.join(timeout=3)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
@@ -291,20 +292,25 @@ def run_gpu(args):
         step_device()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phases = {"ms_bin": 0.0, "ms_sort": 0.0, "ms_render": 0.0, "ms_direct": 0.0}
     launches = 0
     e0.record()
+    dbg = []
     for _ in range(args.steps):
+        t_dbg = time.perf_counter()
         step_device()
+        dbg.append(round((time.perf_counter() - t_dbg) * 1e3, 2))
         for k in phases:
             phases[k] += ops.last_stats.get(k, 0.0)
         launches += ops.last_stats.get("launches", 0)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    if os.environ.get("BENCH_DEBUG"):
+        print("per-step host ms:", dbg, file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     n_pairs = ops.last_stats.get("n_pairs", 0)
     n_direct = ops.last_stats.get("n_direct", 0)

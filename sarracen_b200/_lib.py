@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsphb200.so")
+LIB_PATH = os.environ.get("SPHB_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libsphb200.so")
 
 SPHB_MAX_WEIGHTS = 4
 SPHB_F32, SPHB_F64 = 0, 1

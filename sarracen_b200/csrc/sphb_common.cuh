@@ -55,9 +55,10 @@ template <> struct Real2<double> { using type = double2; };
 // Column table as the device sees it: entry i holds (T[i], T[i+1] - T[i]) so
 // one vector load serves the lerp T[i] + f (T[i+1] - T[i]).
 template <typename R> struct LutView {
-    const typename Real2<R>::type *tab;
-    R scale; // (S - 1) / radius
-    int last; // S - 1
+    const typename Real2<R>::type *tab; // this lane's copy: entry i at tab[i << shift]
+    int shift;                          // log2 of the number of interleaved copies
+    R scale;                            // (S - 1) / radius
+    int last;                           // S - 1
 };
 
 // ---- square root -----------------------------------------------------------
@@ -153,7 +154,7 @@ __device__ __forceinline__ R kernel_eval_q2(R q2, const LutView<R> &lut)
         R f;
         int i = floor_nonneg(q * lut.scale, f);
         i = max(0, min(i, lut.last));
-        typename Real2<R>::type e = lut.tab[i];
+        typename Real2<R>::type e = lut.tab[i << lut.shift];
         return fma(f, e.y, e.x);
     } else {
         return kernel_shape<KIND>(q);
@@ -170,7 +171,7 @@ __device__ __forceinline__ R kernel_eval_pos(R q2, const LutView<R> &lut)
         R f;
         int i = floor_nonneg(q * lut.scale, f);
         i = min(i, lut.last);
-        typename Real2<R>::type e = lut.tab[i];
+        typename Real2<R>::type e = lut.tab[i << lut.shift];
         return fma(f, e.y, e.x);
     } else {
         return kernel_shape<KIND>(q);
@@ -188,7 +189,7 @@ __device__ __forceinline__ R kernel_eval_unguarded(R q2, R rad2, const LutView<R
         R f;
         int i = floor_nonneg(q * lut.scale, f);
         i = min(i, lut.last);
-        typename Real2<R>::type e = lut.tab[i];
+        typename Real2<R>::type e = lut.tab[i << lut.shift];
         return fma(f, e.y, e.x);
     } else {
         R w = kernel_shape<KIND>(q);

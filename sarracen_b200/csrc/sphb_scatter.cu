@@ -32,15 +32,14 @@
 
 namespace sphb {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr int kBatch = kThreads;  // particles staged per round, one per thread
+// CTA shape of the tile render kernel: WARPS warps, one staged particle per thread per round.
 constexpr int kChunkPairs = 2048; // sorted pairs per CTA
 
 // Geometry of one call, shared by every kernel of the pipeline.
 struct View {
     int nx, ny, nz;
-    int tx, ty, tz;    // tile size in pixels
+    int tx, ty, tz;    // tile size in pixels (powers of two)
+    int tx_log, ty_log, tz_log;
     int ntx, nty, ntz; // tiles per axis
     double x_min, y_min, z_min;
     double inv_pwx, inv_pwy, inv_pwz;
@@ -93,8 +92,8 @@ __device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const 
         if (!isfinite(zp)) return false;
         pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, lo, hi);
         if (hi <= lo) return false;
-        b.z0 = lo / v.tz;
-        b.z1 = (hi - 1) / v.tz;
+        b.z0 = lo >> v.tz_log;
+        b.z1 = (hi - 1) >> v.tz_log;
         edge = hi - lo;
     } else if (v.use_z) {
         double dz = v.z_slice - (double)__ldg(z + i);
@@ -102,13 +101,13 @@ __device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const 
     }
     pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, lo, hi);
     if (hi <= lo) return false;
-    b.x0 = lo / v.tx;
-    b.x1 = (hi - 1) / v.tx;
+    b.x0 = lo >> v.tx_log;
+    b.x1 = (hi - 1) >> v.tx_log;
     edge = max(edge, hi - lo);
     pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, lo, hi);
     if (hi <= lo) return false;
-    b.y0 = lo / v.ty;
-    b.y1 = (hi - 1) / v.ty;
+    b.y0 = lo >> v.ty_log;
+    b.y1 = (hi - 1) >> v.ty_log;
     edge = max(edge, hi - lo);
     small = edge <= v.small_edge;
     return true;
@@ -127,8 +126,14 @@ count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64
         c = small ? 1
                   : (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) * (uint64_t)(b.z1 - b.z0 + 1);
     if (i <= n) counts[i] = c;
+    // one global atomic per CTA: a per-warp atomic on a single address serialises in L2
+    __shared__ unsigned block_small;
+    if (threadIdx.x == 0) block_small = 0;
+    __syncthreads();
     const unsigned m = __ballot_sync(0xffffffffu, small && c);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_small, (unsigned long long)__popc(m));
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&block_small, (unsigned)__popc(m));
+    __syncthreads();
+    if (threadIdx.x == 0 && block_small) atomicAdd(n_small, (unsigned long long)block_small);
 }
 
 template <typename T>
@@ -170,13 +175,13 @@ __global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t 
 // tile origin subtracted; in float mode the centre is split into the nearest
 // pixel (ic) and a fraction in [-1/2, 1/2] so that position differences keep
 // full float precision however large the raster is.
-template <typename R, int NW> struct Staged {
-    R fx[kBatch], fy[kBatch], fz[kBatch];    // centre (double mode) / fraction (float mode)
-    R sx[kBatch], sy[kBatch], sz[kBatch];    // (pixel width / h)^2 per axis
-    R c[kBatch];                             // dz^2 / h^2 of a cross-section, else 0
-    R term[NW][kBatch];                      // norm * w / h^ndim
-    int cx[kBatch], cy[kBatch], cz[kBatch];  // nearest pixel (float mode), else 0
-    uint32_t bx[kBatch], by[kBatch], bz[kBatch]; // footprint box ∩ tile: lo | hi << 16
+template <typename R, int NW, int BATCH> struct Staged {
+    R fx[BATCH], fy[BATCH], fz[BATCH];    // centre (double mode) / fraction (float mode)
+    R sx[BATCH], sy[BATCH], sz[BATCH];    // (pixel width / h)^2 per axis
+    R c[BATCH];                             // dz^2 / h^2 of a cross-section, else 0
+    R term[NW][BATCH];                      // norm * w / h^ndim
+    int cx[BATCH], cy[BATCH], cz[BATCH];  // nearest pixel (float mode), else 0
+    uint32_t bx[BATCH], by[BATCH], bz[BATCH]; // footprint box ∩ tile: lo | hi << 16
 };
 
 template <typename R> struct Split;
@@ -221,16 +226,17 @@ __device__ __forceinline__ void add_contribution(R q2, R rad2, const LutView<R> 
 //          power of two >= box width, and accumulate into the warp's part of the
 //          shared-memory tile (plain load / fma / store).
 // Registers and shared memory are merged when the tile segment is flushed.
-template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
               const T *__restrict__ h, const T *__restrict__ w0, const T *__restrict__ w1,
               const T *__restrict__ w2, const T *__restrict__ w3, const double *__restrict__ lut,
-              int lut_samples, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-              const uint32_t *__restrict__ tile_end, int64_t n_pairs, double *o0, double *o1, double *o2,
-              double *o3)
+              int lut_samples, int lut_copies_log, const uint32_t *__restrict__ keys,
+              const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_end, int64_t n_pairs,
+              double *o0, double *o1, double *o2, double *o3)
 {
     using R2 = typename Real2<R>::type;
+    constexpr int kWarps = WARPS, kThreads = WARPS * 32, kBatch = kThreads;
     constexpr int SX = TX + 8;                    // padded row stride
     constexpr int PLANE = SX * TY;                // elements per z-plane
     constexpr int ACC = PLANE * TZ;               // elements per weight
@@ -243,26 +249,34 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *acc = reinterpret_cast<R *>(smem_raw);
-    Staged<R, NW> *st = reinterpret_cast<Staged<R, NW> *>(acc + (size_t)ACC * NW);
+    Staged<R, NW, kBatch> *st = reinterpret_cast<Staged<R, NW, kBatch> *>(acc + (size_t)ACC * NW);
     R2 *lut_s = reinterpret_cast<R2 *>(st + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const T *wsrc[4] = {w0, w1, w2, w3};
     double *outs[4] = {o0, o1, o2, o3};
 
+    // The column table is replicated 2^lut_copies_log times, entry i of copy c at
+    // slot (i << log) + c, and a lane reads copy (lane mod copies): with 8 copies of
+    // 16-byte entries (16 copies of 8-byte entries) every lane of a shared-memory
+    // access phase owns its own bank group, so the random table index causes no bank
+    // conflicts.
     LutView<R> lv;
-    lv.tab = lut_s;
+    lv.tab = lut_s + (lane & ((1 << lut_copies_log) - 1));
+    lv.shift = lut_copies_log;
     lv.scale = R(0);
     lv.last = 0;
     if (KIND == SPHB_COLUMN_LUT) {
-        for (int i = tid; i < lut_samples; i += kThreads) {
+        const int slots = lut_samples << lut_copies_log;
+        for (int j = tid; j < slots; j += kThreads) {
+            const int i = j >> lut_copies_log;
             double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
             R2 e;
             e.x = (R)a;
             e.y = (R)(b - a);
             // the clamp target of out-of-support lookups: W(q >= R) = 0
             if (i == lut_samples - 1) e.x = e.y = R(0);
-            lut_s[i] = e;
+            lut_s[j] = e;
         }
         lv.scale = (R)((double)(lut_samples - 1) / v.radius);
         lv.last = lut_samples - 1;
@@ -386,7 +400,10 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                         R q2 = fma(dy0 * dy0, sy, qx);
                         R d1 = sy * fma(R(2 * RI), dy0, R(RI * RI));
                         const R d2 = sy * R(2 * RI * RI);
-                        constexpr int G = K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1);
+                        #ifndef SPHB_ROW_GROUP
+#define SPHB_ROW_GROUP 4
+#endif
+                        constexpr int G = K % SPHB_ROW_GROUP == 0 ? SPHB_ROW_GROUP : (K % 2 == 0 ? 2 : 1);
 #pragma unroll
                         for (int r0 = 0; r0 < K; r0 += G) {
                             R q[G];
@@ -492,8 +509,9 @@ template <typename R, int NW> struct DirectRec {
     R sx[32], sy[32], sz[32];
     R cq[32];                 // dz^2 / h^2 of a cross-section + sqrt guard
     R term[NW][32];
-    int ox[32], oy[32], oz[32]; // box origin in raster pixels
-    uint32_t dims[32];        // wx | wy << 8 | wz << 16 ; 0 = nothing to do
+    unsigned long long base[32]; // raster offset of the box origin
+    uint32_t inv_wx[32];         // 65536 / wx + 1
+    uint32_t dims[32];           // wx | wy << 8 | wz << 16 ; 0 = nothing to do
 };
 
 template <typename T, typename R, int KIND, int NW, bool DIM3>
@@ -515,6 +533,7 @@ direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
 
     LutView<R> lv;
     lv.tab = lut_s;
+    lv.shift = 0;
     lv.scale = R(0);
     lv.last = 0;
     if (KIND == SPHB_COLUMN_LUT) {
@@ -566,10 +585,9 @@ direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                 const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
 #pragma unroll
                 for (int k = 0; k < NW; k++) rec.term[k][lane] = (R)((double)__ldg(wsrc[k] + p) * scale);
-                rec.ox[lane] = x0;
-                rec.oy[lane] = y0;
-                rec.oz[lane] = z0;
+                rec.base[lane] = ((unsigned long long)z0 * v.ny + (unsigned long long)y0) * v.nx + x0;
                 const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
+                rec.inv_wx[lane] = 65536u / (unsigned)max(wx, 1) + 1u;
                 if (wx > 0 && wy > 0 && wz > 0) {
                     dims = (uint32_t)wx | ((uint32_t)wy << 8) | ((uint32_t)wz << 16);
                     area = wx * wy;
@@ -591,7 +609,6 @@ direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
             const uint32_t dims = rec.dims[s];
             if (dims) {
                 const int wx = (int)(dims & 0xff), wy = (int)((dims >> 8) & 0xff), wz = (int)(dims >> 16);
-                const int x0 = rec.ox[s], y0 = rec.oy[s], z0 = rec.oz[s];
                 const R fx = rec.fx[s], fy = rec.fy[s], sx = rec.sx[s], sy = rec.sy[s], cq = rec.cq[s];
                 R fz = R(0), sz = R(0);
                 if (DIM3) {
@@ -601,12 +618,13 @@ direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                 R term[NW];
 #pragma unroll
                 for (int k = 0; k < NW; k++) term[k] = rec.term[k][s];
-                const unsigned inv_wx = 65536u / (unsigned)wx + 1u;
+                const unsigned inv_wx = rec.inv_wx[s];
+                const unsigned long long base_o = rec.base[s];
                 for (int e = sub; e < wx * wy; e += lpp) {
                     const int iy = (int)(((unsigned)e * inv_wx) >> 16), ix = e - iy * wx;
                     const R dx = int_to_real(ix, R(0)) - fx, dy = int_to_real(iy, R(0)) - fy;
                     const R qxy = fma(dy * dy, sy, fma(dx * dx, sx, cq));
-                    const size_t o = ((size_t)z0 * v.ny + (size_t)(y0 + iy)) * v.nx + (size_t)(x0 + ix);
+                    const size_t o = (size_t)base_o + (size_t)(iy * v.nx + ix);
                     if (DIM3) {
                         // q^2 along z by second differences
                         R q2 = fma(fz * fz, sz, qxy);
@@ -651,18 +669,33 @@ struct Workspace {
     }
 };
 
-template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ>
+template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
 static int launch_render(const View &v, const sphb_particles *p, const sphb_kernel *k, const uint32_t *keys,
                          const uint32_t *vals, const uint32_t *tile_end, int64_t n_pairs,
                          double *const *out, cudaStream_t stream)
 {
     using R2 = typename Real2<R>::type;
-    auto kern = render_kernel<T, R, KIND, NW, DIM3, TX, TY, TZ>;
-    size_t smem = sizeof(R) * (size_t)(TX + 8) * TY * TZ * NW + sizeof(Staged<R, NW>);
-    if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
-    if (smem > 227 * 1024) {
-        set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
-        return SPHB_ERR_ARGUMENT;
+    auto kern = render_kernel<T, R, KIND, NW, DIM3, TX, TY, TZ, WARPS>;
+    const size_t fixed = sizeof(R) * (size_t)(TX + 8) * TY * TZ * NW + sizeof(Staged<R, NW, WARPS * 32>);
+    const size_t limit = 227 * 1024;
+    size_t smem = fixed;
+    int copies_log = 0;
+    if (KIND == SPHB_COLUMN_LUT) {
+        const size_t one = sizeof(R2) * (size_t)k->lut_samples;
+        if (fixed + one > limit) {
+            set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
+            return SPHB_ERR_ARGUMENT;
+        }
+        // as many copies as fit, up to one bank group per lane of an access phase (128 B / entry)
+        // Replicating the table (one bank group per lane) was measured on config 2: 1, 2, 4, 8
+        // copies -> 124, 127, 145, 216 ms (8 warps / CTA) because every doubling costs a
+        // resident CTA, and 147 vs 148 ms with 16-warp CTAs: the random table index is not the
+        // bottleneck, occupancy is worth more.  SPHB_LUT_COPIES_LOG re-enables it for experiments.
+        int max_log = 0;
+        if (const char *e = getenv("SPHB_LUT_COPIES_LOG")) max_log = atoi(e) < 4 ? atoi(e) : 4;
+        if (sizeof(R2) == 16 && max_log > 3) max_log = 3;
+        while (copies_log < max_log && fixed + (one << (copies_log + 1)) <= limit) copies_log++;
+        smem += one << copies_log;
     }
     SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = div_up(n_pairs, kChunkPairs);
@@ -672,10 +705,10 @@ static int launch_render(const View &v, const sphb_particles *p, const sphb_kern
         w[i] = static_cast<const T *>(p->w[i]);
         o[i] = out[i];
     }
-    kern<<<grid, kThreads, smem, stream>>>(v, static_cast<const T *>(p->x), static_cast<const T *>(p->y),
-                                           static_cast<const T *>(p->z), static_cast<const T *>(p->h),
-                                           w[0], w[1], w[2], w[3], k->lut, k->lut_samples, keys, vals,
-                                           tile_end, n_pairs, o[0], o[1], o[2], o[3]);
+    kern<<<grid, WARPS * 32, smem, stream>>>(v, static_cast<const T *>(p->x), static_cast<const T *>(p->y),
+                                             static_cast<const T *>(p->z), static_cast<const T *>(p->h),
+                                             w[0], w[1], w[2], w[3], k->lut, k->lut_samples, copies_log, keys,
+                                             vals, tile_end, n_pairs, o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }
@@ -730,28 +763,29 @@ template <typename T, typename R, bool DIM3, typename... A> static int direct_ki
     }
 }
 
-template <typename T, typename R, int KIND, bool DIM3, int TX, int TY, int TZ, typename... A>
+template <typename T, typename R, int KIND, bool DIM3, int TX, int TY, int TZ, int WARPS, typename... A>
 static int dispatch_nw(int nw, A &&...a)
 {
     switch (nw) {
-    case 1: return launch_render<T, R, KIND, 1, DIM3, TX, TY, TZ>(a...);
-    case 2: return launch_render<T, R, KIND, 2, DIM3, TX, TY, TZ>(a...);
-    case 3: return launch_render<T, R, KIND, 3, DIM3, TX, TY, TZ>(a...);
-    default: return launch_render<T, R, KIND, 4, DIM3, TX, TY, TZ>(a...);
+    case 1: return launch_render<T, R, KIND, 1, DIM3, TX, TY, TZ, WARPS>(a...);
+    case 2: return launch_render<T, R, KIND, 2, DIM3, TX, TY, TZ, WARPS>(a...);
+    case 3: return launch_render<T, R, KIND, 3, DIM3, TX, TY, TZ, WARPS>(a...);
+    default: return launch_render<T, R, KIND, 4, DIM3, TX, TY, TZ, WARPS>(a...);
     }
 }
 
-template <typename T, typename R, bool DIM3, int TX, int TY, int TZ, typename... A>
+template <typename T, typename R, bool DIM3, int TX, int TY, int TZ, int WARPS, typename... A>
 static int dispatch_kind(int kind, int nw, A &&...a)
 {
     switch (kind) {
-    case SPHB_CUBIC: return dispatch_nw<T, R, SPHB_CUBIC, DIM3, TX, TY, TZ>(nw, a...);
-    case SPHB_QUARTIC: return dispatch_nw<T, R, SPHB_QUARTIC, DIM3, TX, TY, TZ>(nw, a...);
-    case SPHB_QUINTIC: return dispatch_nw<T, R, SPHB_QUINTIC, DIM3, TX, TY, TZ>(nw, a...);
-    default: return dispatch_nw<T, R, SPHB_COLUMN_LUT, DIM3, TX, TY, TZ>(nw, a...);
+    case SPHB_CUBIC: return dispatch_nw<T, R, SPHB_CUBIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
+    case SPHB_QUARTIC: return dispatch_nw<T, R, SPHB_QUARTIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
+    case SPHB_QUINTIC: return dispatch_nw<T, R, SPHB_QUINTIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
+    default: return dispatch_nw<T, R, SPHB_COLUMN_LUT, DIM3, TX, TY, TZ, WARPS>(nw, a...);
     }
 }
 
+// 2-D tiles: 32 x 64 pixels, 8 warps with an 8-row strip each (16 warps on 32 x 128 measured 20 % slower).
 constexpr int kTile2X = 32, kTile2Y = 64;
 
 // Footprint boxes up to this many pixels per edge take the direct path.  The
@@ -828,6 +862,10 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     v.tx = dim3 ? kTile3X : kTile2X;
     v.ty = dim3 ? kTile3Y : kTile2Y;
     v.tz = dim3 ? kTile3Z : 1;
+    auto ilog2 = [](int t) { int l = 0; while ((1 << l) < t) l++; return l; };
+    v.tx_log = ilog2(v.tx);
+    v.ty_log = ilog2(v.ty);
+    v.tz_log = ilog2(v.tz);
     v.ntx = div_up(v.nx, v.tx);
     v.nty = div_up(v.ny, v.ty);
     v.ntz = div_up(v.nz, v.tz);
@@ -964,18 +1002,18 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     if (n_large > 0) {
         if (dim3) {
             if (f32)
-                rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z>(
+                rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z, 8>(
                     k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_large, out, stream);
             else
-                rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z>(
+                rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z, 8>(
                     k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_large, out, stream);
         } else {
             if (f32)
-                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
-                                                                        vals_b, tile_end, n_large, out, stream);
+                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, p, k, keys_b,
+                                                                           vals_b, tile_end, n_large, out, stream);
             else
-                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1>(k->kind, p->n_weights, v, p, k, keys_b,
-                                                                         vals_b, tile_end, n_large, out, stream);
+                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, p, k, keys_b,
+                                                                            vals_b, tile_end, n_large, out, stream);
         }
         if (rc) return rc;
     }
