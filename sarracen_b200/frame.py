@@ -1,0 +1,67 @@
+"""`ParticleFrame`: the slice of `SarracenDataFrame` the interpolation front-end needs.
+
+The front-end (`sarracen_b200.interpolate`) only reads a handful of attributes of
+the dataframe it is given: the special column labels, `params`, `kernel`,
+`backend`, `get_dim()` and `centre_of_mass()`
+(sarracen/sarracen_dataframe.py:130-195, :286-311, :573-760).  A real
+`SarracenDataFrame` provides them; `ParticleFrame` provides the same surface for
+users (and tests) that do not have Sarracen installed.  It is pandas glue, not
+compute: readers, writers, plotting and unit handling are out of scope.
+"""
+from typing import Optional
+
+import pandas as pd
+
+from .kernels import BaseKernel, CubicSplineKernel
+
+
+class ParticleFrame(pd.DataFrame):
+    _metadata = ["params", "xcol", "ycol", "zcol", "hcol", "mcol", "rhocol", "vxcol", "vycol", "vzcol",
+                 "_kernel", "backend"]
+
+    def __init__(self, data=None, params: Optional[dict] = None, *args, **kwargs):
+        super().__init__(data, *args, **kwargs)
+        self.params = dict(params or {})
+        self.xcol = self.ycol = self.zcol = None
+        self.hcol = self.mcol = self.rhocol = None
+        self.vxcol = self.vycol = self.vzcol = None
+        self._identify_special_columns()
+        self._kernel = CubicSplineKernel()
+        self.backend = "gpu"
+
+    @property
+    def _constructor(self):
+        return ParticleFrame
+
+    def _identify_special_columns(self) -> None:
+        """Same detection rules as sarracen_dataframe.py:130-195."""
+        cols = list(self.columns)
+        self.xcol = "x" if "x" in cols else "rx" if "rx" in cols else (str(cols[0]) if cols else None)
+        self.ycol = "y" if "y" in cols else "ry" if "ry" in cols else (str(cols[1]) if len(cols) > 1 else None)
+        self.zcol = "z" if "z" in cols else "rz" if "rz" in cols else None
+        self.hcol = "h" if "h" in cols else None
+        self.mcol = "m" if "m" in cols else "mass" if "mass" in cols else None
+        self.rhocol = "rho" if "rho" in cols else "density" if "density" in cols else None
+        self.vxcol = "vx" if "vx" in cols else None
+        self.vycol = "vy" if "vy" in cols else None
+        self.vzcol = "vz" if "vz" in cols else None
+
+    @property
+    def kernel(self) -> BaseKernel:
+        return self._kernel
+
+    @kernel.setter
+    def kernel(self, new_kernel: BaseKernel) -> None:
+        if not isinstance(new_kernel, BaseKernel):
+            raise TypeError("Kernel is an incorrect type.")
+        self._kernel = new_kernel
+
+    def get_dim(self) -> int:
+        return 3 if self.zcol is not None else 2
+
+    def centre_of_mass(self) -> list:
+        """sarracen_dataframe.py:286-311."""
+        mass = self[self.mcol] if self.mcol in self.columns else self.params["mass"]
+        com = [(self[c] * mass).sum() for c in (self.xcol, self.ycol, self.zcol)]
+        inv = 1.0 / mass.sum() if isinstance(mass, pd.Series) else 1.0 / (len(self) * mass)
+        return [c * inv for c in com]
