@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time the BASELINE.json configs that are not bench.py's headline lines (configs 0, 2, 4 of the
 list: 2-D render, cross-section + vector render, exact paths) on one GPU, device-resident, CUDA
-events, 2 warm-ups + 3 timed runs; writes profiles/r1_other_configs.json.
+events, 2 warm-ups + 3 timed runs; writes gpurun_out/other_configs.json (copied to profiles/ by hand).
 
     python profiles/measure_configs.py [--quick]
 """
@@ -104,4 +104,5 @@ for name, n_full, fn in (("exact2d", 1 << 23, ops.exact2d), ("exact3d_proj", 1 <
     bbox = float(np.mean((np.ceil(4 * h / pw) + 1) ** 2))
     record(f"cfg5 {name} 1024^2 cubic f64", n, ms, mean_bbox_pixels=bbox, wall_s=time.perf_counter() - t0)
 
-json.dump(results, open(os.path.join(ROOT, "profiles", "r1_other_configs.json"), "w"), indent=1)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(results, open(os.path.join(ROOT, "gpurun_out", "other_configs.json"), "w"), indent=1)

@@ -141,6 +141,8 @@ class _Device:
     def col(self, name: str) -> torch.Tensor:
         if name not in self.cache:
             arr = np.ascontiguousarray(self.data[name].to_numpy())
+            if not arr.flags.writeable:  # pandas copy-on-write views; torch wants a writable buffer
+                arr = arr.copy()
             self.cache[name] = torch.from_numpy(arr).to(self.dev).to(self.dtype).contiguous()
         return self.cache[name]
 
