@@ -392,8 +392,7 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                         // selected to 0), so no box tests are needed.  q^2 runs down
                         // the lane's rows by second differences.  Rows are handled G at
                         // a time without branches so the G dependent square-root /
-                        // table chains overlap; a group with no lane inside the support
-                        // is skipped by a warp vote.
+                        // table chains overlap; groups that cannot contribute are skipped.
                         const R dx = int_to_real(lx - cx, R(0)) - fx;
                         const R qx = fma(dx * dx, sx, cc) + sqrt_guard(R(0));
                         const R dy0 = int_to_real(own_y0 + ly - cy, R(0)) - fy;
@@ -411,11 +410,21 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
 #pragma unroll
                             for (int j = 0; j < G; j++) {
                                 q[j] = q2;
-                                any = any || (q2 < rad2);
+                                if (sizeof(R) == 4) any = any || (q2 < rad2);
                                 q2 += d1;
                                 d1 += d2;
                             }
-                            if (__any_sync(0xffffffffu, any)) {
+                            // Skip a group that cannot contribute.  double: rows that miss the
+                            // footprint box (warp-uniform integer test; a DSETP per row costs more
+                            // than the rare all-outside group).  float: exact warp vote on q^2
+                            // (comparisons are cheap there, skipped corners are not).  Measured on
+                            // config 2: 124 -> 117 ms (double), 78 vs 83 ms (float).
+                            bool live;
+                            if (sizeof(R) == 4)
+                                live = __any_sync(0xffffffffu, any);
+                            else
+                                live = own_y0 + r0 * RI < y1 && own_y0 + (r0 + G) * RI > y0;
+                            if (live) {
 #pragma unroll
                                 for (int j = 0; j < G; j++) {
                                     const R wv = kernel_eval_unguarded<KIND, R>(q[j], rad2, lv);
