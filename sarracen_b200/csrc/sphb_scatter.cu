@@ -27,6 +27,9 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "sphb_common.cuh"
 
@@ -672,6 +675,48 @@ direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
 // ---------------------------------------------------------------------------
 // Host side.
 
+// Opt a kernel in to the full 227 KB of dynamic shared memory, once per instantiation and
+// device (driver calls per launch are kept to a minimum: they serialise with other
+// driver clients such as NVML monitors).
+template <typename K> static cudaError_t allow_large_smem(K kern)
+{
+    // keyed by (device, kernel address): instantiations share their function-pointer type
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const std::pair<int, const void *> key(dev, reinterpret_cast<const void *>(kern));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (done.count(key)) return cudaSuccess;
+    }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(mu);
+        done.insert(key);
+    }
+    return e;
+}
+
+// Timing events are created once per host thread and device and reused.
+static cudaError_t phase_events(cudaEvent_t *ev, int count)
+{
+    static thread_local cudaEvent_t cache[64][8] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || count > 8) return cudaErrorInvalidValue;
+    for (int i = 0; i < count; i++) {
+        if (!cache[dev][i]) {
+            e = cudaEventCreate(&cache[dev][i]);
+            if (e != cudaSuccess) return e;
+        }
+        ev[i] = cache[dev][i];
+    }
+    return cudaSuccess;
+}
+
 struct Workspace {
     unsigned char *base;
     size_t used;
@@ -713,7 +758,7 @@ static int launch_render(const View &v, const sphb_particles *p, const sphb_kern
         while (copies_log < max_log && fixed + (one << (copies_log + 1)) <= limit) copies_log++;
         smem += one << copies_log;
     }
-    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPHB_CUDA(allow_large_smem(kern));
     const int grid = div_up(n_pairs, kChunkPairs);
     const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -741,7 +786,7 @@ static int launch_direct(const View &v, const sphb_particles *p, const sphb_kern
         set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
         return SPHB_ERR_ARGUMENT;
     }
-    SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPHB_CUDA(allow_large_smem(kern));
     int grid = div_up(n_small, kDirectWarps * 32);
     grid = grid > 148 * 64 ? 148 * 64 : grid;
     const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -928,16 +973,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         stats->n_direct = 0;
         stats->launches = 0;
     }
-    struct EventGuard {
-        cudaEvent_t *e;
-        ~EventGuard()
-        {
-            for (int i = 0; i < 5; i++)
-                if (e[i]) cudaEventDestroy(e[i]);
-        }
-    } guard{ev};
-    if (timed)
-        for (int i = 0; i < 5; i++) SPHB_CUDA(cudaEventCreate(&ev[i]));
+    if (timed) SPHB_CUDA(phase_events(ev, 5));
     if (ws_needed) *ws_needed = 0;
     if (n == 0) return SPHB_OK;
 

@@ -155,9 +155,7 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
     launches = 0
     with torch.cuda.device(device):
         stream = _stream(device)
-        free, _total = torch.cuda.mem_get_info(device)
-        held = _workspaces[str(device)].numel() if str(device) in _workspaces else 0
-        budget = int((free + held) * max_workspace_fraction)
+        budget = None  # worked out only if the workspace has to grow
         todo = [(0, n)]
         done_any = False
         while todo:
@@ -177,6 +175,10 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
                     rc = lib.sphb_scatter2d(ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast),
                                             1 if use_z else 0, float(z_slice), acc, optr, wptr, wlen,
                                             ctypes.byref(need), ctypes.byref(stats), stream)
+                if rc == _lib.SPHB_ERR_WORKSPACE and budget is None:
+                    free, _total = torch.cuda.mem_get_info(device)
+                    held = _workspaces[str(device)].numel() if str(device) in _workspaces else 0
+                    budget = int((free + held) * max_workspace_fraction)
                 if rc == _lib.SPHB_ERR_WORKSPACE and need.value <= budget:
                     ws = None  # drop our reference so the old buffer is freed before growing
                     ws = _workspace(device, need.value)
