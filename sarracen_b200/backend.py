@@ -97,7 +97,18 @@ def _to_device(arrays, device):
     return out
 
 
+_PINNED_MIN, _PINNED_MAX = 8 << 20, 4 << 30
+
+
 def _host(t: torch.Tensor) -> np.ndarray:
+    """Device raster -> new host ndarray.  Large rasters land in page-locked memory from torch's
+    caching host allocator (a plain ndarray to the caller; the block is recycled when the array
+    is released): the copy then runs at PCIe speed instead of through pageable bounce buffers."""
+    nbytes = t.numel() * t.element_size()
+    if _PINNED_MIN <= nbytes <= _PINNED_MAX:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t)
+        return host.numpy()
     return t.cpu().numpy()
 
 

@@ -249,7 +249,8 @@ def _finish(grids: List[torch.Tensor], norm: Optional[torch.Tensor]) -> List[np.
     if norm is not None:
         for g in grids:
             ops.normalize_(g, norm)
-    return [g.cpu().numpy() for g in grids]
+    from .backend import _host
+    return [_host(g) for g in grids]
 
 
 def _image(dv, x_t, y_t, h_t, weights, wf, radius, ndim, raster, exact, exact_fn, z_t=None, z_slice=None):
