@@ -364,6 +364,22 @@ def run_gpu(args):
 
     base = cpu_baseline(wl) if not args.no_cpu else None
 
+    # What bounds the dominant kernel in practice: at SPH-consistent smoothing
+    # lengths the per-contribution arithmetic, not HBM.  Instruction counts per contribution are read
+    # off the SASS of the hot loops (profiles/); peak = 148 SMs x 64 FP64 (128 FP32) lanes x SM clock.
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    rate = contrib / (ms_render * 1e-3) if ms_render > 0 else 0.0
+    if args.dtype == "f64":
+        dp_per = 15.0 if dom == "ms_render" else 16.0
+        compute = {"bound": "fp64 pipe + issue slots", "fp64_inst_per_contribution_est": dp_per,
+                   "achieved_fp64_inst_per_s": rate * dp_per, "peak_fp64_inst_per_s": 148 * 64 * sm_clock * 1e6,
+                   "frac_est": rate * dp_per / (148 * 64 * sm_clock * 1e6)}
+    else:
+        per = 30.0
+        compute = {"bound": "issue slots", "inst_per_contribution_est": per,
+                   "achieved_inst_per_s": rate * per, "peak_inst_per_s": 148 * 128 * sm_clock * 1e6,
+                   "frac_est": rate * per / (148 * 128 * sm_clock * 1e6)}
+
     line = {
         "metric": "particles/sec", "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -381,6 +397,7 @@ def run_gpu(args):
                      "kernel": "render_kernel" if dom == "ms_render" else "direct_kernel",
                      "alg_bytes": wl["alg_bytes"], "peak_source": peak_src,
                      "whole_step_frac": wl["alg_bytes"] / (ms_step * 1e-3) / 1e9 / peak},
+        "compute_bound": compute,
         "cpu_baseline": base,
         "e2e": {"value": wl["n"] * world / t_e2e, "unit": "particles/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3},
