@@ -53,9 +53,55 @@ struct View {
     int dim3;  // voxel raster
     int ndim;  // exponent of h in the particle term
     double norm;
+    int rec_stride;    // elements per packed particle record (4 or 8)
     int small_edge;    // footprint boxes with every edge <= this many pixels take the direct path
     uint32_t flag_bit; // key bit that marks a direct-path particle (sorts after all tile pairs)
 };
+
+// Packed particle record, written once per call by the emit kernel (which streams the
+// columns anyway) so that the render kernels fetch one particle with one or two 16-byte
+// loads from a single place instead of one 8-byte gather per column -- every random gather
+// costs a full DRAM burst, and the sorted lists visit particles in random order.
+//   stride 4 elements: { x, y, h, w0 }                    (no depth column, one weight)
+//   stride 6 elements: { x, y, h, z, w0, w1 }             (double only, up to two weights)
+//   stride 8 elements: { x, y, h, z, w0, w1, w2, w3 }
+template <typename T> struct Rec {
+    T x, y, h, z, w[4];
+};
+
+template <typename T>
+__device__ __forceinline__ Rec<T> load_rec(const T *__restrict__ recs, int stride, int64_t p, int nw)
+{
+    Rec<T> r;
+    const T *b = recs + (size_t)p * stride;
+    if (sizeof(T) == 8) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(b));
+        const double2 c = __ldg(reinterpret_cast<const double2 *>(b) + 1);
+        r.x = (T)a.x; r.y = (T)a.y; r.h = (T)c.x;
+        if (stride == 4) {
+            r.z = T(0); r.w[0] = (T)c.y;
+        } else {
+            r.z = (T)c.y;
+            const double2 d = __ldg(reinterpret_cast<const double2 *>(b) + 2);
+            r.w[0] = (T)d.x; r.w[1] = (T)d.y;
+            if (stride == 8 && nw > 2) {
+                const double2 e = __ldg(reinterpret_cast<const double2 *>(b) + 3);
+                r.w[2] = (T)e.x; r.w[3] = (T)e.y;
+            }
+        }
+    } else {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(b));
+        r.x = (T)a.x; r.y = (T)a.y; r.h = (T)a.z;
+        if (stride == 4) {
+            r.z = T(0); r.w[0] = (T)a.w;
+        } else {
+            r.z = (T)a.w;
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(b) + 1);
+            r.w[0] = (T)d.x; r.w[1] = (T)d.y; r.w[2] = (T)d.z; r.w[3] = (T)d.w;
+        }
+    }
+    return r;
+}
 
 struct TileBox {
     int x0, x1, y0, y1, z0, z1; // tile index ranges, inclusive
@@ -141,14 +187,32 @@ count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n,
-                  const uint64_t *offsets, uint32_t *keys, uint32_t *vals)
+emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0, const T *w1,
+                  const T *w2, const T *w3, int nw, int64_t n, const uint64_t *offsets, uint32_t *keys,
+                  uint32_t *vals, T *recs)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     TileBox b;
     bool small;
     if (!particle_tiles(v, x, y, z, h, i, b, small)) return;
+    {
+        T *r = recs + (size_t)i * v.rec_stride;
+        r[0] = x[i];
+        r[1] = y[i];
+        r[2] = h[i];
+        if (v.rec_stride == 4) {
+            r[3] = w0[i];
+        } else {
+            r[3] = z ? z[i] : T(0);
+            r[4] = w0[i];
+            r[5] = nw > 1 ? w1[i] : T(0);
+            if (v.rec_stride == 8) {
+                r[6] = nw > 2 ? w2[i] : T(0);
+                r[7] = nw > 3 ? w3[i] : T(0);
+            }
+        }
+    }
     uint64_t o = offsets[i];
     if (small) {
         keys[o] = (uint32_t)((b.z0 * v.nty + b.y0) * v.ntx + b.x0) | v.flag_bit;
@@ -238,10 +302,8 @@ template <typename R, bool DIM3, int WARPS> struct RenderBatch {
 
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 1) ? 2 : 4)
-render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-              const T *__restrict__ h, const T *__restrict__ w0, const T *__restrict__ w1,
-              const T *__restrict__ w2, const T *__restrict__ w3, const double *__restrict__ lut,
-              int lut_samples, int lut_copies_log, const uint32_t *__restrict__ keys,
+render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
+              int lut_copies_log, const uint32_t *__restrict__ keys,
               const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_end, int64_t n_pairs,
               double *o0, double *o1, double *o2, double *o3)
 {
@@ -263,7 +325,6 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
     R2 *lut_s = reinterpret_cast<R2 *>(st + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const T *wsrc[4] = {w0, w1, w2, w3};
     double *outs[4] = {o0, o1, o2, o3};
 
     // The column table is replicated 2^lut_copies_log times, entry i of copy c at
@@ -324,8 +385,9 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
             // ---- stage: one particle per thread --------------------------------
             if (tid < nb) {
                 const int64_t p = vals[base + tid];
-                const double hp = (double)__ldg(h + p);
-                const double xp = (double)__ldg(x + p), yp = (double)__ldg(y + p);
+                const Rec<T> pr = load_rec<T>(recs, v.rec_stride, p, NW);
+                const double hp = (double)pr.h;
+                const double xp = (double)pr.x, yp = (double)pr.y;
                 const double rad = v.radius * hp;
                 const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
                 int lo, hi;
@@ -346,7 +408,7 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                 st->sy[tid] = (R)(v.pwy * v.pwy * hinv2);
                 double cc = 0.0;
                 if (DIM3) {
-                    const double zp = (double)__ldg(z + p);
+                    const double zp = (double)pr.z;
                     const double uz = (zp - v.z_min) * v.inv_pwz - 0.5 - oz;
                     pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, lo, hi);
                     lo = max(lo - oz, 0);
@@ -355,13 +417,13 @@ render_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                     Split<R>::apply(uz, st->fz[tid], st->cz[tid]);
                     st->sz[tid] = (R)(v.pwz * v.pwz * hinv2);
                 } else if (v.use_z) {
-                    const double dz = v.z_slice - (double)__ldg(z + p);
+                    const double dz = v.z_slice - (double)pr.z;
                     cc = dz * dz * hinv2;
                 }
                 st->c[tid] = (R)cc;
                 const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
 #pragma unroll
-                for (int k = 0; k < NW; k++) st->term[k][tid] = (R)((double)__ldg(wsrc[k] + p) * scale);
+                for (int k = 0; k < NW; k++) st->term[k][tid] = (R)((double)pr.w[k] * scale);
             }
             __syncthreads();
 
@@ -535,19 +597,16 @@ template <typename R, int NW> struct DirectRec {
 
 template <typename T, typename R, int KIND, int NW, bool DIM3>
 __global__ void __launch_bounds__(kDirectWarps * 32)
-direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-              const T *__restrict__ h, const T *__restrict__ w0, const T *__restrict__ w1,
-              const T *__restrict__ w2, const T *__restrict__ w3, const double *__restrict__ lut,
-              int lut_samples, const uint32_t *__restrict__ order, int64_t n_small, double *o0, double *o1,
-              double *o2, double *o3)
+direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
+              const uint32_t *__restrict__ order, int64_t n_small, double *o0, double *o1, double *o2,
+              double *o3)
 {
     using R2 = typename Real2<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DirectRec<R, NW> *recs = reinterpret_cast<DirectRec<R, NW> *>(smem_raw);
-    R2 *lut_s = reinterpret_cast<R2 *>(recs + kDirectWarps);
+    DirectRec<R, NW> *drecs = reinterpret_cast<DirectRec<R, NW> *>(smem_raw);
+    R2 *lut_s = reinterpret_cast<R2 *>(drecs + kDirectWarps);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    DirectRec<R, NW> &rec = recs[warp];
-    const T *wsrc[4] = {w0, w1, w2, w3};
+    DirectRec<R, NW> &rec = drecs[warp];
     double *outs[4] = {o0, o1, o2, o3};
 
     LutView<R> lv;
@@ -579,8 +638,9 @@ direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
             uint32_t dims = 0;
             if (base + lane < n_small) {
                 const int64_t p = order[base + lane];
-                const double hp = (double)__ldg(h + p);
-                const double xp = (double)__ldg(x + p), yp = (double)__ldg(y + p);
+                const Rec<T> pr = load_rec<T>(recs, v.rec_stride, p, NW);
+                const double hp = (double)pr.h;
+                const double xp = (double)pr.x, yp = (double)pr.y;
                 const double rad = v.radius * hp;
                 const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
                 int x0, x1, y0, y1, z0 = 0, z1 = 1;
@@ -592,18 +652,18 @@ direct_kernel(View v, const T *__restrict__ x, const T *__restrict__ y, const T 
                 rec.sy[lane] = (R)(v.pwy * v.pwy * hinv2);
                 double cc = 0.0;
                 if (DIM3) {
-                    const double zp = (double)__ldg(z + p);
+                    const double zp = (double)pr.z;
                     pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, z0, z1);
                     rec.fz[lane] = (R)((zp - v.z_min) * v.inv_pwz - 0.5 - z0);
                     rec.sz[lane] = (R)(v.pwz * v.pwz * hinv2);
                 } else if (v.use_z) {
-                    const double dz = v.z_slice - (double)__ldg(z + p);
+                    const double dz = v.z_slice - (double)pr.z;
                     cc = dz * dz * hinv2;
                 }
                 rec.cq[lane] = (R)cc + sqrt_guard(R(0));
                 const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
 #pragma unroll
-                for (int k = 0; k < NW; k++) rec.term[k][lane] = (R)((double)__ldg(wsrc[k] + p) * scale);
+                for (int k = 0; k < NW; k++) rec.term[k][lane] = (R)((double)pr.w[k] * scale);
                 rec.base[lane] = ((unsigned long long)z0 * v.ny + (unsigned long long)y0) * v.nx + x0;
                 const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
                 rec.inv_wx[lane] = 65536u / (unsigned)max(wx, 1) + 1u;
@@ -731,7 +791,7 @@ struct Workspace {
 };
 
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
-static int launch_render(const View &v, const sphb_particles *p, const sphb_kernel *k, const uint32_t *keys,
+static int launch_render(const View &v, const T *recs, const sphb_kernel *k, const uint32_t *keys,
                          const uint32_t *vals, const uint32_t *tile_end, int64_t n_pairs,
                          double *const *out, cudaStream_t stream)
 {
@@ -760,22 +820,16 @@ static int launch_render(const View &v, const sphb_particles *p, const sphb_kern
     }
     SPHB_CUDA(allow_large_smem(kern));
     const int grid = div_up(n_pairs, kChunkPairs);
-    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < NW; i++) {
-        w[i] = static_cast<const T *>(p->w[i]);
-        o[i] = out[i];
-    }
-    kern<<<grid, WARPS * 32, smem, stream>>>(v, static_cast<const T *>(p->x), static_cast<const T *>(p->y),
-                                             static_cast<const T *>(p->z), static_cast<const T *>(p->h),
-                                             w[0], w[1], w[2], w[3], k->lut, k->lut_samples, copies_log, keys,
-                                             vals, tile_end, n_pairs, o[0], o[1], o[2], o[3]);
+    for (int i = 0; i < NW; i++) o[i] = out[i];
+    kern<<<grid, WARPS * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, copies_log, keys, vals, tile_end,
+                                             n_pairs, o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }
 
 template <typename T, typename R, int KIND, int NW, bool DIM3>
-static int launch_direct(const View &v, const sphb_particles *p, const sphb_kernel *k, const uint32_t *order,
+static int launch_direct(const View &v, const T *recs, const sphb_kernel *k, const uint32_t *order,
                          int64_t n_small, double *const *out, cudaStream_t stream)
 {
     using R2 = typename Real2<R>::type;
@@ -789,16 +843,10 @@ static int launch_direct(const View &v, const sphb_particles *p, const sphb_kern
     SPHB_CUDA(allow_large_smem(kern));
     int grid = div_up(n_small, kDirectWarps * 32);
     grid = grid > 148 * 64 ? 148 * 64 : grid;
-    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < NW; i++) {
-        w[i] = static_cast<const T *>(p->w[i]);
-        o[i] = out[i];
-    }
-    kern<<<grid, kDirectWarps * 32, smem, stream>>>(
-        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->z),
-        static_cast<const T *>(p->h), w[0], w[1], w[2], w[3], k->lut, k->lut_samples, order, n_small, o[0],
-        o[1], o[2], o[3]);
+    for (int i = 0; i < NW; i++) o[i] = out[i];
+    kern<<<grid, kDirectWarps * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, order, n_small, o[0], o[1],
+                                                    o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }
@@ -946,6 +994,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     v.ndim = k->ndim;
     v.norm = kernel_norm(k->kind, k->ndim);
     v.small_edge = small_edge_setting();
+    v.rec_stride = (!dim3 && !use_z && p->n_weights == 1) ? 4 : (sizeof(T) == 8 && p->n_weights <= 2) ? 6 : 8;
     const int64_t n_tiles = (int64_t)v.ntx * v.nty * v.ntz;
     if (n_tiles > 0x3fffffffLL) {
         set_error("raster has too many tiles");
@@ -1029,6 +1078,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     uint32_t *keys_b = a.take<uint32_t>(n_pairs);
     uint32_t *vals_b = a.take<uint32_t>(n_pairs);
     uint32_t *tile_end = a.take<uint32_t>(n_tiles);
+    T *recs = a.take<T>((size_t)n * v.rec_stride);
     unsigned char *sort_ws = a.take<unsigned char>(sort_tmp);
     const size_t need_b = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_b;
@@ -1037,7 +1087,10 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
                   ws_bytes);
         return SPHB_ERR_WORKSPACE;
     }
-    emit_pairs_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets, keys_a, vals_a);
+    emit_pairs_kernel<T><<<blocks, 256, 0, stream>>>(
+        v, x, y, z, h, static_cast<const T *>(p->w[0]), static_cast<const T *>(p->w[1]),
+        static_cast<const T *>(p->w[2]), static_cast<const T *>(p->w[3]), p->n_weights, n, offsets, keys_a, vals_a,
+        recs);
     SPHB_LAUNCH_CHECK();
     if (timed) SPHB_CUDA(cudaEventRecord(ev[1], stream));
     SPHB_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sort_tmp, keys_a, keys_b, vals_a, vals_b, n_pairs, 0,
@@ -1055,16 +1108,16 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         if (dim3) {
             if (f32)
                 rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z, 8>(
-                    k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_large, out, stream);
+                    k->kind, p->n_weights, v, recs, k, keys_b, vals_b, tile_end, n_large, out, stream);
             else
                 rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z, 8>(
-                    k->kind, p->n_weights, v, p, k, keys_b, vals_b, tile_end, n_large, out, stream);
+                    k->kind, p->n_weights, v, recs, k, keys_b, vals_b, tile_end, n_large, out, stream);
         } else {
             if (f32)
-                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, p, k, keys_b,
+                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, recs, k, keys_b,
                                                                            vals_b, tile_end, n_large, out, stream);
             else
-                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, p, k, keys_b,
+                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, recs, k, keys_b,
                                                                             vals_b, tile_end, n_large, out, stream);
         }
         if (rc) return rc;
@@ -1073,11 +1126,11 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     if (n_small > 0) {
         const uint32_t *order = vals_b + n_large;
         if (dim3)
-            rc = f32 ? direct_kind<T, float, true>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream)
-                     : direct_kind<T, double, true>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream);
+            rc = f32 ? direct_kind<T, float, true>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream)
+                     : direct_kind<T, double, true>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream);
         else
-            rc = f32 ? direct_kind<T, float, false>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream)
-                     : direct_kind<T, double, false>(k->kind, p->n_weights, v, p, k, order, n_small, out, stream);
+            rc = f32 ? direct_kind<T, float, false>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream)
+                     : direct_kind<T, double, false>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream);
     }
     if (rc) return rc;
     if (stats) stats->launches = 2 + (n_large > 0 ? 2 : 0) + (n_small > 0 ? 1 : 0); // count, emit, tile_end, render, direct
