@@ -55,11 +55,26 @@ template <> struct Real2<double> { using type = double2; };
 // Column table as the device sees it: entry i holds (T[i], T[i+1] - T[i]) so
 // one vector load serves the lerp T[i] + f (T[i+1] - T[i]).
 template <typename R> struct LutView {
-    const typename Real2<R>::type *tab; // this lane's copy: entry i at tab[i << shift]
-    int shift;                          // log2 of the number of interleaved copies
-    R scale;                            // (S - 1) / radius
-    int last;                           // S - 1
+    const typename Real2<R>::type *tab;  // shared memory; this lane's copy: entry i at tab[i << shift]
+    const typename Real2<R>::type *gtab; // global memory instead (tables too large for shared memory)
+    int shift;                           // log2 of the number of interleaved copies
+    R scale;                             // (S - 1) / radius
+    int last;                            // S - 1
 };
+
+// Internal kernel id: column table read from global memory (tables too large for shared
+// memory).  A separate template value, not a run-time test, so the common shared-memory
+// lookup stays a single LDS.
+constexpr int SPHB_COLUMN_LUT_GLOBAL = 4;
+
+template <int KIND> __device__ __host__ constexpr bool is_lut() { return KIND == SPHB_COLUMN_LUT || KIND == SPHB_COLUMN_LUT_GLOBAL; }
+
+template <int KIND, typename R>
+__device__ __forceinline__ typename Real2<R>::type lut_entry(const LutView<R> &lut, int i)
+{
+    if (KIND == SPHB_COLUMN_LUT_GLOBAL) return __ldg(lut.gtab + i);
+    return lut.tab[i << lut.shift];
+}
 
 // ---- square root -----------------------------------------------------------
 // double: MUFU.RSQ64H seed (reads the high word only: relative error < 2^-19.9)
@@ -150,11 +165,11 @@ template <int KIND, typename R>
 __device__ __forceinline__ R kernel_eval_q2(R q2, const LutView<R> &lut)
 {
     R q = fast_sqrt(q2);
-    if (KIND == SPHB_COLUMN_LUT) {
+    if (is_lut<KIND>()) {
         R f;
         int i = floor_nonneg(q * lut.scale, f);
         i = max(0, min(i, lut.last));
-        typename Real2<R>::type e = lut.tab[i << lut.shift];
+        typename Real2<R>::type e = lut_entry<KIND>(lut, i);
         return fma(f, e.y, e.x);
     } else {
         return kernel_shape<KIND>(q);
@@ -167,11 +182,11 @@ template <int KIND, typename R>
 __device__ __forceinline__ R kernel_eval_pos(R q2, const LutView<R> &lut)
 {
     R q = sqrt_pos(q2);
-    if (KIND == SPHB_COLUMN_LUT) {
+    if (is_lut<KIND>()) {
         R f;
         int i = floor_nonneg(q * lut.scale, f);
         i = min(i, lut.last);
-        typename Real2<R>::type e = lut.tab[i << lut.shift];
+        typename Real2<R>::type e = lut_entry<KIND>(lut, i);
         return fma(f, e.y, e.x);
     } else {
         return kernel_shape<KIND>(q);
@@ -185,11 +200,11 @@ template <int KIND, typename R>
 __device__ __forceinline__ R kernel_eval_unguarded(R q2, R rad2, const LutView<R> &lut)
 {
     R q = sqrt_pos(q2);
-    if (KIND == SPHB_COLUMN_LUT) {
+    if (is_lut<KIND>()) {
         R f;
         int i = floor_nonneg(q * lut.scale, f);
         i = min(i, lut.last);
-        typename Real2<R>::type e = lut.tab[i << lut.shift];
+        typename Real2<R>::type e = lut_entry<KIND>(lut, i);
         return fma(f, e.y, e.x);
     } else {
         R w = kernel_shape<KIND>(q);

@@ -235,6 +235,24 @@ __global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t 
     if (i == n_pairs - 1 || keys[i] != keys[i + 1]) tile_end[keys[i]] = (uint32_t)(i + 1);
 }
 
+// Column tables of up to kLutSharedMax samples are staged in shared memory by every CTA; larger
+// ones (integral_samples is a user argument, base_kernel.py:68) are expanded once per call into
+// (T[i], T[i+1] - T[i]) pairs in the workspace and read through L1/L2.
+constexpr int kLutSharedMax = 2048;
+
+template <typename R>
+__global__ void lut_pairs_kernel(const double *lut, int samples, typename Real2<R>::type *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= samples) return;
+    const double a = lut[i], b = (i + 1 < samples) ? lut[i + 1] : lut[i];
+    typename Real2<R>::type e;
+    e.x = (R)a;
+    e.y = (R)(b - a);
+    if (i == samples - 1) e.x = e.y = R(0); // clamp target of out-of-support lookups
+    out[i] = e;
+}
+
 // ---------------------------------------------------------------------------
 // Render.
 
@@ -303,7 +321,7 @@ template <typename R, bool DIM3, int WARPS> struct RenderBatch {
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 1) ? 2 : 4)
 render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
-              int lut_copies_log, const uint32_t *__restrict__ keys,
+              const void *__restrict__ lut_global, int lut_copies_log, const uint32_t *__restrict__ keys,
               const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_end, int64_t n_pairs,
               double *o0, double *o1, double *o2, double *o3)
 {
@@ -334,11 +352,12 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     // conflicts.
     LutView<R> lv;
     lv.tab = lut_s + (lane & ((1 << lut_copies_log) - 1));
+    lv.gtab = static_cast<const R2 *>(lut_global);
     lv.shift = lut_copies_log;
     lv.scale = R(0);
     lv.last = 0;
-    if (KIND == SPHB_COLUMN_LUT) {
-        const int slots = lut_samples << lut_copies_log;
+    if (is_lut<KIND>()) {
+        const int slots = KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples << lut_copies_log;
         for (int j = tid; j < slots; j += kThreads) {
             const int i = j >> lut_copies_log;
             double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
@@ -598,7 +617,7 @@ template <typename R, int NW> struct DirectRec {
 template <typename T, typename R, int KIND, int NW, bool DIM3>
 __global__ void __launch_bounds__(kDirectWarps * 32)
 direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
-              const uint32_t *__restrict__ order, int64_t n_small, double *o0, double *o1, double *o2,
+              const void *__restrict__ lut_global, const uint32_t *__restrict__ order, int64_t n_small, double *o0, double *o1, double *o2,
               double *o3)
 {
     using R2 = typename Real2<R>::type;
@@ -611,11 +630,12 @@ direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
 
     LutView<R> lv;
     lv.tab = lut_s;
+    lv.gtab = static_cast<const R2 *>(lut_global);
     lv.shift = 0;
     lv.scale = R(0);
     lv.last = 0;
-    if (KIND == SPHB_COLUMN_LUT) {
-        for (int i = tid; i < lut_samples; i += kDirectWarps * 32) {
+    if (is_lut<KIND>()) {
+        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kDirectWarps * 32) {
             double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
             R2 e;
             e.x = (R)a;
@@ -791,8 +811,8 @@ struct Workspace {
 };
 
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
-static int launch_render(const View &v, const T *recs, const sphb_kernel *k, const uint32_t *keys,
-                         const uint32_t *vals, const uint32_t *tile_end, int64_t n_pairs,
+static int launch_render(const View &v, const T *recs, const sphb_kernel *k, const void *lut_global,
+                         const uint32_t *keys, const uint32_t *vals, const uint32_t *tile_end, int64_t n_pairs,
                          double *const *out, cudaStream_t stream)
 {
     using R2 = typename Real2<R>::type;
@@ -822,15 +842,15 @@ static int launch_render(const View &v, const T *recs, const sphb_kernel *k, con
     const int grid = div_up(n_pairs, kChunkPairs);
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) o[i] = out[i];
-    kern<<<grid, WARPS * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, copies_log, keys, vals, tile_end,
-                                             n_pairs, o[0], o[1], o[2], o[3]);
+    kern<<<grid, WARPS * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, copies_log, keys, vals,
+                                             tile_end, n_pairs, o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }
 
 template <typename T, typename R, int KIND, int NW, bool DIM3>
-static int launch_direct(const View &v, const T *recs, const sphb_kernel *k, const uint32_t *order,
-                         int64_t n_small, double *const *out, cudaStream_t stream)
+static int launch_direct(const View &v, const T *recs, const sphb_kernel *k, const void *lut_global,
+                         const uint32_t *order, int64_t n_small, double *const *out, cudaStream_t stream)
 {
     using R2 = typename Real2<R>::type;
     auto kern = direct_kernel<T, R, KIND, NW, DIM3>;
@@ -845,8 +865,8 @@ static int launch_direct(const View &v, const T *recs, const sphb_kernel *k, con
     grid = grid > 148 * 64 ? 148 * 64 : grid;
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) o[i] = out[i];
-    kern<<<grid, kDirectWarps * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, order, n_small, o[0], o[1],
-                                                    o[2], o[3]);
+    kern<<<grid, kDirectWarps * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, order, n_small,
+                                                    o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }
@@ -868,7 +888,8 @@ template <typename T, typename R, bool DIM3, typename... A> static int direct_ki
     case SPHB_CUBIC: return direct_nw<T, R, SPHB_CUBIC, DIM3>(nw, a...);
     case SPHB_QUARTIC: return direct_nw<T, R, SPHB_QUARTIC, DIM3>(nw, a...);
     case SPHB_QUINTIC: return direct_nw<T, R, SPHB_QUINTIC, DIM3>(nw, a...);
-    default: return direct_nw<T, R, SPHB_COLUMN_LUT, DIM3>(nw, a...);
+    case SPHB_COLUMN_LUT: return direct_nw<T, R, SPHB_COLUMN_LUT, DIM3>(nw, a...);
+    default: return direct_nw<T, R, SPHB_COLUMN_LUT_GLOBAL, DIM3>(nw, a...);
     }
 }
 
@@ -890,7 +911,8 @@ static int dispatch_kind(int kind, int nw, A &&...a)
     case SPHB_CUBIC: return dispatch_nw<T, R, SPHB_CUBIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
     case SPHB_QUARTIC: return dispatch_nw<T, R, SPHB_QUARTIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
     case SPHB_QUINTIC: return dispatch_nw<T, R, SPHB_QUINTIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
-    default: return dispatch_nw<T, R, SPHB_COLUMN_LUT, DIM3, TX, TY, TZ, WARPS>(nw, a...);
+    case SPHB_COLUMN_LUT: return dispatch_nw<T, R, SPHB_COLUMN_LUT, DIM3, TX, TY, TZ, WARPS>(nw, a...);
+    default: return dispatch_nw<T, R, SPHB_COLUMN_LUT_GLOBAL, DIM3, TX, TY, TZ, WARPS>(nw, a...);
     }
 }
 
@@ -1079,6 +1101,8 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     uint32_t *vals_b = a.take<uint32_t>(n_pairs);
     uint32_t *tile_end = a.take<uint32_t>(n_tiles);
     T *recs = a.take<T>((size_t)n * v.rec_stride);
+    const bool big_lut = k->kind == SPHB_COLUMN_LUT && k->lut_samples > kLutSharedMax;
+    void *lut_global = big_lut ? static_cast<void *>(a.take<double2>(k->lut_samples)) : nullptr;
     unsigned char *sort_ws = a.take<unsigned char>(sort_tmp);
     const size_t need_b = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_b;
@@ -1100,24 +1124,35 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         SPHB_LAUNCH_CHECK();
     }
 
+    if (big_lut) {
+        if (p->dtype == SPHB_F32)
+            lut_pairs_kernel<float><<<div_up(k->lut_samples, 256), 256, 0, stream>>>(
+                k->lut, k->lut_samples, static_cast<float2 *>(lut_global));
+        else
+            lut_pairs_kernel<double><<<div_up(k->lut_samples, 256), 256, 0, stream>>>(
+                k->lut, k->lut_samples, static_cast<double2 *>(lut_global));
+        SPHB_LAUNCH_CHECK();
+    }
+
     // ---- phase C: render ---------------------------------------------------
     if (timed) SPHB_CUDA(cudaEventRecord(ev[2], stream));
     const bool f32 = p->dtype == SPHB_F32;
+    const int kind = big_lut ? SPHB_COLUMN_LUT_GLOBAL : k->kind;
     int rc = SPHB_OK;
     if (n_large > 0) {
         if (dim3) {
             if (f32)
                 rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z, 8>(
-                    k->kind, p->n_weights, v, recs, k, keys_b, vals_b, tile_end, n_large, out, stream);
+                    kind, p->n_weights, v, recs, k, lut_global, keys_b, vals_b, tile_end, n_large, out, stream);
             else
                 rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z, 8>(
-                    k->kind, p->n_weights, v, recs, k, keys_b, vals_b, tile_end, n_large, out, stream);
+                    kind, p->n_weights, v, recs, k, lut_global, keys_b, vals_b, tile_end, n_large, out, stream);
         } else {
             if (f32)
-                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, recs, k, keys_b,
+                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1, 8>(kind, p->n_weights, v, recs, k, lut_global, keys_b,
                                                                            vals_b, tile_end, n_large, out, stream);
             else
-                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1, 8>(k->kind, p->n_weights, v, recs, k, keys_b,
+                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1, 8>(kind, p->n_weights, v, recs, k, lut_global, keys_b,
                                                                             vals_b, tile_end, n_large, out, stream);
         }
         if (rc) return rc;
@@ -1126,11 +1161,11 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     if (n_small > 0) {
         const uint32_t *order = vals_b + n_large;
         if (dim3)
-            rc = f32 ? direct_kind<T, float, true>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream)
-                     : direct_kind<T, double, true>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream);
+            rc = f32 ? direct_kind<T, float, true>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream)
+                     : direct_kind<T, double, true>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream);
         else
-            rc = f32 ? direct_kind<T, float, false>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream)
-                     : direct_kind<T, double, false>(k->kind, p->n_weights, v, recs, k, order, n_small, out, stream);
+            rc = f32 ? direct_kind<T, float, false>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream)
+                     : direct_kind<T, double, false>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream);
     }
     if (rc) return rc;
     if (stats) stats->launches = 2 + (n_large > 0 ? 2 : 0) + (n_small > 0 ? 1 : 0); // count, emit, tile_end, render, direct

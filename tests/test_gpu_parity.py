@@ -295,3 +295,23 @@ def test_mixed_footprints_use_both_paths(B):
         assert ops.last_stats["n_direct"] > 0 and ops.last_stats["n_pairs"] > 0
         ref = OracleBackend.interpolate_2d_render(*a, OracleKernel("quintic"), 3, 300, 217, 0, 1, 0, 1, False)
         assert_parity(out, ref, tol, f"mixed footprints {np.dtype(dtype).name}")
+
+
+@pytest.mark.parametrize("samples", [2, 3000, 10000])
+def test_column_table_sizes(B, samples):
+    """integral_samples is a user argument (base_kernel.py:68): 2 (the reference's
+    test_column_samples), and tables too large for shared memory (read from global memory)."""
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(21)
+    n = 3000
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    h = np.exp(rng.uniform(np.log(0.003), np.log(0.2), n))
+    w = rng.uniform(0.1, 1, n) * h ** 2
+    k = _kernel("cubic")
+    out = B.interpolate_3d_projection(x, y, w, h, k.get_column_kernel_func(samples), 2, 90, 70, 0, 1, 0, 1, False)
+    ref = OracleBackend.interpolate_3d_projection(x, y, w, h, OracleKernel.column("cubic", samples), 2, 90, 70, 0, 1,
+                                                  0, 1, False)
+    assert_parity(out, ref, TOL64, f"column table S={samples}")
+    out = B.interpolate_3d_projection(*(a.astype(np.float32) for a in (x, y, w, h)),
+                                      k.get_column_kernel_func(samples), 2, 90, 70, 0, 1, 0, 1, False)
+    assert_parity(out, ref, TOL32, f"column table S={samples} f32")
