@@ -55,9 +55,8 @@ template <> struct Real2<double> { using type = double2; };
 // Column table as the device sees it: entry i holds (T[i], T[i+1] - T[i]) so
 // one vector load serves the lerp T[i] + f (T[i+1] - T[i]).
 template <typename R> struct LutView {
-    const typename Real2<R>::type *tab;  // shared memory; this lane's copy: entry i at tab[i << shift]
+    const typename Real2<R>::type *tab;  // shared memory
     const typename Real2<R>::type *gtab; // global memory instead (tables too large for shared memory)
-    int shift;                           // log2 of the number of interleaved copies
     R scale;                             // (S - 1) / radius
     int last;                            // S - 1
 };
@@ -73,7 +72,7 @@ template <int KIND, typename R>
 __device__ __forceinline__ typename Real2<R>::type lut_entry(const LutView<R> &lut, int i)
 {
     if (KIND == SPHB_COLUMN_LUT_GLOBAL) return __ldg(lut.gtab + i);
-    return lut.tab[i << lut.shift];
+    return lut.tab[i];
 }
 
 // ---- square root -----------------------------------------------------------
@@ -93,7 +92,14 @@ __device__ __forceinline__ double sqrt_pos(double a)
     double r = fma(-g, h, 0.5);
     return fma(g, r, g);
 }
-__device__ __forceinline__ float sqrt_pos(float a) { return a * rsqrtf(a); }
+__device__ __forceinline__ float sqrt_pos(float a)
+{
+    // one MUFU.RSQ: the argument is a normal number (callers add sqrt_guard), so the
+    // denormal rescaling that rsqrtf() wraps around it is not needed
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    return a * y;
+}
 
 __device__ __forceinline__ double fast_sqrt(double a)
 {

@@ -321,7 +321,7 @@ template <typename R, bool DIM3, int WARPS> struct RenderBatch {
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 1) ? 2 : 4)
 render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
-              const void *__restrict__ lut_global, int lut_copies_log, const uint32_t *__restrict__ keys,
+              const void *__restrict__ lut_global, const uint32_t *__restrict__ keys,
               const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_end, int64_t n_pairs,
               double *o0, double *o1, double *o2, double *o3)
 {
@@ -345,28 +345,24 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *outs[4] = {o0, o1, o2, o3};
 
-    // The column table is replicated 2^lut_copies_log times, entry i of copy c at
-    // slot (i << log) + c, and a lane reads copy (lane mod copies): with 8 copies of
-    // 16-byte entries (16 copies of 8-byte entries) every lane of a shared-memory
-    // access phase owns its own bank group, so the random table index causes no bank
-    // conflicts.
+    // Column table in shared memory as (T[i], T[i+1] - T[i]) pairs.  (Replicating it so that every
+    // lane of an access phase owns a bank group was measured on config 2: 1, 2, 4, 8 copies ->
+    // 124, 127, 145, 216 ms, every doubling costs a resident CTA; the random index is not the
+    // bottleneck.)
     LutView<R> lv;
-    lv.tab = lut_s + (lane & ((1 << lut_copies_log) - 1));
+    lv.tab = lut_s;
     lv.gtab = static_cast<const R2 *>(lut_global);
-    lv.shift = lut_copies_log;
     lv.scale = R(0);
     lv.last = 0;
     if (is_lut<KIND>()) {
-        const int slots = KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples << lut_copies_log;
-        for (int j = tid; j < slots; j += kThreads) {
-            const int i = j >> lut_copies_log;
+        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kThreads) {
             double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
             R2 e;
             e.x = (R)a;
             e.y = (R)(b - a);
             // the clamp target of out-of-support lookups: W(q >= R) = 0
             if (i == lut_samples - 1) e.x = e.y = R(0);
-            lut_s[j] = e;
+            lut_s[i] = e;
         }
         lv.scale = (R)((double)(lut_samples - 1) / v.radius);
         lv.last = lut_samples - 1;
@@ -631,7 +627,6 @@ direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     LutView<R> lv;
     lv.tab = lut_s;
     lv.gtab = static_cast<const R2 *>(lut_global);
-    lv.shift = 0;
     lv.scale = R(0);
     lv.last = 0;
     if (is_lut<KIND>()) {
@@ -820,29 +815,16 @@ static int launch_render(const View &v, const T *recs, const sphb_kernel *k, con
     const size_t fixed = sizeof(R) * (size_t)(TX + 8) * TY * TZ * NW + sizeof(Staged<R, NW, RenderBatch<R, DIM3, WARPS>::value>);
     const size_t limit = 227 * 1024;
     size_t smem = fixed;
-    int copies_log = 0;
-    if (KIND == SPHB_COLUMN_LUT) {
-        const size_t one = sizeof(R2) * (size_t)k->lut_samples;
-        if (fixed + one > limit) {
-            set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
-            return SPHB_ERR_ARGUMENT;
-        }
-        // as many copies as fit, up to one bank group per lane of an access phase (128 B / entry)
-        // Replicating the table (one bank group per lane) was measured on config 2: 1, 2, 4, 8
-        // copies -> 124, 127, 145, 216 ms (8 warps / CTA) because every doubling costs a
-        // resident CTA, and 147 vs 148 ms with 16-warp CTAs: the random table index is not the
-        // bottleneck, occupancy is worth more.  SPHB_LUT_COPIES_LOG re-enables it for experiments.
-        int max_log = 0;
-        if (const char *e = getenv("SPHB_LUT_COPIES_LOG")) max_log = atoi(e) < 4 ? atoi(e) : 4;
-        if (sizeof(R2) == 16 && max_log > 3) max_log = 3;
-        while (copies_log < max_log && fixed + (one << (copies_log + 1)) <= limit) copies_log++;
-        smem += one << copies_log;
+    if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
+    if (smem > limit) {
+        set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
+        return SPHB_ERR_ARGUMENT;
     }
     SPHB_CUDA(allow_large_smem(kern));
     const int grid = div_up(n_pairs, kChunkPairs);
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) o[i] = out[i];
-    kern<<<grid, WARPS * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, copies_log, keys, vals,
+    kern<<<grid, WARPS * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, keys, vals,
                                              tile_end, n_pairs, o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
