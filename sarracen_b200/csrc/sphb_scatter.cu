@@ -261,12 +261,19 @@ __global__ void lut_pairs_kernel(const double *lut, int samples, typename Real2<
 // pixel (ic) and a fraction in [-1/2, 1/2] so that position differences keep
 // full float precision however large the raster is.
 template <typename R, int NW, int BATCH> struct Staged {
-    R fx[BATCH], fy[BATCH], fz[BATCH];    // centre (double mode) / fraction (float mode)
-    R sx[BATCH], sy[BATCH], sz[BATCH];    // (pixel width / h)^2 per axis
-    R c[BATCH];                             // dz^2 / h^2 of a cross-section, else 0
-    R term[NW][BATCH];                      // norm * w / h^ndim
-    int cx[BATCH], cy[BATCH], cz[BATCH];  // nearest pixel (float mode), else 0
-    uint32_t bx[BATCH], by[BATCH], bz[BATCH]; // footprint box ∩ tile: lo | hi << 16
+    using R2 = typename Real2<R>::type;
+    // read one per lane when a warp scans the batch for its strip: the box along the split axis
+    // (rows in 2-D, z-planes in 3-D), lo | hi << 16 -- kept as its own array so that the scan is
+    // conflict-free
+    uint32_t key[BATCH];
+    // the rest is read by whole warps (broadcast) when a particle hits: packed so that a hit costs
+    // 4 (2-D) or 6 (3-D) 16-byte loads instead of 10-14 scalar ones
+    int4 ibox[BATCH];            // bx, by (lo | hi << 16), cx, cy (nearest pixel in float mode, else 0)
+    int4 ibox3[BATCH];           // bz, cz, -, -
+    R2 fxy[BATCH];               // centre (double mode) / fraction (float mode), tile-local pixel units
+    R2 sxy[BATCH];               // (pixel width / h)^2
+    R2 fsz[BATCH];               // fz, sz
+    R2 ct[(NW + 2) / 2][BATCH];  // c (dz^2/h^2 of a cross-section), term[0] | term[1], term[2] | term[3], -
 };
 
 template <typename R> struct Split;
@@ -412,15 +419,21 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                 pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, lo, hi);
                 lo = max(lo - ox, 0);
                 hi = min(hi - ox, lim_x);
-                st->bx[tid] = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
+                const uint32_t bx = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
                 pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, lo, hi);
                 lo = max(lo - oy, 0);
                 hi = min(hi - oy, lim_y);
-                st->by[tid] = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
-                Split<R>::apply(ux, st->fx[tid], st->cx[tid]);
-                Split<R>::apply(uy, st->fy[tid], st->cy[tid]);
-                st->sx[tid] = (R)(v.pwx * v.pwx * hinv2);
-                st->sy[tid] = (R)(v.pwy * v.pwy * hinv2);
+                const uint32_t by = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
+                R2 f, sc;
+                int cx, cy;
+                Split<R>::apply(ux, f.x, cx);
+                Split<R>::apply(uy, f.y, cy);
+                sc.x = (R)(v.pwx * v.pwx * hinv2);
+                sc.y = (R)(v.pwy * v.pwy * hinv2);
+                st->ibox[tid] = make_int4((int)bx, (int)by, cx, cy);
+                st->fxy[tid] = f;
+                st->sxy[tid] = sc;
+                uint32_t key = by;
                 double cc = 0.0;
                 if (DIM3) {
                     const double zp = (double)pr.z;
@@ -428,17 +441,38 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                     pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, lo, hi);
                     lo = max(lo - oz, 0);
                     hi = min(hi - oz, lim_z);
-                    st->bz[tid] = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
-                    Split<R>::apply(uz, st->fz[tid], st->cz[tid]);
-                    st->sz[tid] = (R)(v.pwz * v.pwz * hinv2);
+                    key = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
+                    R2 fz;
+                    int cz;
+                    Split<R>::apply(uz, fz.x, cz);
+                    fz.y = (R)(v.pwz * v.pwz * hinv2);
+                    st->fsz[tid] = fz;
+                    st->ibox3[tid] = make_int4((int)key, cz, 0, 0);
                 } else if (v.use_z) {
                     const double dz = v.z_slice - (double)pr.z;
                     cc = dz * dz * hinv2;
                 }
-                st->c[tid] = (R)cc;
+                st->key[tid] = key;
                 const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
+                R tv[4] = {R(0), R(0), R(0), R(0)};
 #pragma unroll
-                for (int k = 0; k < NW; k++) st->term[k][tid] = (R)((double)pr.w[k] * scale);
+                for (int k = 0; k < NW; k++) tv[k] = (R)((double)pr.w[k] * scale);
+                R2 e0;
+                e0.x = (R)cc;
+                e0.y = tv[0];
+                st->ct[0][tid] = e0;
+                if (NW > 1) {
+                    R2 e1;
+                    e1.x = tv[1];
+                    e1.y = tv[2];
+                    st->ct[1][tid] = e1;
+                }
+                if (NW > 3) {
+                    R2 e2;
+                    e2.x = tv[3];
+                    e2.y = R(0);
+                    st->ct[2][tid] = e2;
+                }
             }
             __syncthreads();
 
@@ -447,7 +481,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                 const int me = g + lane;
                 bool hit = false;
                 if (me < nb) {
-                    const uint32_t b = DIM3 ? st->bz[me] : st->by[me];
+                    const uint32_t b = st->key[me];
                     const int lo = (int)(b & 0xffff), hi = (int)(b >> 16);
                     hit = max(lo, own_lo) < min(hi, own_hi);
                 }
@@ -455,21 +489,29 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                 while (mask) {
                     const int s = g + __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const uint32_t bx = st->bx[s], by = st->by[s];
+                    const int4 ib = st->ibox[s];
+                    const uint32_t bx = (uint32_t)ib.x, by = (uint32_t)ib.y;
                     const int x0 = (int)(bx & 0xffff), x1 = (int)(bx >> 16);
                     const int y0 = max((int)(by & 0xffff), own_y0), y1 = min((int)(by >> 16), own_y0 + ROWS);
                     const int wx = x1 - x0;
                     if (wx <= 0 || y1 <= y0) continue;
-                    const R fx = st->fx[s], fy = st->fy[s], sx = st->sx[s], sy = st->sy[s];
-                    const int cx = st->cx[s], cy = st->cy[s];
-                    R cc = st->c[s];
+                    const R2 f = st->fxy[s], sc = st->sxy[s], e0 = st->ct[0][s];
+                    const R fx = f.x, fy = f.y, sx = sc.x, sy = sc.y;
+                    const int cx = ib.z, cy = ib.w;
+                    R cc = e0.x;
                     if (DIM3) {
-                        const R dz = int_to_real(warp - st->cz[s], R(0)) - st->fz[s];
-                        cc = dz * dz * st->sz[s];
+                        const R2 fz = st->fsz[s];
+                        const R dz = int_to_real(warp - st->ibox3[s].y, R(0)) - fz.x;
+                        cc = dz * dz * fz.y;
                     }
                     R term[NW];
-#pragma unroll
-                    for (int k = 0; k < NW; k++) term[k] = st->term[k][s];
+                    term[0] = e0.y;
+                    if (NW > 1) {
+                        const R2 e1 = st->ct[1][s];
+                        term[1] = e1.x;
+                        if (NW > 2) term[2] = e1.y;
+                    }
+                    if (NW > 3) term[3] = st->ct[2][s].x;
 
                     if (wx > TX / 2) {
                         // ---- wide: fixed pixels, register accumulators -------------
