@@ -318,15 +318,14 @@ __device__ __forceinline__ void add_contribution(R q2, R rad2, const LutView<R> 
 //          power of two >= box width, and accumulate into the warp's part of the
 //          shared-memory tile (plain load / fma / store).
 // Registers and shared memory are merged when the tile segment is flushed.
-// Particles staged per round.  The double-precision image kernel stages half a CTA's worth so
-// that four CTAs fit in shared memory (and asks for <= 64 registers to match): measured
-// 117 -> 113 ms on config 2; the float kernel already fits and is faster with a full batch.
+// Particles staged per round.  The double-precision image kernel stages half a CTA's worth to
+// keep three CTAs per SM in shared memory next to the 40 KB tile and the 16 KB column table.
 template <typename R, bool DIM3, int WARPS> struct RenderBatch {
     static constexpr int value = (sizeof(R) == 8 && !DIM3) ? WARPS * 16 : WARPS * 32;
 };
 
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 1) ? 2 : 4)
+__global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 1) ? 2 : 3)
 render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
               const void *__restrict__ lut_global, const uint32_t *__restrict__ keys,
               const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_end, int64_t n_pairs,
@@ -940,8 +939,11 @@ static int dispatch_kind(int kind, int nw, A &&...a)
     }
 }
 
-// 2-D tiles: 32 x 64 pixels, 8 warps with an 8-row strip each (16 warps on 32 x 128 measured 20 % slower).
-constexpr int kTile2X = 32, kTile2Y = 64;
+// 2-D tiles: 32 x 128 pixels, 8 warps with a 16-row strip each (16 register accumulators per lane
+// and weight): per-hit set-up is amortised over twice the rows of a 32 x 64 tile and the pair list
+// shrinks by 28 %; measured 104 -> 99.5 ms (double), 68.9 -> 63.6 ms (float) on config 2 at
+// 3 CTAs/SM (80 registers).  16 warps x 8 rows on the same tile was 20 % slower.
+constexpr int kTile2X = 32, kTile2Y = 128;
 
 // Footprint boxes up to this many pixels per edge take the direct path.  The
 // default can be overridden with SPHB_SMALL_EDGE (0 sends everything through
