@@ -315,3 +315,31 @@ def test_column_table_sizes(B, samples):
     out = B.interpolate_3d_projection(*(a.astype(np.float32) for a in (x, y, w, h)),
                                       k.get_column_kernel_func(samples), 2, 90, 70, 0, 1, 0, 1, False)
     assert_parity(out, ref, TOL32, f"column table S={samples} f32")
+
+
+@pytest.mark.parametrize("n", [25, 31, 63, 127, 129])
+def test_particle_exactly_on_a_pixel_centre(B, n):
+    """q = 0 at a pixel centre, reached through the row recurrences of q^2 (odd rasters put the
+    centre pixel on the particle): the image must stay finite and match the oracle."""
+    from oracle import OracleBackend, OracleKernel
+    x, y, z = np.array([0.0, 0.25]), np.array([0.0, -0.5]), np.array([0.0, 0.0])
+    h, w = np.array([0.9, 0.3]), np.array([0.35, 0.2])
+    for dtype, tol in ((np.float64, TOL64), (np.float32, TOL32)):
+        a = [v.astype(dtype) for v in (x, y, w, h)]
+        for kind in KINDS:
+            k = _kernel(kind)
+            out = B.interpolate_2d_render(*a, k.w, k.get_radius(), n, n, -1.0, 1.0, -1.0, 1.0, False)
+            ref = OracleBackend.interpolate_2d_render(*a, OracleKernel(kind), k.get_radius(), n, n, -1.0, 1.0, -1.0,
+                                                      1.0, False)
+            assert_parity(out, ref, tol, f"{kind} {n} {np.dtype(dtype).name}")
+        k = _kernel("quintic")
+        out = B.interpolate_3d_projection(*a, k.get_column_kernel_func(1000), 3, n, n, -1.0, 1.0, -1.0, 1.0, False)
+        ref = OracleBackend.interpolate_3d_projection(*a, OracleKernel.column("quintic"), 3, n, n, -1.0, 1.0, -1.0, 1.0,
+                                                      False)
+        assert_parity(out, ref, tol, f"column {n} {np.dtype(dtype).name}")
+    if n <= 31:
+        k = _kernel("cubic")
+        out = B.interpolate_3d_grid(x, y, z, w, h, k.w, 2, n, n, n, -1.0, 1.0, -1.0, 1.0, -1.0, 1.0)
+        ref = OracleBackend.interpolate_3d_grid(x, y, z, w, h, OracleKernel("cubic"), 2, n, n, n, -1.0, 1.0, -1.0, 1.0,
+                                                -1.0, 1.0)
+        assert_parity(out, ref, TOL64, f"grid {n}")
