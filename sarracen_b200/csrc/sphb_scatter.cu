@@ -517,16 +517,12 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                         // Every lane evaluates its own pixels: a pixel outside the
                         // footprint box has q >= R and W(q) = 0 there (the table is
                         // clamped to its zero last entry, the analytic shapes are
-                        // selected to 0), so no box tests are needed.  q^2 runs down
-                        // the lane's rows by second differences.  Rows are handled G at
+                        // selected to 0), so no box tests are needed.  Rows are handled G at
                         // a time without branches so the G dependent square-root /
                         // table chains overlap; groups that cannot contribute are skipped.
                         const R dx = int_to_real(lx - cx, R(0)) - fx;
                         const R qx = fma(dx * dx, sx, cc) + sqrt_guard(R(0));
                         const R dy0 = int_to_real(own_y0 + ly - cy, R(0)) - fy;
-                        R q2 = fma(dy0 * dy0, sy, qx);
-                        R d1 = sy * fma(R(2 * RI), dy0, R(RI * RI));
-                        const R d2 = sy * R(2 * RI * RI);
                         #ifndef SPHB_ROW_GROUP
 #define SPHB_ROW_GROUP 4
 #endif
@@ -537,10 +533,15 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                             bool any = false;
 #pragma unroll
                             for (int j = 0; j < G; j++) {
-                                q[j] = q2;
-                                if (sizeof(R) == 4) any = any || (q2 < rad2);
-                                q2 += d1;
-                                d1 += d2;
+                                // q^2 is evaluated directly per row.  Second differences down the
+                                // strip (one add less) carry an absolute error of ulp(q^2_max of the
+                                // strip): too much for float against the 1e-5 budget, and in double
+                                // it shows as an error of sqrt(1e-14) in q right at q = 0, which a
+                                // coarse column table (integral_samples = 2: a cusp at 0) turns into
+                                // 4e-9 -- found by tests/test_gpu_fuzz.py.
+                                const R dy = dy0 + R((r0 + j) * RI);
+                                q[j] = fma(dy * dy, sy, qx);
+                                if (sizeof(R) == 4) any = any || (q[j] < rad2);
                             }
                             // Skip a group that cannot contribute.  double: rows that miss the
                             // footprint box (warp-uniform integer test; a DSETP per row costs more
@@ -761,19 +762,15 @@ direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                     const R qxy = fma(dy * dy, sy, fma(dx * dx, sx, cq));
                     const size_t o = (size_t)base_o + (size_t)(iy * v.nx + ix);
                     if (DIM3) {
-                        // q^2 along z by second differences
-                        R q2 = fma(fz * fz, sz, qxy);
-                        R d1 = sz * fma(R(-2), fz, R(1));
-                        const R d2 = sz + sz;
                         size_t oo = o;
                         for (int iz = 0; iz < wz; iz++) {
+                            const R dz = int_to_real(iz, R(0)) - fz; // direct evaluation (see render_kernel)
+                            const R q2 = fma(dz * dz, sz, qxy);
                             if (q2 < rad2) {
                                 const R wv = kernel_eval_pos<KIND, R>(q2, lv);
 #pragma unroll
                                 for (int k = 0; k < NW; k++) red_add(outs[k] + oo, (double)(term[k] * wv));
                             }
-                            q2 += d1;
-                            d1 += d2;
                             oo += (size_t)v.ny * v.nx;
                         }
                     } else if (qxy < rad2) {
