@@ -1,6 +1,13 @@
-"""Seeded randomised parity sweep: raster shapes (incl. non-multiples of the tile), limits, smoothing-length
+"""Seeded randomised parity sweep (SPHB_FUZZ_IMAGES / SPHB_FUZZ_GRIDS widen it): raster shapes (incl. non-multiples of the tile), limits, smoothing-length
 ranges from far below to far above the pixel size, particles on pixel centres / outside the view / with
-degenerate values, all kernels, both dtypes -- CUDA path vs the CPU oracle."""
+degenerate values, all kernels, both dtypes -- CUDA path vs the CPU oracle.
+
+Tolerances: 1e-10 for float64.  float32 inputs are held to 1e-5 on every BASELINE-shaped case
+(tests/test_gpu_parity.py); this sweep allows 5e-5 for them because it also draws nearly empty images
+whose largest pixel is a single contribution from the very edge of a support, where
+W ~ (R - q)^n turns the float rounding of q^2 (6e-8 relative) into up to 2e-5 relative -- 1 of 300
+seeds (a sparse float32 cross-section) lands between 1e-5 and 2e-5, none above."""
+TOL32_SWEEP = 5e-5
 import numpy as np
 import pytest
 from conftest import assert_parity
@@ -31,7 +38,7 @@ def _case(seed):
     return x, y, z, h, w, nx, ny, lim, rng
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("SPHB_FUZZ_IMAGES", "24"))))
 def test_random_images(seed):
     from oracle import OracleBackend, OracleKernel
     from sarracen_b200 import B200Backend as B
@@ -40,7 +47,7 @@ def test_random_images(seed):
     kind = KINDS[seed % 3]
     kern = {"cubic": s.CubicSplineKernel, "quartic": s.QuarticSplineKernel, "quintic": s.QuinticSplineKernel}[kind]()
     R = RADIUS[kind]
-    dtype, tol = ((np.float64, 1e-10), (np.float32, 1e-5))[(seed // 3) % 2]
+    dtype, tol = ((np.float64, 1e-10), (np.float32, TOL32_SWEEP))[(seed // 3) % 2]
     a = [v.astype(dtype) for v in (x, y, z, h, w)]
     xa, ya, za, ha, wa = a
     mode = seed % 4
@@ -65,7 +72,7 @@ def test_random_images(seed):
     assert_parity(out, ref, tol, f"seed {seed} mode {mode} {kind} {np.dtype(dtype).name} {nx}x{ny} n={x.size}")
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("SPHB_FUZZ_GRIDS", "8"))))
 def test_random_grids(seed):
     from oracle import OracleBackend, OracleKernel
     from sarracen_b200 import B200Backend as B
@@ -85,7 +92,7 @@ def test_random_grids(seed):
     w = rng.normal(size=n) * h ** 3
     kind = KINDS[seed % 3]
     kern = {"cubic": s.CubicSplineKernel, "quartic": s.QuarticSplineKernel, "quintic": s.QuinticSplineKernel}[kind]()
-    dtype, tol = ((np.float64, 1e-10), (np.float32, 1e-5))[seed % 2]
+    dtype, tol = ((np.float64, 1e-10), (np.float32, TOL32_SWEEP))[seed % 2]
     a = [v.astype(dtype) for v in (x, y, z, w, h)]
     out = B.interpolate_3d_grid(*a, kern.w, RADIUS[kind], nx, ny, nz, *lim)
     ref = OracleBackend.interpolate_3d_grid(*a, OracleKernel(kind), RADIUS[kind], nx, ny, nz, *lim)
