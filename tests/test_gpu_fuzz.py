@@ -117,3 +117,39 @@ def test_degenerate_particles_are_skipped():
     ref = OracleBackend.interpolate_2d_render(x[good], y[good], w[good], h[good], OracleKernel("cubic"), 2, 40, 40, 0, 1,
                                               0, 1, False)
     assert_parity(out, ref, 1e-10, "degenerate particles")
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_lines_and_exact(seed):
+    from oracle import OracleBackend, OracleKernel
+    from sarracen_b200 import B200Backend as B
+    import sarracen_b200 as s
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(1, 1200))
+    x, y, z = rng.uniform(-0.2, 1.2, (3, n))
+    h = np.exp(rng.uniform(np.log(0.004), np.log(0.3), n))
+    w = rng.normal(size=n) * h ** 2
+    kind = KINDS[seed % 3]
+    kern = {"cubic": s.CubicSplineKernel, "quartic": s.QuarticSplineKernel, "quintic": s.QuinticSplineKernel}[kind]()
+    R = RADIUS[kind]
+    px = int(rng.integers(1, 1500))
+    c2 = [tuple(rng.uniform(0, 1, 4)), (0.1, 0.9, 0.4, 0.4), (0.5, 0.5, 0.1, 0.9), (0.9, 0.2, 0.3, 0.8)][seed % 4]
+    out = B.interpolate_2d_line(x, y, w, h, kern.w, R, px, *c2)
+    ref = OracleBackend.interpolate_2d_line(x, y, w, h, OracleKernel(kind), R, px, *c2)
+    assert_parity(out, ref, 1e-10, f"line2d seed {seed} {c2}")
+    c3 = tuple(rng.uniform(0, 1, 6))
+    out = B.interpolate_3d_line(x, y, z, w, h, kern.w, R, px, *c3)
+    ref = OracleBackend.interpolate_3d_line(x, y, z, w, h, OracleKernel(kind), R, px, *c3)
+    assert_parity(out, ref, 1e-10, f"line3d seed {seed}")
+    # exact paths (cubic only); positive weights, centres inside and outside the view
+    m = min(n, 150)
+    nx, ny = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+    lim = (0.1, 0.9, 0.2, 0.8)
+    wpos = np.abs(w[:m]) + 1e-3
+    k = s.CubicSplineKernel()
+    out = B.interpolate_2d_render(x[:m], y[:m], wpos, h[:m], k.w, 2, nx, ny, *lim, True)
+    ref = OracleBackend.interpolate_2d_render(x[:m], y[:m], wpos, h[:m], OracleKernel("cubic"), 2, nx, ny, *lim, True)
+    assert_parity(out, ref, 1e-10, f"exact2d seed {seed} {nx}x{ny}")
+    out = B.interpolate_3d_projection(x[:m], y[:m], wpos, h[:m], k.w, 2, nx, ny, *lim, True)
+    ref = OracleBackend.interpolate_3d_projection(x[:m], y[:m], wpos, h[:m], OracleKernel("cubic"), 2, nx, ny, *lim, True)
+    assert_parity(out, ref, 1e-10, f"exact3d seed {seed} {nx}x{ny}")
