@@ -96,8 +96,10 @@ __device__ __forceinline__ double f2_2d(const Angle &a, double q0)
 // cubic_spline_exact.py:199-217 -- region q > 2
 __device__ __forceinline__ double f3_2d(double phi) { return 0.5 / kPi * phi; }
 
-// cubic_spline_exact.py:58-121; `t` is tan(phi) of the segment end point
-__device__ double full_2d_mod(double t, double q0)
+// cubic_spline_exact.py:58-121; `t` is tan(phi) of the segment end point.  Not inlined: eight call sites per
+// pixel would otherwise blow the kernel past the instruction cache (ncu: 14.6 'no instruction' stalls per
+// issue with everything inlined).
+__device__ __noinline__ double full_2d_mod(double t, double q0)
 {
     const Angle e = angle_from_tan(t);
     const double q = q0 / e.c;
@@ -133,12 +135,12 @@ struct ITerms {
     double i0, i1, i2, i3, i4, i5;
 };
 
-__device__ __noinline__ ITerms get_i_terms(double cosp, double a2, double a)
+// `p` = acos(cosp) and `tn` = tan(p) are passed in: for the segment end point they are known
+// (p = atan(t), tn = t) and need no inverse cosine.
+__device__ __noinline__ ITerms get_i_terms(double cosp, double p, double tn, double a2, double a)
 {
     ITerms t;
     const double cosp2 = cosp * cosp;
-    const double p = acos(cosp);
-    const double tn = sqrt(1.0 - cosp2) / cosp;
     const double mu2_1 = 1.0 / (1.0 + cosp2 / a2);
     const double u2 = (1.0 - cosp2) * mu2_1, u = sqrt(u2);
     const double logs = log((1.0 + u) / (1.0 - u));
@@ -156,12 +158,19 @@ __device__ __noinline__ ITerms get_i_terms(double cosp, double a2, double a)
     return t;
 }
 
+__device__ __forceinline__ ITerms get_i_terms_cos(double cosp, double a2, double a)
+{
+    return get_i_terms(cosp, acos(cosp), sqrt(1.0 - cosp * cosp) / cosp, a2, a);
+}
+
 // cubic_spline_exact.py:353-454
 __device__ __noinline__ double full_integral_3d(double d, double r0, double r1, double h)
 {
     const double r0h = r0 / h;
-    const double phi = atan(fabs(d) / r1);
-    if (fabs(r0h) == 0.0 || fabs(r1 / h) == 0.0 || fabs(phi) == 0.0) return 0.0;
+    // phi = atan(|d| / r1): its cosine and tangent are algebraic in t = |d| / r1
+    const double tphi = fabs(d) / r1;
+    if (fabs(r0h) == 0.0 || fabs(r1 / h) == 0.0 || tphi == 0.0) return 0.0;
+    const double phi = atan(tphi);
 
     const double h2 = h * h, r03 = r0 * r0 * r0;
     const double r0h2 = r0h * r0h, r0h3 = r0h2 * r0h;
@@ -180,24 +189,26 @@ __device__ __noinline__ double full_integral_3d(double d, double r0, double r1, 
 
     const double a = r1 / r0, a2 = a * a;
     const double linedist2 = r0 * r0 + r1 * r1;
-    const double cphi = cos(phi);
-    const double r_ = r1 / cphi;
+    const double tcl = fmin(tphi, 1e150);
+    const double sec = sqrt(fma(tcl, tcl, 1.0)); // 1 / cos(phi)
+    const double cphi = 1.0 / sec;
+    const double r_ = r1 * sec;
     const double r2 = r0 * r0 + r_ * r_;
     double d2 = 0.0, d3 = 0.0;
 
     if (linedist2 < h2) {
-        const ITerms t = get_i_terms(r1 / sqrt(h2 - r0 * r0), a2, a);
+        const ITerms t = get_i_terms_cos(r1 / sqrt(h2 - r0 * r0), a2, a);
         d2 = -1.0 / 6.0 * t.i2 + 0.25 * r0h * t.i3 - 0.15 * r0h2 * t.i4;
         d2 += 1.0 / 30.0 * r0h3 * t.i5 - 1.0 / 60.0 * r0h_3 * t.i1;
         d2 += (b1 - b2) / r03 * t.i0;
     }
     if (linedist2 < 4.0 * h2) {
-        const ITerms t = get_i_terms(r1 / sqrt(4.0 * h2 - r0 * r0), a2, a);
+        const ITerms t = get_i_terms_cos(r1 / sqrt(4.0 * h2 - r0 * r0), a2, a);
         d3 = 1.0 / 3.0 * t.i2 - 0.25 * r0h * t.i3 + 3.0 / 40.0 * r0h2 * t.i4;
         d3 += -1.0 / 120.0 * r0h3 * t.i5 + 4.0 / 15.0 * r0h_3 * t.i1;
         d3 += (b2 - b3) / r03 * t.i0 + d2;
     }
-    const ITerms t = get_i_terms(cphi, a2, a);
+    const ITerms t = get_i_terms(cphi, phi, tcl, a2, a);
     if (r2 <= h2)
         return r0h3 / kPi * (1.0 / 6.0 * t.i2 - 3.0 / 40.0 * r0h2 * t.i4 + 1.0 / 40.0 * r0h3 * t.i5 + b1 / r03 * t.i0);
     if (r2 <= 4.0 * h2)
