@@ -240,7 +240,7 @@ __device__ double line_int3d(double r0, double r1, double d1, double d2, double 
 }
 
 // cubic_spline_exact.py:220-281
-__device__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx, double wy,
+__device__ __noinline__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx, double wy,
                               double h)
 {
     const double dx = x2 - x1, dy = y2 - y1;
