@@ -268,11 +268,29 @@ def run_gpu(args):
             if world > 1:
                 combine_image(out[0], dst=0)
 
-    host_out = torch.empty(out_shape, dtype=torch.float64).pin_memory()
+    slab_shape = (wl["nz"] // world, wl["ny"], wl["nx"]) if (dim3 and world > 1) else out_shape
+    host_out = torch.empty(slab_shape, dtype=torch.float64).pin_memory()
 
     def step_e2e():
-        # the call a Sarracen user reaches through backend='gpu': host arrays in, host array out
-        c = wl["cols"]
+        if world > 1:
+            # N ranks: pinned host columns -> device, partial raster, NCCL combine, result back to the
+            # host (rank 0's image, or every rank's z-slab of the grid) -- the multi-GPU recipe of
+            # INTEGRATION.md section 4 with the host copies inside the timed region
+            dcols = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            if dim3:
+                part = ops.scatter3d(dcols["x"], dcols["y"], dcols["z"], dcols["h"], [dcols["w"]], wf, wl["radius"],
+                                     raster)[0]
+                combine_grid_along_z(part, slab)
+                host_out.copy_(slab)
+            else:
+                part = ops.scatter2d(dcols["x"], dcols["y"], dcols["h"], [dcols["w"]], wf, wl["radius"], wl["ndim"],
+                                     raster)[0]
+                combine_image(part, dst=0)
+                if rank == 0:
+                    host_out.copy_(part)
+            torch.cuda.synchronize()
+            return host_out
+        # one GPU: the call a Sarracen user reaches through backend='gpu': host arrays in, host array out
         if dim3:
             img = s.B200Backend.interpolate_3d_grid(host["x"], host["y"], host["z"], host["w"], host["h"], wf,
                                                     wl["radius"], wl["nx"], wl["ny"], wl["nz"], *wl["lim"])
@@ -337,7 +355,7 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = float(te.item())
     h2d = sum(v.numel() * v.element_size() for k, v in host.items())
-    d2h = int(np.prod(out_shape)) * 8
+    d2h = int(np.prod(slab_shape)) * 8
 
     # ---- contributions (outside the timed region) ------------------------------
     contrib = ops.count_contributions(devc["x"], devc["y"], devc["h"], wl["radius"], raster,
