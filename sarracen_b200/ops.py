@@ -19,7 +19,10 @@ _KIND = {"cubic": _lib.SPHB_CUBIC, "quartic": _lib.SPHB_QUARTIC, "quintic": _lib
 
 # Workspace handling: one growing byte buffer per device.  A call whose bin
 # list would not fit in `max_workspace_fraction` of the free memory is split
-# into particle batches that accumulate into the same output.
+# into particle batches that accumulate into the same output.  The buffer is
+# shared by every call on that device: like the reference's backends, the
+# operators are synchronous and meant to be called from one host thread per
+# device (one process per GPU under torch.distributed).
 _workspaces = {}
 max_workspace_fraction = 0.6
 last_stats = {}
