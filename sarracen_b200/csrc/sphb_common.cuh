@@ -86,10 +86,9 @@ __device__ __forceinline__ float sqrt_guard(float) { return 1e-35f; }
 
 __device__ __forceinline__ double sqrt_pos(double a)
 {
-    // q^2 reaches here through second differences, so at a pixel centre that coincides with the
-    // particle it can come out as 0 or a rounding error below 0: floor it at 2^-975 with one
-    // integer max on the high word (negative doubles are negative ints) instead of an FP64 max.
-    a = __hiloint2double(max(__double2hiint(a), 0x03000000), __double2loint(a));
+    // a > 0 is the caller's job: every call site forms q^2 as fma(d * d, s, base) with
+    // base >= sqrt_guard() > 0, so no floor is needed here.  (When q^2 came from second differences
+    // it could round to <= 0 at a pixel centre on the particle and had to be floored.)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     double g = a * y, h = 0.5 * y;
@@ -98,7 +97,6 @@ __device__ __forceinline__ double sqrt_pos(double a)
 }
 __device__ __forceinline__ float sqrt_pos(float a)
 {
-    a = fmaxf(a, 1e-35f); // same guard against a rounded-to-zero or negative q^2 (one FMNMX)
     // one MUFU.RSQ: the argument is a normal number (callers add sqrt_guard), so the
     // denormal rescaling that rsqrtf() wraps around it is not needed
     float y;
