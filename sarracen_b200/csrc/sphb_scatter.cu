@@ -260,7 +260,7 @@ __global__ void lut_pairs_kernel(const double *lut, int samples, typename Real2<
 // tile origin subtracted; in float mode the centre is split into the nearest
 // pixel (ic) and a fraction in [-1/2, 1/2] so that position differences keep
 // full float precision however large the raster is.
-template <typename R, int NW, int BATCH> struct Staged {
+template <typename R, int NW, int BATCH, bool DIM3> struct Staged {
     using R2 = typename Real2<R>::type;
     // read one per lane when a warp scans the batch for its strip: the box along the split axis
     // (rows in 2-D, z-planes in 3-D), lo | hi << 16 -- kept as its own array so that the scan is
@@ -269,10 +269,10 @@ template <typename R, int NW, int BATCH> struct Staged {
     // the rest is read by whole warps (broadcast) when a particle hits: packed so that a hit costs
     // 4 (2-D) or 6 (3-D) 16-byte loads instead of 10-14 scalar ones
     int4 ibox[BATCH];            // bx, by (lo | hi << 16), cx, cy (nearest pixel in float mode, else 0)
-    int4 ibox3[BATCH];           // bz, cz, -, -
+    int4 ibox3[DIM3 ? BATCH : 1]; // bz, cz, -, -   (3-D only)
     R2 fxy[BATCH];               // centre (double mode) / fraction (float mode), tile-local pixel units
     R2 sxy[BATCH];               // (pixel width / h)^2
-    R2 fsz[BATCH];               // fz, sz
+    R2 fsz[DIM3 ? BATCH : 1];    // fz, sz         (3-D only)
     R2 ct[(NW + 2) / 2][BATCH];  // c (dz^2/h^2 of a cross-section), term[0] | term[1], term[2] | term[3], -
 };
 
@@ -318,10 +318,9 @@ __device__ __forceinline__ void add_contribution(R q2, R rad2, const LutView<R> 
 //          power of two >= box width, and accumulate into the warp's part of the
 //          shared-memory tile (plain load / fma / store).
 // Registers and shared memory are merged when the tile segment is flushed.
-// Particles staged per round.  The double-precision image kernel stages half a CTA's worth to
-// keep three CTAs per SM in shared memory next to the 40 KB tile and the 16 KB column table.
+// Particles staged per round: one per thread.
 template <typename R, bool DIM3, int WARPS> struct RenderBatch {
-    static constexpr int value = (sizeof(R) == 8 && !DIM3) ? WARPS * 16 : WARPS * 32;
+    static constexpr int value = WARPS * 32;
 };
 
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
@@ -345,7 +344,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *acc = reinterpret_cast<R *>(smem_raw);
-    Staged<R, NW, kBatch> *st = reinterpret_cast<Staged<R, NW, kBatch> *>(acc + (size_t)ACC * NW);
+    Staged<R, NW, kBatch, DIM3> *st = reinterpret_cast<Staged<R, NW, kBatch, DIM3> *>(acc + (size_t)ACC * NW);
     R2 *lut_s = reinterpret_cast<R2 *>(st + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -850,7 +849,7 @@ static int launch_render(const View &v, const T *recs, const sphb_kernel *k, con
 {
     using R2 = typename Real2<R>::type;
     auto kern = render_kernel<T, R, KIND, NW, DIM3, TX, TY, TZ, WARPS>;
-    const size_t fixed = sizeof(R) * (size_t)(TX + 8) * TY * TZ * NW + sizeof(Staged<R, NW, RenderBatch<R, DIM3, WARPS>::value>);
+    const size_t fixed = sizeof(R) * (size_t)(TX + 8) * TY * TZ * NW + sizeof(Staged<R, NW, RenderBatch<R, DIM3, WARPS>::value, DIM3>);
     const size_t limit = 227 * 1024;
     size_t smem = fixed;
     if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
