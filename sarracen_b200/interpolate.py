@@ -140,6 +140,10 @@ class _Device:
 
     def col(self, name: str) -> torch.Tensor:
         if name not in self.cache:
+            resident = getattr(self.data, "_device_cache", None)
+            if resident and name in resident and resident[name].device == self.dev:
+                self.cache[name] = resident[name].to(self.dtype).contiguous()  # no copy if dtype matches
+                return self.cache[name]
             arr = np.ascontiguousarray(self.data[name].to_numpy())
             if not arr.flags.writeable:  # pandas copy-on-write views; torch wants a writable buffer
                 arr = arr.copy()

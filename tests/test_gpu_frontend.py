@@ -74,3 +74,23 @@ def test_normalized_constant_field_is_constant():
     inside = img != 0
     assert inside.any() and not inside.all()
     np.testing.assert_allclose(img[inside], 2.5, rtol=1e-12)
+
+
+def test_device_resident_frame_gives_the_same_results():
+    """ParticleFrame.to_device(): columns stay on the GPU between calls; same result (to the rounding of the
+    order in which red.global.add.f64 lands, which differs from run to run)."""
+    import sarracen_b200 as s
+    from sarracen_b200 import interpolate as front
+    rng = np.random.default_rng(8)
+    n = 5000
+    cols = dict(x=rng.uniform(0, 1, n), y=rng.uniform(0, 1, n), z=rng.uniform(0, 1, n), h=rng.uniform(0.01, 0.08, n),
+                m=np.full(n, 1.0 / n), rho=rng.uniform(0.5, 2, n), T=rng.uniform(0, 1, n))
+    sdf = s.ParticleFrame(cols, params={"hfact": 1.2})
+    kw = dict(x_pixels=64, y_pixels=48, xlim=(0, 1), ylim=(0, 1), rotation=[10, 20, 30], rot_origin="com")
+    a = front.interpolate_3d_proj(sdf, "T", **kw)
+    sdf.to_device()
+    assert sdf._device_cache["x"].is_cuda
+    b = front.interpolate_3d_proj(sdf, "T", **kw)
+    np.testing.assert_allclose(a, b, rtol=1e-13, atol=0)
+    sdf.release_device()
+    assert sdf._device_cache is None
