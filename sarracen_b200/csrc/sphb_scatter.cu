@@ -511,7 +511,10 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                     }
                     if (NW > 3) term[3] = st->ct[2][s].x;
 
-                    if (wx > TX / 2) {
+                    // wide when the box spans more than half the tile width (a quarter in float mode,
+                    // where idle lanes are cheaper than the narrow path's shared-memory updates:
+                    // 65.5 -> 63.0 ms on config 2; no gain in double)
+                    if (wx > TX / (sizeof(R) == 4 ? 4 : 2)) {
                         // ---- wide: fixed pixels, register accumulators -------------
                         // Every lane evaluates its own pixels: a pixel outside the
                         // footprint box has q >= R and W(q) = 0 there (the table is
