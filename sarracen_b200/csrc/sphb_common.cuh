@@ -254,11 +254,6 @@ __device__ __forceinline__ void red_add(double *addr, double v)
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
-template <typename T> __device__ __forceinline__ double load_as_double(const void *base, int64_t i)
-{
-    return (double)__ldg(reinterpret_cast<const T *>(base) + i);
-}
-
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

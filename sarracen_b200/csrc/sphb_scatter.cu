@@ -525,10 +525,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                         const R dx = int_to_real(lx - cx, R(0)) - fx;
                         const R qx = fma(dx * dx, sx, cc) + sqrt_guard(R(0));
                         const R dy0 = int_to_real(own_y0 + ly - cy, R(0)) - fy;
-                        #ifndef SPHB_ROW_GROUP
-#define SPHB_ROW_GROUP 4
-#endif
-                        constexpr int G = K % SPHB_ROW_GROUP == 0 ? SPHB_ROW_GROUP : (K % 2 == 0 ? 2 : 1);
+                        constexpr int G = K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1);
 #pragma unroll
                         for (int r0 = 0; r0 < K; r0 += G) {
                             R q[G];
