@@ -343,3 +343,23 @@ def test_particle_exactly_on_a_pixel_centre(B, n):
         ref = OracleBackend.interpolate_3d_grid(x, y, z, w, h, OracleKernel("cubic"), 2, n, n, n, -1.0, 1.0, -1.0, 1.0,
                                                 -1.0, 1.0)
         assert_parity(out, ref, TOL64, f"grid {n}")
+
+
+def test_backend_accepts_what_the_front_end_passes(B):
+    """pandas Series, column views of an N x 3 array (non-contiguous), integer weight
+    columns and a float32 h next to float64 positions all reach the backend."""
+    import pandas as pd
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(31)
+    n = 800
+    pos = rng.uniform(0, 1, (n, 3))
+    x, y, z = pos[:, 0], pos[:, 1], pos[:, 2]           # strided views
+    h32 = rng.uniform(0.02, 0.1, n).astype(np.float32)
+    wi = rng.integers(1, 5, n)                           # integer weights
+    k = _kernel("cubic")
+    out = B.interpolate_3d_cross(pd.Series(x), pd.Series(y), z, 0.5, wi, pd.Series(h32), k.w, 2, 33, 21, 0, 1, 0, 1)
+    ref = OracleBackend.interpolate_3d_cross(x, y, z, 0.5, wi.astype(float), h32.astype(float), OracleKernel("cubic"),
+                                             2, 33, 21, 0, 1, 0, 1)
+    assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+    assert_parity(out, ref, TOL64, "mixed inputs")
+    assert x.base is pos and not x.flags["C_CONTIGUOUS"]  # inputs untouched
