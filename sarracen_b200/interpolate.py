@@ -133,7 +133,10 @@ class _Device:
             raise RuntimeError("sarracen_b200.interpolate needs a CUDA device; there is no CPU fallback")
         self.data = data
         self.dev = torch.device("cuda", torch.cuda.current_device())
-        dtypes = [np.asarray(data[c]).dtype for c in columns if c is not None and c in data.columns]
+        flat = []
+        for c in columns:  # a target may be a list of labels
+            flat.extend(c if isinstance(c, (list, tuple)) else [c])
+        dtypes = [np.asarray(data[c]).dtype for c in flat if isinstance(c, str) and c in data.columns]
         self.dtype = torch.float32 if dtypes and all(dt == np.float32 for dt in dtypes) else torch.float64
         self.cache = {}
         self.n = len(data)
@@ -257,6 +260,26 @@ def _finish(grids: List[torch.Tensor], norm: Optional[torch.Tensor]) -> List[np.
     return [_host(g) for g in grids]
 
 
+def _target_weights(dv, target, dens_weight, normalize):
+    """Weight columns of one call.  `target` is a column label as in the reference, or -- an
+    extension -- a list / tuple of up to three labels (four without normalisation) that share the
+    bin, sort and footprint walk (several columns rendered on the same geometry)."""
+    many = isinstance(target, (list, tuple))
+    names = list(target) if many else [target]
+    limit = ops._lib.SPHB_MAX_WEIGHTS - (1 if normalize else 0)
+    if not 1 <= len(names) <= limit:
+        raise ValueError(f"between 1 and {limit} targets can share one call")
+    weights = [dv.weight(t, dens_weight) for t in names]
+    if normalize:
+        weights.append(dv.weight(None, dens_weight))
+    return weights, many
+
+
+def _finish_targets(out, normalize, many):
+    grids = _finish(out[:-1] if normalize else out, out[-1] if normalize else None)
+    return grids if many else grids[0]
+
+
 def _image(dv, x_t, y_t, h_t, weights, wf, radius, ndim, raster, exact, exact_fn, z_t=None, z_slice=None):
     if exact:
         return exact_fn(x_t, y_t, h_t, weights, raster)
@@ -276,13 +299,13 @@ def interpolate_2d(data, target, x=None, y=None, kernel: Optional[BaseKernel] = 
     xlim, ylim = _bounds(dv.col(x), dv.col(y), xlim, ylim)
     x_pixels, y_pixels = _set_pixels(x_pixels, y_pixels, xlim, ylim)
     _check_boundaries(x_pixels, y_pixels, xlim, ylim)
-    weights = [dv.weight(target, dens_weight)] + ([dv.weight(None, dens_weight)] if normalize else [])
+    weights, many = _target_weights(dv, target, dens_weight, normalize)
     kernel = kernel if kernel is not None else data.kernel
     pix = max((xlim[1] - xlim[0]) / x_pixels, (ylim[1] - ylim[0]) / y_pixels)
     r = ops.Raster(x_pixels, y_pixels, xlim[0], xlim[1], ylim[0], ylim[1])
     out = _image(dv, dv.col(x), dv.col(y), dv.smoothing(hmin, pix), weights, kernel.w, kernel.get_radius(), 2, r,
                  exact, ops.exact2d)
-    return _finish(out[:1], out[1] if normalize else None)[0]
+    return _finish_targets(out, normalize, many)
 
 
 def interpolate_2d_vec(data, target_x, target_y, x=None, y=None, kernel: Optional[BaseKernel] = None,
@@ -322,7 +345,7 @@ def interpolate_2d_line(data, target, x=None, y=None, kernel: Optional[BaseKerne
     _verify_columns(data, x, y)
     _check_backend(backend, data)
     dv = _Device(data, [x, y, data.hcol, data.mcol, data.rhocol, target])
-    weights = [dv.weight(target, dens_weight)] + ([dv.weight(None, dens_weight)] if normalize else [])
+    weights, many = _target_weights(dv, target, dens_weight, normalize)
     xlim, ylim = _bounds(dv.col(x), dv.col(y), _line_limits(xlim), _line_limits(ylim))
     if xlim[0] == xlim[1] and ylim[0] == ylim[1]:
         raise ValueError("Zero length cross section!")
@@ -333,7 +356,7 @@ def interpolate_2d_line(data, target, x=None, y=None, kernel: Optional[BaseKerne
     pix = np.sqrt((xlim[1] - xlim[0]) ** 2 + (ylim[1] - ylim[0]) ** 2) / pixels
     out = ops.line2d(dv.col(x), dv.col(y), dv.smoothing(hmin, pix), weights, kernel.w, kernel.get_radius(), pixels,
                      xlim[0], xlim[1], ylim[0], ylim[1])
-    return _finish(out[:1], out[1] if normalize else None)[0]
+    return _finish_targets(out, normalize, many)
 
 
 def interpolate_3d_line(data, target, x=None, y=None, z=None, kernel: Optional[BaseKernel] = None, pixels=None,
@@ -345,7 +368,7 @@ def interpolate_3d_line(data, target, x=None, y=None, z=None, kernel: Optional[B
     _verify_columns(data, x, y)
     _check_backend(backend, data)
     dv = _Device(data, [x, y, z, data.hcol, data.mcol, data.rhocol, target])
-    weights = [dv.weight(target, dens_weight)] + ([dv.weight(None, dens_weight)] if normalize else [])
+    weights, many = _target_weights(dv, target, dens_weight, normalize)
     xlim, ylim, zlim = _line_limits(xlim), _line_limits(ylim), _line_limits(zlim)
     zmin = float(dv.col(z).min().item())  # both defaults are the minimum (interpolate.py:905-906)
     zlim = (zmin if zlim is None or zlim[0] is None else zlim[0], zmin if zlim is None or zlim[1] is None else zlim[1])
@@ -359,7 +382,7 @@ def interpolate_3d_line(data, target, x=None, y=None, z=None, kernel: Optional[B
     pix = np.sqrt((xlim[1] - xlim[0]) ** 2 + (ylim[1] - ylim[0]) ** 2 + (zlim[1] - zlim[0]) ** 2) / pixels
     out = ops.line3d(dv.col(x), dv.col(y), dv.col(z), dv.smoothing(hmin, pix), weights, kernel.w,
                      kernel.get_radius(), pixels, xlim[0], xlim[1], ylim[0], ylim[1], zlim[0], zlim[1])
-    return _finish(out[:1], out[1] if normalize else None)[0]
+    return _finish_targets(out, normalize, many)
 
 
 def interpolate_3d_proj(data, target, x=None, y=None, kernel: Optional[BaseKernel] = None, integral_samples=1000,
@@ -372,9 +395,12 @@ def interpolate_3d_proj(data, target, x=None, y=None, kernel: Optional[BaseKerne
     _verify_columns(data, x, y)
     _check_backend(backend, data)
     if dens_weight is None:
-        dens_weight = (target != "rho")
+        flags = {t != "rho" for t in (target if isinstance(target, (list, tuple)) else [target])}
+        if len(flags) != 1:
+            raise ValueError("pass dens_weight explicitly when 'rho' is rendered together with other targets")
+        dens_weight = flags.pop()
     dv = _Device(data, [data.xcol, data.ycol, data.zcol, x, y, data.hcol, data.mcol, data.rhocol, target])
-    weights = [dv.weight(target, dens_weight)] + ([dv.weight(None, dens_weight)] if normalize else [])
+    weights, many = _target_weights(dv, target, dens_weight, normalize)
     if corotation is not None:
         rotation, rot_origin = _corotate(corotation, rotation)
     x_t, y_t, _ = dv.rotate_xyz(x, y, z, rotation, rot_origin)
@@ -387,7 +413,7 @@ def interpolate_3d_proj(data, target, x=None, y=None, kernel: Optional[BaseKerne
     r = ops.Raster(x_pixels, y_pixels, xlim[0], xlim[1], ylim[0], ylim[1])
     out = _image(dv, x_t, y_t, dv.smoothing(hmin, pix), weights, wf, kernel.get_radius(), 2, r, exact,
                  ops.exact3d_proj)
-    return _finish(out[:1], out[1] if normalize else None)[0]
+    return _finish_targets(out, normalize, many)
 
 
 def interpolate_3d_vec(data, target_x, target_y, target_z, x=None, y=None, kernel: Optional[BaseKernel] = None,
@@ -434,7 +460,7 @@ def interpolate_3d_cross(data, target, x=None, y=None, z=None, z_slice=None, ker
     dv = _Device(data, [data.xcol, data.ycol, data.zcol, x, y, z, data.hcol, data.mcol, data.rhocol, target])
     if z_slice is None:
         z_slice = float(dv.col(z).to(torch.float64).mean().item())  # of the unrotated column (:1327-1328)
-    weights = [dv.weight(target, dens_weight)] + ([dv.weight(None, dens_weight)] if normalize else [])
+    weights, many = _target_weights(dv, target, dens_weight, normalize)
     kernel = kernel if kernel is not None else data.kernel
     if corotation is not None:
         rotation, rot_origin = _corotate(corotation, rotation)
@@ -446,7 +472,7 @@ def interpolate_3d_cross(data, target, x=None, y=None, z=None, z_slice=None, ker
     r = ops.Raster(x_pixels, y_pixels, xlim[0], xlim[1], ylim[0], ylim[1])
     out = ops.scatter2d(x_t, y_t, dv.smoothing(hmin, pix), weights, kernel.w, kernel.get_radius(), 3, r, z=z_t,
                         z_slice=float(z_slice))
-    return _finish(out[:1], out[1] if normalize else None)[0]
+    return _finish_targets(out, normalize, many)
 
 
 def interpolate_3d_cross_vec(data, target_x, target_y, target_z, z_slice=None, x=None, y=None, z=None,
@@ -491,7 +517,7 @@ def interpolate_3d_grid(data, target, x=None, y=None, z=None, kernel: Optional[B
     _verify_columns(data, x, y)
     _check_backend(backend, data)
     dv = _Device(data, [data.xcol, data.ycol, data.zcol, x, y, z, data.hcol, data.mcol, data.rhocol, target])
-    weights = [dv.weight(target, dens_weight)] + ([dv.weight(None, dens_weight)] if normalize else [])
+    weights, many = _target_weights(dv, target, dens_weight, normalize)
     x_t, y_t, z_t = dv.rotate_xyz(x, y, z, rotation, rot_origin)
     xlim, ylim = _bounds(x_t, y_t, xlim if xlim else (None, None), ylim if ylim else (None, None))
     zlim = zlim if zlim else (float(z_t.min().item()), float(z_t.max().item()))
@@ -507,4 +533,4 @@ def interpolate_3d_grid(data, target, x=None, y=None, z=None, kernel: Optional[B
     pix = max((xlim[1] - xlim[0]) / x_pixels, (ylim[1] - ylim[0]) / y_pixels)  # x / y only (:1619-1620)
     r = ops.Raster(x_pixels, y_pixels, xlim[0], xlim[1], ylim[0], ylim[1], z_pixels, zlim[0], zlim[1])
     out = ops.scatter3d(x_t, y_t, z_t, dv.smoothing(hmin, pix), weights, kernel.w, kernel.get_radius(), r)
-    return _finish(out[:1], out[1] if normalize else None)[0]
+    return _finish_targets(out, normalize, many)

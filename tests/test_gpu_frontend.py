@@ -94,3 +94,26 @@ def test_device_resident_frame_gives_the_same_results():
     np.testing.assert_allclose(a, b, rtol=1e-13, atol=0)
     sdf.release_device()
     assert sdf._device_cache is None
+
+
+def test_several_targets_share_one_walk():
+    """Extension: a list of targets is rendered in one bin / sort / walk and equals the
+    single-target calls."""
+    import sarracen_b200 as s
+    from sarracen_b200 import interpolate as front, ops
+    rng = np.random.default_rng(12)
+    n = 4000
+    cols = dict(x=rng.uniform(0, 1, n), y=rng.uniform(0, 1, n), z=rng.uniform(0, 1, n), h=rng.uniform(0.01, 0.08, n),
+                m=np.full(n, 1.0 / n), rho=rng.uniform(0.5, 2, n), T=rng.uniform(0, 1, n), P=rng.uniform(1, 2, n),
+                B=rng.normal(size=n))
+    sdf = s.ParticleFrame(cols, params={"hfact": 1.2})
+    kw = dict(x_pixels=48, y_pixels=40, xlim=(0, 1), ylim=(0, 1))
+    for fn, extra in ((front.interpolate_3d_proj, {}), (front.interpolate_3d_cross, dict(z_slice=0.4)),
+                      (front.interpolate_3d_grid, dict(z_pixels=8, zlim=(0, 1)))):
+        imgs = fn(sdf, ["T", "P", "B"], **kw, **extra)
+        assert isinstance(imgs, list) and len(imgs) == 3
+        for name, img in zip(("T", "P", "B"), imgs):
+            np.testing.assert_allclose(img, fn(sdf, name, **kw, **extra), rtol=1e-12, atol=1e-15)
+    with pytest.raises(ValueError):
+        front.interpolate_3d_proj(sdf, ["T", "P", "B", "rho"], dens_weight=True, **kw)   # 4 targets + norm > 4 weights
+    assert len(front.interpolate_3d_proj(sdf, ["T", "P", "B", "rho"], dens_weight=True, normalize=False, **kw)) == 4
