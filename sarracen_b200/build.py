@@ -38,19 +38,24 @@ def _stale(target, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False) -> str:
+    """debug_bounds=True builds lib/libsphb200_dbg.so with -DSPHB_DEBUG_BOUNDS (device asserts on
+    every index the kernels form); point SPHB_LIB_OVERRIDE at it to run the GPU tests against it."""
     os.makedirs(BUILD_DIR, exist_ok=True)
     nvcc = _nvcc()
+    suffix = "_dbg" if debug_bounds else ""
+    flags = NVCC_FLAGS + (["-DSPHB_DEBUG_BOUNDS"] if debug_bounds else [])
+    lib = LIB.replace(".so", suffix + ".so")
     jobs = []
     for src in SOURCES:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(BUILD_DIR, src.replace(".cu", suffix + ".o"))
         if force or _stale(obj, [path] + HEADERS):
             jobs.append((path, obj))
 
     def compile_one(job):
         path, obj = job
-        cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-c", path, "-o", obj]
+        cmd = [nvcc] + ARCH + flags + ["-c", path, "-o", obj]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         log = obj.replace(".o", ".ptxas.log")
         with open(log, "w") as f:
@@ -65,12 +70,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             for o in outs:
                 print(o)
-    objs = [os.path.join(BUILD_DIR, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs
+    objs = [os.path.join(BUILD_DIR, s.replace(".cu", suffix + ".o")) for s in SOURCES]
+    if force or jobs or _stale(lib, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", lib] + objs
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug_bounds="--debug-bounds" in sys.argv))

@@ -27,6 +27,17 @@ void set_error(const char *fmt, ...);
 
 #define SPHB_LAUNCH_CHECK() SPHB_CUDA(cudaGetLastError())
 
+// Index checks for debug builds (python -m sarracen_b200.build --debug-bounds builds
+// lib/libsphb200_dbg.so; run the GPU tests against it with SPHB_LIB_OVERRIDE).  compute-sanitizer
+// is not available on the target pool, so every shared-memory / raster / table index the kernels
+// form is asserted in that build instead.
+#ifdef SPHB_DEBUG_BOUNDS
+#include <cassert>
+#define SPHB_ASSERT(cond) assert(cond)
+#else
+#define SPHB_ASSERT(cond) ((void)0)
+#endif
+
 constexpr double kPi = 3.14159265358979323846;
 
 // sigma_d of each kernel (cubic_spline.py:15-17, quartic_spline.py:15-17,
@@ -71,6 +82,7 @@ template <int KIND> __device__ __host__ constexpr bool is_lut() { return KIND ==
 template <int KIND, typename R>
 __device__ __forceinline__ typename Real2<R>::type lut_entry(const LutView<R> &lut, int i)
 {
+    SPHB_ASSERT(i >= 0 && i <= lut.last);
     if (KIND == SPHB_COLUMN_LUT_GLOBAL) return __ldg(lut.gtab + i);
     return lut.tab[i];
 }

@@ -357,6 +357,7 @@ exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, cons
             val = s * (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
         }
         if (val != 0.0) {
+            SPHB_ASSERT(i >= 0 && i < v.nx && j >= 0 && j < v.ny && p >= 0 && p < n);
 #pragma unroll
             for (int k = 0; k < NW; k++)
                 red_add(outs[k] + (size_t)j * v.nx + i, (double)__ldg(wsrc[k] + p) * val);

@@ -155,6 +155,7 @@ line_kernel(LineGeom g, const T *__restrict__ x, const T *__restrict__ y, const 
                 }
                 const double wv = kernel_eval_any<KIND>(q, g.radius, lut, g.lut_samples);
 #pragma unroll
+                SPHB_ASSERT(i >= 0 && i < g.pixels);
                 for (int k = 0; k < NW; k++) {
                     if (use_smem)
                         mine[k * g.pixels + i] += st[k] * wv;

@@ -54,6 +54,7 @@ struct View {
     int ndim;  // exponent of h in the particle term
     double norm;
     int rec_stride;    // elements per packed particle record (4 or 8)
+    unsigned long long n_out;   // raster elements per weight (debug index checks)
     int small_edge;    // footprint boxes with every edge <= this many pixels take the direct path
     uint32_t flag_bit; // key bit that marks a direct-path particle (sorts after all tile pairs)
 };
@@ -214,6 +215,7 @@ emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, const 
         }
     }
     uint64_t o = offsets[i];
+    SPHB_ASSERT(o < offsets[n]);
     if (small) {
         keys[o] = (uint32_t)((b.z0 * v.nty + b.y0) * v.ntx + b.x0) | v.flag_bit;
         vals[o] = (uint32_t)i;
@@ -222,6 +224,7 @@ emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, const 
     for (int tz = b.z0; tz <= b.z1; tz++)
         for (int ty = b.y0; ty <= b.y1; ty++)
             for (int tx = b.x0; tx <= b.x1; tx++) {
+                SPHB_ASSERT(o < offsets[n] && tx < v.ntx && ty < v.nty && tz < v.ntz);
                 keys[o] = (uint32_t)((tz * v.nty + ty) * v.ntx + tx);
                 vals[o] = (uint32_t)i;
                 o++;
@@ -395,6 +398,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
 
     while (pos < chunk_hi) {
         const uint32_t tile = keys[pos];
+        SPHB_ASSERT(tile < (uint32_t)(v.ntx * v.nty * v.ntz) && (int64_t)tile_end[tile] > pos);
         const int64_t seg_hi = min((int64_t)tile_end[tile], chunk_hi);
         const int ttx = tile % v.ntx, tty = (tile / v.ntx) % v.nty, ttz = tile / (v.ntx * v.nty);
         const int ox = ttx * TX, oy = tty * TY, oz = ttz * TZ; // tile origin in pixels
@@ -450,6 +454,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                     const double dz = v.z_slice - (double)pr.z;
                     cc = dz * dz * hinv2;
                 }
+                SPHB_ASSERT(tid < kBatch && p >= 0);
                 st->key[tid] = key;
                 const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
                 R tv[4] = {R(0), R(0), R(0), R(0)};
@@ -581,6 +586,8 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                                 if (q2 < rad2) {
                                     const R wv = kernel_eval_q2<KIND, R>(q2, lv);
 #pragma unroll
+                                    SPHB_ASSERT(px >= 0 && px < TX && py >= own_y0 && py < own_y0 + ROWS &&
+                                                a >= acc && a + (NW - 1) * ACC < acc + (size_t)ACC * NW);
                                     for (int k = 0; k < NW; k++) a[k * ACC] = fma(term[k], wv, a[k * ACC]);
                                 }
                             }
@@ -615,6 +622,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                 for (int k = 0; k < NW; k++) {
                     const R val = acc[k * ACC + a];
                     if (val != R(0)) {
+                        SPHB_ASSERT(o < v.n_out && a < ACC);
                         red_add(outs[k] + o, (double)val);
                         acc[k * ACC + a] = R(0);
                     }
@@ -768,12 +776,14 @@ direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                             if (q2 < rad2) {
                                 const R wv = kernel_eval_pos<KIND, R>(q2, lv);
 #pragma unroll
+                                SPHB_ASSERT(oo < v.n_out);
                                 for (int k = 0; k < NW; k++) red_add(outs[k] + oo, (double)(term[k] * wv));
                             }
                             oo += (size_t)v.ny * v.nx;
                         }
                     } else if (qxy < rad2) {
                         const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
+                        SPHB_ASSERT(o < v.n_out);
 #pragma unroll
                         for (int k = 0; k < NW; k++) red_add(outs[k] + o, (double)(term[k] * wv));
                     }
@@ -1050,6 +1060,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     end_bit++;
     const int64_t n = p->n;
     const size_t n_out = (size_t)v.nx * v.ny * v.nz;
+    v.n_out = n_out;
 
     if (!accumulate)
         for (int i = 0; i < p->n_weights; i++)
