@@ -103,8 +103,11 @@ __device__ __forceinline__ double sqrt_pos(double a)
     // it could round to <= 0 at a pixel centre on the particle and had to be floored.)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double g = a * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
+    // y / 2 by an integer decrement of the exponent (y is a normal number): one FP64-pipe
+    // instruction less per square root
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
+    const double g = a * y;
+    const double r = fma(-g, h, 0.5);
     return fma(g, r, g);
 }
 __device__ __forceinline__ float sqrt_pos(float a)
@@ -159,42 +162,43 @@ template <int KIND, typename R> __device__ __forceinline__ R kernel_shape(R q)
     }
 }
 
-// floor(t) for 0 <= t < 2^22 without the conversion pipe: adding 1.5 * 2^52
-// (1.5 * 2^23) leaves rint(t - 1/2) in the low mantissa bits.  The 1.5 keeps
-// the sum inside one binade (unit spacing) even when t - 1/2 is negative.
-// When t is an exact integer the index may come out one lower with f = 1,
-// which evaluates to the same table value.
-__device__ __forceinline__ int floor_nonneg(double t, double &f)
+// Column-table lookup.  The reference evaluates T[i] + f (T[i+1] - T[i]) with i = floor(t),
+// f = t - i, t = q (S - 1) / R (sarracen/kernels/base_kernel.py:88-110 via np.interp).  On each
+// segment that is the straight line A_i + B_i q with B_i = (T[i+1] - T[i]) (S - 1) / R and
+// A_i = T[i] - i (T[i+1] - T[i]); the table holds (A_i, B_i), so a lookup is one fused
+// multiply-add for the index -- q * scale + 1.5 * 2^52 rounded DOWN leaves floor(t) in the low
+// mantissa bits -- and one for the value.  Values agree with the reference's form to a few ulp
+// of max|T| (A_i carries the cancellation i dT_i ~ q T'(q)).
+__device__ __forceinline__ int lut_index(double q, double scale)
 {
-    const double magic = 6755399441055744.0;
-    double m = (t - 0.5) + magic;
-    int i = __double2loint(m);
-    f = t - (m - magic);
-    return i;
+    return __double2loint(__fma_rd(q, scale, 6755399441055744.0));
 }
-__device__ __forceinline__ int floor_nonneg(float t, float &f)
+__device__ __forceinline__ int lut_index(float q, float scale)
 {
-    const float magic = 12582912.0f;
-    float m = (t - 0.5f) + magic;
-    int i = __float_as_int(m) & 0x3fffff;
-    f = t - (m - magic);
-    return i;
+    return __float_as_int(__fmaf_rd(q, scale, 12582912.0f)) & 0x3fffff;
 }
-
-// W(q) from q^2 (caller guarantees q^2 < radius^2).
-template <int KIND, typename R>
-__device__ __forceinline__ R kernel_eval_q2(R q2, const LutView<R> &lut)
+// Table entry i from T (double, S samples): shared by every kernel that builds the table.
+template <typename R>
+__device__ __forceinline__ typename Real2<R>::type lut_make_entry(const double *lut, int samples, int i, double scale)
 {
-    R q = fast_sqrt(q2);
-    if (is_lut<KIND>()) {
-        R f;
-        int i = floor_nonneg(q * lut.scale, f);
-        i = max(0, min(i, lut.last));
-        typename Real2<R>::type e = lut_entry<KIND>(lut, i);
-        return fma(f, e.y, e.x);
-    } else {
-        return kernel_shape<KIND>(q);
+    typename Real2<R>::type e;
+    if (i >= samples - 1) {
+        // the clamp target of out-of-support lookups: W(q >= R) = 0
+        e.x = e.y = R(0);
+        return e;
     }
+    const double a = lut[i], d = lut[i + 1] - a;
+    e.x = (R)(a - (double)i * d);
+    e.y = (R)(d * scale);
+    return e;
+}
+template <int KIND, typename R>
+__device__ __forceinline__ R lut_eval(R q, const LutView<R> &lut)
+{
+    int i = lut_index(q, lut.scale);
+    i = min(i, lut.last);
+    typename Real2<R>::type e = lut_entry<KIND>(lut, i);
+    return fma(e.y, q, e.x);
 }
 
 // W(q) from 0 < q^2 < radius^2 (the caller has tested the range and added
@@ -204,11 +208,7 @@ __device__ __forceinline__ R kernel_eval_pos(R q2, const LutView<R> &lut)
 {
     R q = sqrt_pos(q2);
     if (is_lut<KIND>()) {
-        R f;
-        int i = floor_nonneg(q * lut.scale, f);
-        i = min(i, lut.last);
-        typename Real2<R>::type e = lut_entry<KIND>(lut, i);
-        return fma(f, e.y, e.x);
+        return lut_eval<KIND, R>(q, lut);
     } else {
         return kernel_shape<KIND>(q);
     }
@@ -222,11 +222,7 @@ __device__ __forceinline__ R kernel_eval_unguarded(R q2, R rad2, const LutView<R
 {
     R q = sqrt_pos(q2);
     if (is_lut<KIND>()) {
-        R f;
-        int i = floor_nonneg(q * lut.scale, f);
-        i = min(i, lut.last);
-        typename Real2<R>::type e = lut_entry<KIND>(lut, i);
-        return fma(f, e.y, e.x);
+        return lut_eval<KIND, R>(q, lut);
     } else {
         R w = kernel_shape<KIND>(q);
         return q2 < rad2 ? w : R(0);

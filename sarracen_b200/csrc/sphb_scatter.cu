@@ -244,16 +244,11 @@ __global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t 
 constexpr int kLutSharedMax = 2048;
 
 template <typename R>
-__global__ void lut_pairs_kernel(const double *lut, int samples, typename Real2<R>::type *out)
+__global__ void lut_pairs_kernel(const double *lut, int samples, double scale, typename Real2<R>::type *out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= samples) return;
-    const double a = lut[i], b = (i + 1 < samples) ? lut[i + 1] : lut[i];
-    typename Real2<R>::type e;
-    e.x = (R)a;
-    e.y = (R)(b - a);
-    if (i == samples - 1) e.x = e.y = R(0); // clamp target of out-of-support lookups
-    out[i] = e;
+    out[i] = lut_make_entry<R>(lut, samples, i, scale);
 }
 
 // ---------------------------------------------------------------------------
@@ -296,18 +291,6 @@ template <> struct Split<float> {
         f = (float)(u - r);
     }
 };
-
-// One evaluation of a staged particle at one pixel, given q^2.
-template <int KIND, typename R, int NW>
-__device__ __forceinline__ void add_contribution(R q2, R rad2, const LutView<R> &lv, const R (&term)[NW],
-                                                 R (&dst)[NW])
-{
-    if (q2 < rad2) {
-        const R wv = kernel_eval_q2<KIND, R>(q2, lv);
-#pragma unroll
-        for (int k = 0; k < NW; k++) dst[k] = fma(term[k], wv, dst[k]);
-    }
-}
 
 // Tile render.  Work split inside a CTA of kWarps warps:
 //   2-D tile TX x TY pixels: warp w owns the strip of rows [w TY/8, (w+1) TY/8);
@@ -353,7 +336,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *outs[4] = {o0, o1, o2, o3};
 
-    // Column table in shared memory as (T[i], T[i+1] - T[i]) pairs.  (Replicating it so that every
+    // Column table in shared memory as segment lines (A_i, B_i), see lut_index().  (Replicating it so that every
     // lane of an access phase owns a bank group was measured on config 2: 1, 2, 4, 8 copies ->
     // 124, 127, 145, 216 ms, every doubling costs a resident CTA; the random index is not the
     // bottleneck.)
@@ -363,16 +346,10 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     lv.scale = R(0);
     lv.last = 0;
     if (is_lut<KIND>()) {
-        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kThreads) {
-            double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
-            R2 e;
-            e.x = (R)a;
-            e.y = (R)(b - a);
-            // the clamp target of out-of-support lookups: W(q >= R) = 0
-            if (i == lut_samples - 1) e.x = e.y = R(0);
-            lut_s[i] = e;
-        }
-        lv.scale = (R)((double)(lut_samples - 1) / v.radius);
+        const double lut_scale = (double)(lut_samples - 1) / v.radius;
+        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kThreads)
+            lut_s[i] = lut_make_entry<R>(lut, lut_samples, i, lut_scale);
+        lv.scale = (R)lut_scale;
         lv.last = lut_samples - 1;
     }
     for (int i = tid; i < ACC * NW; i += kThreads) acc[i] = R(0);
@@ -430,8 +407,8 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                 int cx, cy;
                 Split<R>::apply(ux, f.x, cx);
                 Split<R>::apply(uy, f.y, cy);
-                sc.x = (R)(v.pwx * v.pwx * hinv2);
-                sc.y = (R)(v.pwy * v.pwy * hinv2);
+                sc.x = (R)(v.pwx * hinv); // pixel -> q along x and y
+                sc.y = (R)(v.pwy * hinv);
                 st->ibox[tid] = make_int4((int)bx, (int)by, cx, cy);
                 st->fxy[tid] = f;
                 st->sxy[tid] = sc;
@@ -527,9 +504,9 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                         // selected to 0), so no box tests are needed.  Rows are handled G at
                         // a time without branches so the G dependent square-root /
                         // table chains overlap; groups that cannot contribute are skipped.
-                        const R dx = int_to_real(lx - cx, R(0)) - fx;
-                        const R qx = fma(dx * dx, sx, cc) + sqrt_guard(R(0));
-                        const R dy0 = int_to_real(own_y0 + ly - cy, R(0)) - fy;
+                        const R dx = (int_to_real(lx - cx, R(0)) - fx) * sx;
+                        const R qx = fma(dx, dx, cc) + sqrt_guard(R(0));
+                        const R dy0 = (int_to_real(own_y0 + ly - cy, R(0)) - fy) * sy;
                         constexpr int G = K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1);
 #pragma unroll
                         for (int r0 = 0; r0 < K; r0 += G) {
@@ -543,8 +520,8 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                                 // it shows as an error of sqrt(1e-14) in q right at q = 0, which a
                                 // coarse column table (integral_samples = 2: a cusp at 0) turns into
                                 // 4e-9 -- found by tests/test_gpu_fuzz.py.
-                                const R dy = dy0 + R((r0 + j) * RI);
-                                q[j] = fma(dy * dy, sy, qx);
+                                const R dy = (r0 + j) == 0 ? dy0 : fma(R((r0 + j) * RI), sy, dy0);
+                                q[j] = fma(dy, dy, qx);
                                 if (sizeof(R) == 4) any = any || (q[j] < rad2);
                             }
                             // Skip a group that cannot contribute.  double: rows that miss the
@@ -575,19 +552,20 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                         const int px = x0 + (lane & ((1 << lw_log) - 1));
                         const int pr = lane >> lw_log;
                         const bool in_x = px < x1;
-                        const R dx = int_to_real(px - cx, R(0)) - fx;
-                        const R qx = fma(dx * dx, sx, cc);
+                        const R dx = (int_to_real(px - cx, R(0)) - fx) * sx;
+                        const R qx = fma(dx, dx, cc) + sqrt_guard(R(0));
                         R dy = int_to_real(y0 + pr - cy, R(0)) - fy;
                         const R dstep = int_to_real(rows_per_it, R(0));
                         R *a = my_acc + ((y0 + pr) * SX + px);
                         for (int py = y0 + pr; py < y1; py += rows_per_it) {
                             if (in_x) {
-                                const R q2 = fma(dy * dy, sy, qx);
+                                const R dys = dy * sy;
+                                const R q2 = fma(dys, dys, qx);
                                 if (q2 < rad2) {
-                                    const R wv = kernel_eval_q2<KIND, R>(q2, lv);
-#pragma unroll
+                                    const R wv = kernel_eval_pos<KIND, R>(q2, lv);
                                     SPHB_ASSERT(px >= 0 && px < TX && py >= own_y0 && py < own_y0 + ROWS &&
                                                 a >= acc && a + (NW - 1) * ACC < acc + (size_t)ACC * NW);
+#pragma unroll
                                     for (int k = 0; k < NW; k++) a[k * ACC] = fma(term[k], wv, a[k * ACC]);
                                 }
                             }
@@ -679,15 +657,10 @@ direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     lv.scale = R(0);
     lv.last = 0;
     if (is_lut<KIND>()) {
-        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kDirectWarps * 32) {
-            double a = lut[i], b = (i + 1 < lut_samples) ? lut[i + 1] : lut[i];
-            R2 e;
-            e.x = (R)a;
-            e.y = (R)(b - a);
-            if (i == lut_samples - 1) e.x = e.y = R(0);
-            lut_s[i] = e;
-        }
-        lv.scale = (R)((double)(lut_samples - 1) / v.radius);
+        const double lut_scale = (double)(lut_samples - 1) / v.radius;
+        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kDirectWarps * 32)
+            lut_s[i] = lut_make_entry<R>(lut, lut_samples, i, lut_scale);
+        lv.scale = (R)lut_scale;
         lv.last = lut_samples - 1;
         __syncthreads();
     }
@@ -775,8 +748,8 @@ direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                             const R q2 = fma(dz * dz, sz, qxy);
                             if (q2 < rad2) {
                                 const R wv = kernel_eval_pos<KIND, R>(q2, lv);
-#pragma unroll
                                 SPHB_ASSERT(oo < v.n_out);
+#pragma unroll
                                 for (int k = 0; k < NW; k++) red_add(outs[k] + oo, (double)(term[k] * wv));
                             }
                             oo += (size_t)v.ny * v.nx;
@@ -1160,10 +1133,10 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     if (big_lut) {
         if (p->dtype == SPHB_F32)
             lut_pairs_kernel<float><<<div_up(k->lut_samples, 256), 256, 0, stream>>>(
-                k->lut, k->lut_samples, static_cast<float2 *>(lut_global));
+                k->lut, k->lut_samples, (double)(k->lut_samples - 1) / v.radius, static_cast<float2 *>(lut_global));
         else
             lut_pairs_kernel<double><<<div_up(k->lut_samples, 256), 256, 0, stream>>>(
-                k->lut, k->lut_samples, static_cast<double2 *>(lut_global));
+                k->lut, k->lut_samples, (double)(k->lut_samples - 1) / v.radius, static_cast<double2 *>(lut_global));
         SPHB_LAUNCH_CHECK();
     }
 
