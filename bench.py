@@ -343,7 +343,11 @@ def run_gpu(args):
 
     # ---- end-to-end timing through the backend API -----------------------------
     e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
+    # two warm-ups that keep the previous result alive, like the timed loop does: the backend returns
+    # the raster in page-locked memory from torch's caching host allocator, and the steady state
+    # alternates between two such blocks (a first-time 1 GiB page-locked allocation costs ~0.4 s)
+    img = step_e2e()
+    img = step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

@@ -97,6 +97,94 @@ def _to_device(arrays, device):
     return out
 
 
+# ---- streamed uploads -------------------------------------------------------------------------
+# Host columns of a large particle set are not uploaded in one piece: they go up in chunks on a
+# copy stream, double-buffered, while the scatter pipeline of the previous chunk runs; every chunk
+# accumulates into the same raster.  At 2^27 particles the upload (5.4 GB, ~100 ms over PCIe)
+# costs twice the kernels, so hiding one behind the other is worth more than any kernel tuning
+# for a host-array caller.  Chunk sizes grow geometrically -- n/16 first (the only upload nothing
+# hides), then 3x each up to 2^24 particles -- because a projection renders a few big chunks more
+# efficiently than many small ones (fewer, longer tile segments), while an upload-bound voxel grid
+# only needs the chunks to be short next to the whole.  Sets below 2^22 go up in one piece.
+_STREAM_MIN = 1 << 22
+_CHUNK_FIRST_MIN, _CHUNK_FIRST_MAX, _CHUNK_GROWTH, _CHUNK_MAX = 1 << 20, 1 << 23, 3, 1 << 24
+
+
+def _chunk_bounds(n: int):
+    size = min(max(n // 16, _CHUNK_FIRST_MIN), _CHUNK_FIRST_MAX)
+    bounds, lo = [], 0
+    while lo < n:
+        hi = min(lo + size, n)
+        bounds.append((lo, hi))
+        lo, size = hi, min(size * _CHUNK_GROWTH, _CHUNK_MAX)
+    return bounds
+
+
+_copy_streams = {}
+
+
+def _host_columns(arrays):
+    """1-D host tensors sharing memory with the inputs, or None if any column is not host data."""
+    cols = []
+    for a in arrays:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return None
+            t = a.detach().contiguous().reshape(-1)
+        else:
+            arr = np.ascontiguousarray(np.asarray(a))
+            if arr.dtype.kind not in "fiu" or arr.dtype.byteorder not in ("=", "|") or not arr.flags.writeable:
+                return None
+            t = torch.from_numpy(arr).reshape(-1)
+        cols.append(t)
+    n = cols[0].numel()
+    return cols if all(c.numel() == n for c in cols) else None
+
+
+def _streamed(arrays, dev, render):
+    """Run `render(device_columns, out, accumulate) -> [rasters]` over the particle set.
+
+    Small or device-resident sets: one call.  Large host sets: chunked as described above."""
+    cols = _host_columns(arrays)
+    n = cols[0].numel() if cols else 0
+    if cols is None or n < _STREAM_MIN:
+        return render(_to_device(arrays, dev), None, False)
+    dtype = _common_dtype(cols)
+    bounds = _chunk_bounds(n)
+    largest = max(hi - lo for lo, hi in bounds)
+    copy_stream = _copy_streams.get(dev.index)
+    if copy_stream is None:
+        copy_stream = _copy_streams[dev.index] = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    bufs = [[torch.empty(largest, dtype=c.dtype, device=dev) for c in cols] for _ in range(2)]
+    ready, free = [None, None], [None, None]
+
+    def upload(k):
+        b, (lo, hi) = k % 2, bounds[k]
+        with torch.cuda.stream(copy_stream):
+            if free[b] is not None:
+                copy_stream.wait_event(free[b])
+            for buf, c in zip(bufs[b], cols):
+                buf[:hi - lo].copy_(c[lo:hi], non_blocking=True)
+            ready[b] = torch.cuda.Event()
+            ready[b].record(copy_stream)
+
+    upload(0)
+    out = None
+    for k, (lo, hi) in enumerate(bounds):
+        b = k % 2
+        if k + 1 < len(bounds):
+            upload(k + 1)
+        main.wait_event(ready[b])
+        views = [buf[:hi - lo] if buf.dtype == dtype else buf[:hi - lo].to(dtype) for buf in bufs[b]]
+        out = render(views, out, k > 0)
+        free[b] = torch.cuda.Event()
+        free[b].record(main)
+    # the buffers go back to the caching allocator of the main stream: make it wait for the copies
+    main.wait_stream(copy_stream)
+    return out
+
+
 _PINNED_MIN, _PINNED_MAX = 8 << 20, 4 << 30
 
 
@@ -119,25 +207,27 @@ class B200Backend:
     def interpolate_2d_render(x, y, weight, h, weight_function, kernel_radius, x_pixels, y_pixels,
                               x_min, x_max, y_min, y_max, exact) -> np.ndarray:
         dev = _device()
-        xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         if exact:
+            xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
             return _host(ops.exact2d(xd, yd, hd, [wd], r)[0])
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(ops.scatter2d(xd, yd, hd, [wd], wf, kernel_radius, 2, r)[0])
+        return _host(_streamed([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc))[0])
 
     @staticmethod
     def interpolate_2d_render_vec(x, y, weight_x, weight_y, h, weight_function, kernel_radius, x_pixels,
                                   y_pixels, x_min, x_max, y_min, y_max,
                                   exact) -> Tuple[np.ndarray, np.ndarray]:
         dev = _device()
-        xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         if exact:
+            xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
             a, b = ops.exact2d(xd, yd, hd, [wx, wy], r)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
-            a, b = ops.scatter2d(xd, yd, hd, [wx, wy], wf, kernel_radius, 2, r)
+            a, b = _streamed([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+                c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc))
         return _host(a), _host(b)
 
     @staticmethod
@@ -160,55 +250,59 @@ class B200Backend:
     def interpolate_3d_projection(x, y, weight, h, weight_function, kernel_radius, x_pixels, y_pixels,
                                   x_min, x_max, y_min, y_max, exact) -> np.ndarray:
         dev = _device()
-        xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         if exact:
+            xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
             return _host(ops.exact3d_proj(xd, yd, hd, [wd], r)[0])
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(ops.scatter2d(xd, yd, hd, [wd], wf, kernel_radius, 2, r)[0])
+        return _host(_streamed([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc))[0])
 
     @staticmethod
     def interpolate_3d_projection_vec(x, y, weight_x, weight_y, h, weight_function, kernel_radius,
                                       x_pixels, y_pixels, x_min, x_max, y_min, y_max,
                                       exact) -> Tuple[np.ndarray, np.ndarray]:
         dev = _device()
-        xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         if exact:
+            xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
             a, b = ops.exact3d_proj(xd, yd, hd, [wx, wy], r)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
-            a, b = ops.scatter2d(xd, yd, hd, [wx, wy], wf, kernel_radius, 2, r)
+            a, b = _streamed([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+                c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc))
         return _host(a), _host(b)
 
     @staticmethod
     def interpolate_3d_cross(x, y, z, z_slice, weight, h, weight_function, kernel_radius, x_pixels,
                              y_pixels, x_min, x_max, y_min, y_max) -> np.ndarray:
         dev = _device()
-        xd, yd, zd, wd, hd = _to_device([x, y, z, weight, h], dev)
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(ops.scatter2d(xd, yd, hd, [wd], wf, kernel_radius, 3, r, z=zd, z_slice=float(z_slice))[0])
+        zs = float(z_slice)
+        return _host(_streamed([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[4], [c[3]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc))[0])
 
     @staticmethod
     def interpolate_3d_cross_vec(x, y, z, z_slice, weight_x, weight_y, h, weight_function, kernel_radius,
                                  x_pixels, y_pixels, x_min, x_max, y_min,
                                  y_max) -> Tuple[np.ndarray, np.ndarray]:
         dev = _device()
-        xd, yd, zd, wx, wy, hd = _to_device([x, y, z, weight_x, weight_y, h], dev)
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
-        a, b = ops.scatter2d(xd, yd, hd, [wx, wy], wf, kernel_radius, 3, r, z=zd, z_slice=float(z_slice))
+        zs = float(z_slice)
+        a, b = _streamed([x, y, z, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[5], [c[3], c[4]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc))
         return _host(a), _host(b)
 
     @staticmethod
     def interpolate_3d_grid(x, y, z, weight, h, weight_function, kernel_radius, x_pixels, y_pixels,
                             z_pixels, x_min, x_max, y_min, y_max, z_min, z_max) -> np.ndarray:
         dev = _device()
-        xd, yd, zd, wd, hd = _to_device([x, y, z, weight, h], dev)
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max, z_pixels, z_min, z_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(ops.scatter3d(xd, yd, zd, hd, [wd], wf, kernel_radius, r)[0])
+        return _host(_streamed([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter3d(
+            c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r, out=out, accumulate=acc))[0])
 
 
 def install() -> None:

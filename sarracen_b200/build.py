@@ -38,13 +38,14 @@ def _stale(target, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False, defines=(), suffix: str = "") -> str:
     """debug_bounds=True builds lib/libsphb200_dbg.so with -DSPHB_DEBUG_BOUNDS (device asserts on
     every index the kernels form); point SPHB_LIB_OVERRIDE at it to run the GPU tests against it."""
     os.makedirs(BUILD_DIR, exist_ok=True)
     nvcc = _nvcc()
-    suffix = "_dbg" if debug_bounds else ""
-    flags = NVCC_FLAGS + (["-DSPHB_DEBUG_BOUNDS"] if debug_bounds else [])
+    # `defines` / `suffix`: experimental variants (python -m sarracen_b200.build --suffix _x -DNAME=1)
+    suffix = suffix or ("_dbg" if debug_bounds else "")
+    flags = NVCC_FLAGS + (["-DSPHB_DEBUG_BOUNDS"] if debug_bounds else []) + ["-D" + d for d in defines]
     lib = LIB.replace(".so", suffix + ".so")
     jobs = []
     for src in SOURCES:
@@ -78,4 +79,6 @@ def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug_bounds="--debug-bounds" in sys.argv))
+    _suffix = sys.argv[sys.argv.index("--suffix") + 1] if "--suffix" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug_bounds="--debug-bounds" in sys.argv,
+                defines=[a[2:] for a in sys.argv if a.startswith("-D")], suffix=_suffix))

@@ -363,3 +363,53 @@ def test_backend_accepts_what_the_front_end_passes(B):
     assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
     assert_parity(out, ref, TOL64, "mixed inputs")
     assert x.base is pos and not x.flags["C_CONTIGUOUS"]  # inputs untouched
+
+
+def test_streamed_uploads_match_single_upload(B, monkeypatch):
+    """Large host inputs go up in double-buffered chunks that accumulate into one raster
+    (backend._streamed); force the chunked path on a small set -- ragged last chunk, mixed
+    dtypes, every sampled method -- and compare with the single-upload result and the oracle."""
+    import torch
+    from sarracen_b200 import backend
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(77)
+    n = 5003
+    x, y, z = rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    h = rng.uniform(0.01, 0.06, n)
+    w, w2 = rng.uniform(0.5, 1.5, n) / n, rng.normal(size=n) / n
+    k = _kernel("cubic")
+    col = k.get_column_kernel_func(1000)
+    lim = (0.0, 1.0, 0.0, 1.0)
+
+    def run_all():
+        return [
+            B.interpolate_2d_render(x, y, w, h, k.w, 2.0, 96, 80, *lim, False),
+            *B.interpolate_2d_render_vec(x, y, w, w2, h, k.w, 2.0, 96, 80, *lim, False),
+            B.interpolate_3d_projection(x, y, w, h, col, 2.0, 96, 80, *lim, False),
+            *B.interpolate_3d_projection_vec(x, y, w, w2, h, col, 2.0, 96, 80, *lim, False),
+            B.interpolate_3d_cross(x, y, z, 0.5, w, h, k.w, 2.0, 96, 80, *lim),
+            *B.interpolate_3d_cross_vec(x, y, z, 0.5, w, w2, h, k.w, 2.0, 96, 80, *lim),
+            B.interpolate_3d_grid(x, y, z, w, h, k.w, 2.0, 24, 20, 16, *lim, 0.0, 1.0),
+        ]
+
+    single = run_all()
+    monkeypatch.setattr(backend, "_STREAM_MIN", 1000)
+    monkeypatch.setattr(backend, "_CHUNK_FIRST_MIN", 300)
+    monkeypatch.setattr(backend, "_CHUNK_MAX", 1500)
+    assert backend._chunk_bounds(n) == [(0, 312), (312, 1248), (1248, 2748), (2748, 4248), (4248, 5003)]
+    calls = []
+    real = backend.ops.scatter2d
+    monkeypatch.setattr(backend.ops, "scatter2d", lambda *a, **kw: (calls.append(kw.get("accumulate")), real(*a, **kw))[1])
+    chunked = run_all()
+    assert calls[:5] == [False] + [True] * 4   # the first call of a method clears, later chunks accumulate
+    for a, b in zip(single, chunked):
+        assert_parity(b, a, 1e-13, "streamed vs single upload")
+    ref = OracleBackend.interpolate_3d_grid(x, y, z, w, h, OracleKernel("cubic"), 2.0, 24, 20, 16, *lim, 0.0, 1.0)
+    assert_parity(chunked[-1], ref, TOL64, "streamed grid vs oracle")
+    # mixed dtypes (float32 positions, int weights) and pinned torch columns take the same path
+    xf, yf = x.astype(np.float32), y.astype(np.float32)
+    wi = np.ones(n, dtype=np.int64)
+    a = B.interpolate_2d_render(torch.from_numpy(xf).pin_memory(), yf, wi, h, k.w, 2.0, 96, 80, *lim, False)
+    monkeypatch.setattr(backend, "_STREAM_MIN", 1 << 30)
+    b = B.interpolate_2d_render(xf, yf, wi, h, k.w, 2.0, 96, 80, *lim, False)
+    assert_parity(a, b, 1e-13, "streamed mixed dtypes")
