@@ -392,7 +392,9 @@ def run_gpu(args):
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
     rate = contrib / (ms_render * 1e-3) if ms_render > 0 else 0.0
     if args.dtype == "f64":
-        dp_per = 15.0 if dom == "ms_render" else 16.0
+        # render: 8 per evaluation in the hot loop, ~12 per useful contribution with idle lanes and the
+        # per-hit set-up (ncu: fp64 pipe 48.9 % at 86 ms, profiles/r1_proj_f64_full_v8.txt)
+        dp_per = 12.0 if dom == "ms_render" else 16.0
         compute = {"bound": "fp64 pipe + issue slots", "fp64_inst_per_contribution_est": dp_per,
                    "achieved_fp64_inst_per_s": rate * dp_per, "peak_fp64_inst_per_s": 148 * 64 * sm_clock * 1e6,
                    "frac_est": rate * dp_per / (148 * 64 * sm_clock * 1e6)}
