@@ -309,6 +309,14 @@ template <typename R, bool DIM3, int WARPS> struct RenderBatch {
     static constexpr int value = WARPS * 32;
 };
 
+// Row padding of the shared-memory tile.  2-D (32 pixels per row): 4 elements, so that consecutive
+// rows start 8 banks apart in double -- as good for the narrow path's few-rows-by-few-columns
+// accesses as the former 8, and what lets two CTAs of the two-weight double kernel (2 x 36.9 KB of
+// tile each) share an SM.
+template <bool DIM3> struct RowPad {
+    static constexpr int value = DIM3 ? 8 : 4;
+};
+
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 1) ? 2 : 3)
 render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
@@ -318,7 +326,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
 {
     using R2 = typename Real2<R>::type;
     constexpr int kWarps = WARPS, kThreads = WARPS * 32, kBatch = RenderBatch<R, DIM3, WARPS>::value;
-    constexpr int SX = TX + 8;                    // padded row stride
+    constexpr int SX = TX + RowPad<DIM3>::value;  // padded row stride
     constexpr int PLANE = SX * TY;                // elements per z-plane
     constexpr int ACC = PLANE * TZ;               // elements per weight
     constexpr int ROWS = DIM3 ? TY : TY / kWarps; // rows of the warp's box
@@ -832,7 +840,7 @@ static int launch_render(const View &v, const T *recs, const sphb_kernel *k, con
 {
     using R2 = typename Real2<R>::type;
     auto kern = render_kernel<T, R, KIND, NW, DIM3, TX, TY, TZ, WARPS>;
-    const size_t fixed = sizeof(R) * (size_t)(TX + 8) * TY * TZ * NW + sizeof(Staged<R, NW, RenderBatch<R, DIM3, WARPS>::value, DIM3>);
+    const size_t fixed = sizeof(R) * (size_t)(TX + RowPad<DIM3>::value) * TY * TZ * NW + sizeof(Staged<R, NW, RenderBatch<R, DIM3, WARPS>::value, DIM3>);
     const size_t limit = 227 * 1024;
     size_t smem = fixed;
     if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
