@@ -318,7 +318,7 @@ template <bool DIM3> struct RowPad {
 };
 
 template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 1) ? 2 : 3)
+__global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 2 || (NW > 1 && sizeof(R) == 8)) ? 2 : 3)
 render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
               const void *__restrict__ lut_global, const uint32_t *__restrict__ keys,
               const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_end, int64_t n_pairs,
