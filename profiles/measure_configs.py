@@ -85,6 +85,9 @@ for dt in (np.float32, np.float64):
     c = ops.count_contributions(xd, yd, hd, 2.0, r)
     record(f"cfg3b interpolate_3d_vec (2 weights, one walk) 4096^2 cubic column table {np.dtype(dt).name}", n, ms,
            contributions=c, stats=dict(ops.last_stats))
+    ms = timed(lambda: ops.scatter2d(xd, yd, hd, [wx, wy, wd], col, 2, 2, r), warm=1, reps=2)
+    record(f"cfg3c vector render + normalisation weight (3 weights, one walk) 4096^2 {np.dtype(dt).name}", n, ms,
+           contributions=c, stats=dict(ops.last_stats))
     del xd, yd, zd, hd, wd, wx, wy
     torch.cuda.empty_cache()
 

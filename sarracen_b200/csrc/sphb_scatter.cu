@@ -909,8 +909,9 @@ static int dispatch_nw(int nw, A &&...a)
     switch (nw) {
     case 1: return launch_render<T, R, KIND, 1, DIM3, TX, TY, TZ, WARPS>(a...);
     case 2: return launch_render<T, R, KIND, 2, DIM3, TX, TY, TZ, WARPS>(a...);
-    case 3: return launch_render<T, R, KIND, 3, DIM3, TX, TY, TZ, WARPS>(a...);
-    default: return launch_render<T, R, KIND, 4, DIM3, TX, TY, TZ, WARPS>(a...);
+    // three and four weights in double: half-height 2-D tiles (see tile2y())
+    case 3: return launch_render<T, R, KIND, 3, DIM3, TX, (!DIM3 && sizeof(R) == 8) ? TY / 2 : TY, TZ, WARPS>(a...);
+    default: return launch_render<T, R, KIND, 4, DIM3, TX, (!DIM3 && sizeof(R) == 8) ? TY / 2 : TY, TZ, WARPS>(a...);
     }
 }
 
@@ -945,6 +946,11 @@ static int small_edge_setting()
     return 8;
 }
 constexpr int kTile3X = 16, kTile3Y = 16, kTile3Z = 8;
+
+// Height of the 2-D tile.  With three or four weight columns in double a 32 x 128 tile needs
+// 111 / 148 KB of accumulators and 96 / 128 accumulator registers per lane: one CTA per SM, with
+// spills.  Half the height brings back two CTAs per SM and spill-free code.
+static int tile2y(bool f32, int n_weights) { return (!f32 && n_weights >= 3) ? kTile2Y / 2 : kTile2Y; }
 
 static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
                     int use_z, double *const *out)
@@ -1004,7 +1010,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     v.ny = r->ny;
     v.nz = dim3 ? r->nz : 1;
     v.tx = dim3 ? kTile3X : kTile2X;
-    v.ty = dim3 ? kTile3Y : kTile2Y;
+    v.ty = dim3 ? kTile3Y : tile2y(p->dtype == SPHB_F32, p->n_weights);
     v.tz = dim3 ? kTile3Z : 1;
     auto ilog2 = [](int t) { int l = 0; while ((1 << l) < t) l++; return l; };
     v.tx_log = ilog2(v.tx);
