@@ -163,15 +163,32 @@ __device__ __forceinline__ ITerms get_i_terms_cos(double cosp, double a2, double
     return get_i_terms(cosp, acos(cosp), sqrt(1.0 - cosp * cosp) / cosp, a2, a);
 }
 
-// cubic_spline_exact.py:353-454
-__device__ __noinline__ double full_integral_3d(double d, double r0, double r1, double h)
+// I_1 alone (the only term besides I_0 = phi that the region outside the kernel support needs):
+// no logarithm, no higher terms.
+__device__ __forceinline__ double get_i1(double cosp, double a2, double a)
+{
+    const double cosp2 = cosp * cosp;
+    const double mu2_1 = 1.0 / (1.0 + cosp2 / a2);
+    const double u = sqrt((1.0 - cosp2) * mu2_1);
+    return atan2(u, a);
+}
+
+// cubic_spline_exact.py:353-454, split in two.  The reference evaluates `full_integral_3d(d, r0, r1, h)`
+// for both half-segments d1, d2 of an edge (cubic_spline_exact.py:284-350); everything that does not
+// depend on d -- the B terms, a = r1 / r0 and the two inner-boundary corrections D2, D3 with their
+// inverse cosines, logarithms and arctangents -- is the same for both calls and is worked out once per
+// edge here (Edge3), leaving the phi-dependent part (edge_integral) to be evaluated twice.
+struct Edge3 {
+    double r0, r1, h2, r03, r0h, r0h2, r0h3, r0h_3;
+    double b1, b2, b3, a, a2, d2, d3;
+    bool zero; // r0 = 0 or r1 = 0: the integral vanishes for every d
+};
+
+__device__ __forceinline__ void edge_setup(double r0, double r1, double h, Edge3 &s)
 {
     const double r0h = r0 / h;
-    // phi = atan(|d| / r1): its cosine and tangent are algebraic in t = |d| / r1
-    const double tphi = fabs(d) / r1;
-    if (fabs(r0h) == 0.0 || fabs(r1 / h) == 0.0 || tphi == 0.0) return 0.0;
-    const double phi = atan(tphi);
-
+    s.zero = fabs(r0h) == 0.0 || fabs(r1 / h) == 0.0;
+    if (s.zero) return;
     const double h2 = h * h, r03 = r0 * r0 * r0;
     const double r0h2 = r0h * r0h, r0h3 = r0h2 * r0h;
     const double r0h_2 = 1.0 / r0h2, r0h_3 = 1.0 / r0h3;
@@ -186,16 +203,9 @@ __device__ __noinline__ double full_integral_3d(double d, double r0, double r1, 
         b2 = 0.25 * r03 * (-2.0 / 3.0 + 0.3 * r0h2 - 0.1 * r0h3 - 0.2 * r0h_2);
         b1 = 0.25 * r03 * (-2.0 / 3.0 + 0.3 * r0h2 - 0.1 * r0h3);
     }
-
     const double a = r1 / r0, a2 = a * a;
     const double linedist2 = r0 * r0 + r1 * r1;
-    const double tcl = fmin(tphi, 1e150);
-    const double sec = sqrt(fma(tcl, tcl, 1.0)); // 1 / cos(phi)
-    const double cphi = 1.0 / sec;
-    const double r_ = r1 * sec;
-    const double r2 = r0 * r0 + r_ * r_;
     double d2 = 0.0, d3 = 0.0;
-
     if (linedist2 < h2) {
         const ITerms t = get_i_terms_cos(r1 / sqrt(h2 - r0 * r0), a2, a);
         d2 = -1.0 / 6.0 * t.i2 + 0.25 * r0h * t.i3 - 0.15 * r0h2 * t.i4;
@@ -208,19 +218,37 @@ __device__ __noinline__ double full_integral_3d(double d, double r0, double r1, 
         d3 += -1.0 / 120.0 * r0h3 * t.i5 + 4.0 / 15.0 * r0h_3 * t.i1;
         d3 += (b2 - b3) / r03 * t.i0 + d2;
     }
-    const ITerms t = get_i_terms(cphi, phi, tcl, a2, a);
-    if (r2 <= h2)
-        return r0h3 / kPi * (1.0 / 6.0 * t.i2 - 3.0 / 40.0 * r0h2 * t.i4 + 1.0 / 40.0 * r0h3 * t.i5 + b1 / r03 * t.i0);
-    if (r2 <= 4.0 * h2)
-        return r0h3 / kPi *
-               (0.25 * (4.0 / 3.0 * t.i2 - (r0 / h) * t.i3 + 0.3 * r0h2 * t.i4 - 1.0 / 30.0 * r0h3 * t.i5 +
-                        1.0 / 15.0 * r0h_3 * t.i1) +
-                b2 / r03 * t.i0 + d2);
-    return r0h3 / kPi * (-0.25 * r0h_3 * t.i1 + b3 / r03 * t.i0 + d3);
+    s.r0 = r0; s.r1 = r1; s.h2 = h2; s.r03 = r03;
+    s.r0h = r0h; s.r0h2 = r0h2; s.r0h3 = r0h3; s.r0h_3 = r0h_3;
+    s.b1 = b1; s.b2 = b2; s.b3 = b3; s.a = a; s.a2 = a2; s.d2 = d2; s.d3 = d3;
 }
 
-// cubic_spline_exact.py:284-350 (its diagnostic prints are dropped)
-__device__ double line_int3d(double r0, double r1, double d1, double d2, double h)
+__device__ __forceinline__ double edge_integral(double d, const Edge3 &s)
+{
+    // phi = atan(|d| / r1): its cosine and tangent are algebraic in t = |d| / r1
+    const double tphi = fabs(d) / s.r1;
+    if (s.zero || tphi == 0.0) return 0.0;
+    const double phi = atan(tphi);
+    const double tcl = fmin(tphi, 1e150);
+    const double sec = sqrt(fma(tcl, tcl, 1.0)); // 1 / cos(phi)
+    const double cphi = 1.0 / sec;
+    const double r_ = s.r1 * sec;
+    const double r2 = s.r0 * s.r0 + r_ * r_;
+    if (!(r2 <= 4.0 * s.h2)) // beyond the support: I_0 and I_1 only
+        return s.r0h3 / kPi * (-0.25 * s.r0h_3 * get_i1(cphi, s.a2, s.a) + s.b3 / s.r03 * phi + s.d3);
+    const ITerms t = get_i_terms(cphi, phi, tcl, s.a2, s.a);
+    if (r2 <= s.h2)
+        return s.r0h3 / kPi *
+               (1.0 / 6.0 * t.i2 - 3.0 / 40.0 * s.r0h2 * t.i4 + 1.0 / 40.0 * s.r0h3 * t.i5 + s.b1 / s.r03 * t.i0);
+    return s.r0h3 / kPi *
+           (0.25 * (4.0 / 3.0 * t.i2 - s.r0h * t.i3 + 0.3 * s.r0h2 * t.i4 - 1.0 / 30.0 * s.r0h3 * t.i5 +
+                    1.0 / 15.0 * s.r0h_3 * t.i1) +
+            s.b2 / s.r03 * t.i0 + s.d2);
+}
+
+// cubic_spline_exact.py:284-350 (its diagnostic prints are dropped).  Not inlined: one copy serves the
+// 20 edges of a pixel column (instruction cache, see full_2d_mod).
+__device__ __noinline__ double line_int3d(double r0, double r1, double d1, double d2, double h)
 {
     if (fabs(r0) == 0.0) return 0.0;
     double sign = r0 > 0.0 ? 1.0 : -1.0;
@@ -230,8 +258,10 @@ __device__ double line_int3d(double r0, double r1, double d1, double d2, double 
         sign = -sign;
         ar1 = -r1;
     }
-    double int1 = full_integral_3d(d1, ar0, ar1, h);
-    double int2 = full_integral_3d(d2, ar0, ar1, h);
+    Edge3 s;
+    edge_setup(ar0, ar1, h, s);
+    double int1 = edge_integral(d1, s);
+    double int2 = edge_integral(d2, s);
     if (int1 < 0.0) int1 = 0.0;
     if (int2 < 0.0) int2 = 0.0;
     if (d1 * d2 >= 0.0) return sign * (int1 + int2);
@@ -240,7 +270,7 @@ __device__ double line_int3d(double r0, double r1, double d1, double d2, double 
 }
 
 // cubic_spline_exact.py:220-281
-__device__ __noinline__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx, double wy,
+__device__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx, double wy,
                               double h)
 {
     const double dx = x2 - x1, dy = y2 - y1;
