@@ -276,15 +276,16 @@ def run_gpu(args):
             # N ranks: pinned host columns -> device, partial raster, NCCL combine, result back to the
             # host (rank 0's image, or every rank's z-slab of the grid) -- the multi-GPU recipe of
             # INTEGRATION.md section 4 with the host copies inside the timed region
-            dcols = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             if dim3:
-                part = ops.scatter3d(dcols["x"], dcols["y"], dcols["z"], dcols["h"], [dcols["w"]], wf, wl["radius"],
-                                     raster)[0]
+                part = s.backend.streamed_scatter(
+                    [host[k] for k in "xyzwh"], dev, lambda c, out, acc: ops.scatter3d(
+                        c[0], c[1], c[2], c[4], [c[3]], wf, wl["radius"], raster, out=out, accumulate=acc))[0]
                 combine_grid_along_z(part, slab)
                 host_out.copy_(slab)
             else:
-                part = ops.scatter2d(dcols["x"], dcols["y"], dcols["h"], [dcols["w"]], wf, wl["radius"], wl["ndim"],
-                                     raster)[0]
+                part = s.backend.streamed_scatter(
+                    [host[k] for k in "xywh"], dev, lambda c, out, acc: ops.scatter2d(
+                        c[0], c[1], c[3], [c[2]], wf, wl["radius"], wl["ndim"], raster, out=out, accumulate=acc))[0]
                 combine_image(part, dst=0)
                 if rank == 0:
                     host_out.copy_(part)

@@ -141,10 +141,14 @@ def _host_columns(arrays):
     return cols if all(c.numel() == n for c in cols) else None
 
 
-def _streamed(arrays, dev, render):
-    """Run `render(device_columns, out, accumulate) -> [rasters]` over the particle set.
+def streamed_scatter(arrays, dev, render):
+    """Run `render(device_columns, out, accumulate) -> [rasters]` over a particle set given as host
+    (or device) columns; returns the device rasters.  `device_columns` are 1-D tensors of one
+    dtype, in the order of `arrays`.
 
-    Small or device-resident sets: one call.  Large host sets: chunked as described above."""
+    Small or device-resident sets: one call.  Large host sets: chunked as described above.  Public
+    because multi-GPU callers use it per rank on their shard before the NCCL combine
+    (INTEGRATION.md section 4)."""
     cols = _host_columns(arrays)
     n = cols[0].numel() if cols else 0
     if cols is None or n < _STREAM_MIN:
@@ -212,7 +216,7 @@ class B200Backend:
             xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
             return _host(ops.exact2d(xd, yd, hd, [wd], r)[0])
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(_streamed([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+        return _host(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
             c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc))[0])
 
     @staticmethod
@@ -226,7 +230,7 @@ class B200Backend:
             a, b = ops.exact2d(xd, yd, hd, [wx, wy], r)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
-            a, b = _streamed([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+            a, b = streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
                 c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc))
         return _host(a), _host(b)
 
@@ -255,7 +259,7 @@ class B200Backend:
             xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
             return _host(ops.exact3d_proj(xd, yd, hd, [wd], r)[0])
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(_streamed([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+        return _host(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
             c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc))[0])
 
     @staticmethod
@@ -269,7 +273,7 @@ class B200Backend:
             a, b = ops.exact3d_proj(xd, yd, hd, [wx, wy], r)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
-            a, b = _streamed([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+            a, b = streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
                 c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc))
         return _host(a), _host(b)
 
@@ -280,7 +284,7 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
         zs = float(z_slice)
-        return _host(_streamed([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+        return _host(streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter2d(
             c[0], c[1], c[4], [c[3]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc))[0])
 
     @staticmethod
@@ -291,7 +295,7 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
         zs = float(z_slice)
-        a, b = _streamed([x, y, z, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+        a, b = streamed_scatter([x, y, z, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
             c[0], c[1], c[5], [c[3], c[4]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc))
         return _host(a), _host(b)
 
@@ -301,7 +305,7 @@ class B200Backend:
         dev = _device()
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max, z_pixels, z_min, z_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(_streamed([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter3d(
+        return _host(streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter3d(
             c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r, out=out, accumulate=acc))[0])
 
 

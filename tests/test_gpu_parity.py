@@ -367,7 +367,7 @@ def test_backend_accepts_what_the_front_end_passes(B):
 
 def test_streamed_uploads_match_single_upload(B, monkeypatch):
     """Large host inputs go up in double-buffered chunks that accumulate into one raster
-    (backend._streamed); force the chunked path on a small set -- ragged last chunk, mixed
+    (backend.streamed_scatter); force the chunked path on a small set -- ragged last chunk, mixed
     dtypes, every sampled method -- and compare with the single-upload result and the oracle."""
     import torch
     from sarracen_b200 import backend
