@@ -14,6 +14,7 @@ time (interpolate.py:1640-1658): every `backend='gpu'` call of
 `interpolate_*`, `SarracenDataFrame.render` and `.sph_interpolate` then lands
 here with no signature change.
 """
+import warnings
 from typing import Tuple
 
 import numpy as np
@@ -82,6 +83,20 @@ def _common_dtype(arrays) -> torch.dtype:
     return torch.float32
 
 
+def _from_numpy(arr: np.ndarray) -> torch.Tensor:
+    """Host tensor sharing memory with `arr` where possible.  Read-only arrays (pandas hands them out
+    under copy-on-write) are wrapped without the copy torch's warning suggests: the columns are only
+    ever read."""
+    arr = np.ascontiguousarray(arr)
+    if arr.dtype.byteorder not in ("=", "|"):
+        arr = arr.astype(arr.dtype.newbyteorder("="))
+    if not arr.flags.writeable:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            return torch.from_numpy(arr)
+    return torch.from_numpy(arr)
+
+
 def _to_device(arrays, device):
     dtype = _common_dtype(arrays)
     out = []
@@ -89,10 +104,7 @@ def _to_device(arrays, device):
         if isinstance(a, torch.Tensor):
             t = a.to(device=device, dtype=dtype).contiguous().reshape(-1)
         else:
-            arr = np.ascontiguousarray(np.asarray(a))
-            if arr.dtype.byteorder not in ("=", "|") or not arr.flags.writeable:
-                arr = arr.astype(arr.dtype.newbyteorder("="), copy=True)
-            t = torch.from_numpy(arr).to(device=device, dtype=dtype).reshape(-1)
+            t = _from_numpy(np.asarray(a)).to(device=device, dtype=dtype).reshape(-1)
         out.append(t)
     return out
 
@@ -132,10 +144,10 @@ def _host_columns(arrays):
                 return None
             t = a.detach().contiguous().reshape(-1)
         else:
-            arr = np.ascontiguousarray(np.asarray(a))
-            if arr.dtype.kind not in "fiu" or arr.dtype.byteorder not in ("=", "|") or not arr.flags.writeable:
+            arr = np.asarray(a)
+            if arr.dtype.kind not in "fiu":
                 return None
-            t = torch.from_numpy(arr).reshape(-1)
+            t = _from_numpy(arr).reshape(-1)
         cols.append(t)
     n = cols[0].numel()
     return cols if all(c.numel() == n for c in cols) else None

@@ -408,6 +408,7 @@ def test_streamed_uploads_match_single_upload(B, monkeypatch):
     assert_parity(chunked[-1], ref, TOL64, "streamed grid vs oracle")
     # mixed dtypes (float32 positions, int weights) and pinned torch columns take the same path
     xf, yf = x.astype(np.float32), y.astype(np.float32)
+    yf.flags.writeable = False   # pandas hands out read-only columns under copy-on-write
     wi = np.ones(n, dtype=np.int64)
     a = B.interpolate_2d_render(torch.from_numpy(xf).pin_memory(), yf, wi, h, k.w, 2.0, 96, 80, *lim, False)
     monkeypatch.setattr(backend, "_STREAM_MIN", 1 << 30)
