@@ -414,3 +414,28 @@ def test_streamed_uploads_match_single_upload(B, monkeypatch):
     monkeypatch.setattr(backend, "_STREAM_MIN", 1 << 30)
     b = B.interpolate_2d_render(xf, yf, wi, h, k.w, 2.0, 96, 80, *lim, False)
     assert_parity(a, b, 1e-13, "streamed mixed dtypes")
+
+
+@pytest.mark.parametrize("samples", [2048, 2049, 6000])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_large_column_tables(B, samples, dtype, tol):
+    """Column tables above 2048 samples do not fit the render kernels' shared memory and are read
+    from global memory (a separate kernel variant); 2048 is the largest shared-memory table.  Mixed
+    footprints so that both the tile path and the direct path look the table up."""
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(2048 + samples)
+    n = 6000
+    x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    h = np.exp(rng.uniform(np.log(0.004), np.log(0.3), n))
+    w, w2 = rng.uniform(0, 1, n) / n, rng.normal(size=n) / n
+    x, y, h, w, w2 = (a.astype(dtype) for a in (x, y, h, w, w2))
+    lim = (-1.0, 1.0, -1.0, 1.0)
+    k = _kernel("cubic")
+    out = B.interpolate_3d_projection(x, y, w, h, k.get_column_kernel_func(samples), 2, 200, 160, *lim, False)
+    okern = OracleKernel.column("cubic", samples)
+    ref = OracleBackend.interpolate_3d_projection(x, y, w, h, okern, 2, 200, 160, *lim, False)
+    assert_parity(out, ref, tol, f"projection, {samples}-sample table")
+    a, b = B.interpolate_3d_projection_vec(x, y, w, w2, h, k.get_column_kernel_func(samples), 2, 200, 160, *lim, False)
+    ra, rb = OracleBackend.interpolate_3d_projection_vec(x, y, w, w2, h, okern, 2, 200, 160, *lim, False)
+    assert_parity(a, ra, tol, "vec x")
+    assert_parity(b, rb, tol, "vec y")
