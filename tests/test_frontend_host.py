@@ -90,3 +90,39 @@ def test_corotation_matches_reference_formula():
     rot, origin = front._corotate([[0.1, 0.2, 0.0], [0.6, -0.3, 0.0]], None)
     assert origin == [0.1, 0.2, 0.0]
     np.testing.assert_allclose(rot, [-np.degrees(np.arctan2(-0.5, 0.5)), 0, 0])
+
+
+def test_upload_chunk_schedule_and_host_column_views():
+    """Host logic of backend.streamed_scatter: the chunk schedule covers the particle range exactly
+    once, grows geometrically and respects its caps; host columns are wrapped without copies
+    (read-only and pandas columns included) and anything non-numeric falls back to the plain path."""
+    import warnings
+
+    import pandas as pd
+    import torch
+
+    from sarracen_b200 import backend
+
+    for n in (1 << 22, (1 << 24) + 12345, 1 << 27, 5_000_001):
+        b = backend._chunk_bounds(n)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert backend._CHUNK_FIRST_MIN <= sizes[0] <= backend._CHUNK_FIRST_MAX
+        assert max(sizes) <= backend._CHUNK_MAX
+        assert all(sizes[i + 1] <= backend._CHUNK_GROWTH * sizes[i] for i in range(len(sizes) - 1))
+    assert len(backend._chunk_bounds(1 << 24)) == 4 and len(backend._chunk_bounds(1 << 27)) == 9
+
+    a = np.arange(6.0)
+    ro = np.arange(6.0)
+    ro.flags.writeable = False
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")   # no "non-writable array" warning, no copy
+        cols = backend._host_columns([a, ro, pd.Series(a), torch.arange(6.0), a[::-1].astype(">f4")])
+    assert cols is not None and all(c.shape == (6,) for c in cols)
+    assert cols[0].data_ptr() == a.ctypes.data and cols[1].data_ptr() == ro.ctypes.data
+    assert cols[4].dtype == torch.float32 and cols[4][0].item() == 5.0
+    assert backend._common_dtype(cols) == torch.float64
+    assert backend._common_dtype([cols[4], cols[4]]) == torch.float32
+    assert backend._host_columns([a, np.array(["x"] * 6)]) is None     # not numeric
+    assert backend._host_columns([a, np.arange(5.0)]) is None          # ragged

@@ -439,3 +439,31 @@ def test_large_column_tables(B, samples, dtype, tol):
     ra, rb = OracleBackend.interpolate_3d_projection_vec(x, y, w, w2, h, okern, 2, 200, 160, *lim, False)
     assert_parity(a, ra, tol, "vec x")
     assert_parity(b, rb, tol, "vec y")
+
+
+@pytest.mark.parametrize("nw", [2, 3, 4])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_multi_weight_tiles_across_a_tall_raster(B, nw, dtype, tol):
+    """Weight counts pick different tile shapes and CTA residencies (float64: 32x128 tiles up to two
+    weights, 32x64 for three and four); a raster several tiles tall and wide, wide and narrow
+    footprints, analytic kernel and column table."""
+    import torch
+    from sarracen_b200 import ops
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(300 + nw)
+    n = 3000
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    h = np.exp(rng.uniform(np.log(0.002), np.log(0.12), n))
+    ws = [rng.normal(size=n) * h ** 2 for _ in range(nw)]
+    x, y, h = (a.astype(dtype) for a in (x, y, h))
+    ws = [w.astype(dtype) for w in ws]
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    nx, ny = 150, 330
+    r = ops.Raster(nx, ny, 0.0, 1.0, 0.0, 1.0)
+    k = _kernel("quintic")
+    for wf, okern in ((k.w, OracleKernel("quintic")), (k.get_column_kernel_func(1000), OracleKernel.column("quintic", 1000))):
+        outs = ops.scatter2d(t(x), t(y), t(h), [t(w) for w in ws], wf, 3.0, 2, r)
+        for w, o in zip(ws, outs):
+            ref = OracleBackend.interpolate_2d_render(x, y, w, h, okern, 3.0, nx, ny, 0.0, 1.0, 0.0, 1.0, False)
+            assert_parity(o.cpu().numpy(), ref, tol, f"{nw} weights")
