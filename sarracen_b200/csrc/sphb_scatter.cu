@@ -168,22 +168,30 @@ __global__ void __launch_bounds__(256)
 count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint64_t *counts,
                    unsigned long long *n_small)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    TileBox b;
-    uint64_t c = 0; // counts[n] = 0 so that the exclusive scan leaves the total there
-    bool small = false;
-    if (i < n && particle_tiles(v, x, y, z, h, i, b, small))
-        c = small ? 1
-                  : (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) * (uint64_t)(b.z1 - b.z0 + 1);
-    if (i <= n) counts[i] = c;
-    // one global atomic per CTA: a per-warp atomic on a single address serialises in L2
-    __shared__ unsigned block_small;
+    // Grid-stride over the particles, so that the number of direct-path particles reaches global
+    // memory as ONE atomic per CTA of a few-hundred-CTA grid: with a CTA per 256 particles a
+    // set that is all small footprints (config 4: 2^27 particles) queued half a million atomics on
+    // one address.
+    unsigned mine = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        TileBox b;
+        uint64_t c = 0; // counts[n] = 0 so that the exclusive scan leaves the total there
+        bool small = false;
+        if (i < n && particle_tiles(v, x, y, z, h, i, b, small))
+            c = small ? 1
+                      : (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) * (uint64_t)(b.z1 - b.z0 + 1);
+        counts[i] = c;
+        mine += (small && c) ? 1u : 0u;
+    }
+    __shared__ unsigned long long block_small;
     if (threadIdx.x == 0) block_small = 0;
     __syncthreads();
-    const unsigned m = __ballot_sync(0xffffffffu, small && c);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&block_small, (unsigned)__popc(m));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&block_small, (unsigned long long)mine);
     __syncthreads();
-    if (threadIdx.x == 0 && block_small) atomicAdd(n_small, (unsigned long long)block_small);
+    if (threadIdx.x == 0 && block_small) atomicAdd(n_small, block_small);
 }
 
 template <typename T>
@@ -802,6 +810,29 @@ template <typename K> static cudaError_t allow_large_smem(K kern)
     return e;
 }
 
+// SM count of the current device (cached per device).
+static cudaError_t sm_count(int *out)
+{
+    static std::mutex mu;
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64 || cached[dev] == 0) {
+        int val = 0;
+        e = cudaDeviceGetAttribute(&val, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64) {
+            *out = val;
+            return cudaSuccess;
+        }
+        cached[dev] = val;
+    }
+    *out = cached[dev];
+    return cudaSuccess;
+}
+
 // Timing events are created once per host thread and device and reused.
 static cudaError_t phase_events(cudaEvent_t *ev, int count)
 {
@@ -1087,7 +1118,12 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     const int blocks = div_up(n + 1, 256);
     if (timed) SPHB_CUDA(cudaEventRecord(ev[0], stream));
     SPHB_CUDA(cudaMemsetAsync(n_small_dev, 0, sizeof(unsigned long long), stream));
-    count_tiles_kernel<T><<<blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets, n_small_dev);
+    {
+        int sms = 0;
+        SPHB_CUDA(sm_count(&sms));
+        const int count_blocks = std::min<int64_t>(blocks, (int64_t)sms * 16);
+        count_tiles_kernel<T><<<count_blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets, n_small_dev);
+    }
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
     uint64_t total = 0;
