@@ -91,16 +91,15 @@ __device__ __forceinline__ typename Real2<R>::type lut_entry(const LutView<R> &l
 // double: MUFU.RSQ64H seed (reads the high word only: relative error < 2^-19.9)
 // followed by one coupled Goldschmidt step -> relative error < 1.5 * 2^-39.8
 // ~ 1.6e-12, far inside the 1e-10 parity budget (it moves W by < |W'| q 1.6e-12).
-// `fast_sqrt` adds a Heron correction for ~1 ulp.  Arguments must be > 0: callers
-// add sqrt_guard() once per particle so that a == 0 cannot reach rsqrt.
+// Arguments must be > 0: callers add sqrt_guard() once per particle so that a == 0 cannot
+// reach rsqrt.
 __device__ __forceinline__ double sqrt_guard(double) { return 1e-290; }
 __device__ __forceinline__ float sqrt_guard(float) { return 1e-35f; }
 
 __device__ __forceinline__ double sqrt_pos(double a)
 {
     // a > 0 is the caller's job: every call site forms q^2 as fma(d * d, s, base) with
-    // base >= sqrt_guard() > 0, so no floor is needed here.  (When q^2 came from second differences
-    // it could round to <= 0 at a pixel centre on the particle and had to be floored.)
+    // base >= sqrt_guard() > 0, so no floor is needed here.
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     // y / 2 by an integer decrement of the exponent (y is a normal number): one FP64-pipe
@@ -117,24 +116,6 @@ __device__ __forceinline__ float sqrt_pos(float a)
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
     return a * y;
-}
-
-__device__ __forceinline__ double fast_sqrt(double a)
-{
-    a += 1e-290; // a >= 0: keeps rsqrt finite at a == 0 and changes no other value
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double g = a * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, g, a);
-    return fma(r, h, g);
-}
-__device__ __forceinline__ float fast_sqrt(float a)
-{
-    a += 1e-35f;
-    return a * rsqrtf(a);
 }
 
 // ---- unnormalised kernel shapes, valid for 0 <= q < radius ----------------

@@ -249,7 +249,7 @@ __global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t 
 
 // Column tables of up to kLutSharedMax samples are staged in shared memory by every CTA; larger
 // ones (integral_samples is a user argument, base_kernel.py:68) are expanded once per call into
-// (T[i], T[i+1] - T[i]) pairs in the workspace and read through L1/L2.
+// segment lines (A_i, B_i) (sphb_common.cuh, lut_index) in the workspace and read through L1/L2.
 constexpr int kLutSharedMax = 2048;
 
 template <typename R>
