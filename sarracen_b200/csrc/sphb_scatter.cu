@@ -455,7 +455,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
 #pragma unroll
                 for (int k = 0; k < NW; k++) tv[k] = (R)((double)pr.w[k] * scale);
                 R2 e0;
-                e0.x = (R)cc;
+                e0.x = (R)cc + sqrt_guard(R(0)); // every q^2 built on it is > 0 (sqrt_pos)
                 e0.y = tv[0];
                 st->ct[0][tid] = e0;
                 if (NW > 1) {
@@ -494,12 +494,14 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                     if (wx <= 0 || y1 <= y0) continue;
                     const R2 f = st->fxy[s], sc = st->sxy[s], e0 = st->ct[0][s];
                     const R fx = f.x, fy = f.y, sx = sc.x, sy = sc.y;
-                    const int cx = ib.z, cy = ib.w;
+                    // double mode stages whole coordinates (Split<double>: nearest pixel 0): keeping that
+                    // a compile-time fact makes the lane's own pixel coordinate loop-invariant
+                    const int cx = sizeof(R) == 8 ? 0 : ib.z, cy = sizeof(R) == 8 ? 0 : ib.w;
                     R cc = e0.x;
                     if (DIM3) {
                         const R2 fz = st->fsz[s];
                         const R dz = int_to_real(warp - st->ibox3[s].y, R(0)) - fz.x;
-                        cc = dz * dz * fz.y;
+                        cc = fma(dz * dz, fz.y, sqrt_guard(R(0)));
                     }
                     R term[NW];
                     term[0] = e0.y;
@@ -522,7 +524,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                         // a time without branches so the G dependent square-root /
                         // table chains overlap; groups that cannot contribute are skipped.
                         const R dx = (int_to_real(lx - cx, R(0)) - fx) * sx;
-                        const R qx = fma(dx, dx, cc) + sqrt_guard(R(0));
+                        const R qx = fma(dx, dx, cc); // cc carries sqrt_guard()
                         const R dy0 = (int_to_real(own_y0 + ly - cy, R(0)) - fy) * sy;
                         constexpr int G = K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1);
 #pragma unroll
@@ -563,14 +565,13 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
                         }
                     } else {
                         // ---- narrow: lanes over the footprint box, shared memory ----
-                        int lw_log = 0;
-                        while ((1 << lw_log) < wx) lw_log++;
+                        const int lw_log = 32 - __clz(wx - 1); // smallest power of two >= wx (wx >= 1)
                         const int rows_per_it = 32 >> lw_log;
                         const int px = x0 + (lane & ((1 << lw_log) - 1));
                         const int pr = lane >> lw_log;
                         const bool in_x = px < x1;
                         const R dx = (int_to_real(px - cx, R(0)) - fx) * sx;
-                        const R qx = fma(dx, dx, cc) + sqrt_guard(R(0));
+                        const R qx = fma(dx, dx, cc); // cc carries sqrt_guard()
                         R dy = int_to_real(y0 + pr - cy, R(0)) - fy;
                         const R dstep = int_to_real(rows_per_it, R(0));
                         R *a = my_acc + ((y0 + pr) * SX + px);
