@@ -66,7 +66,10 @@ template <> struct Real2<double> { using type = double2; };
 // Column table as the device sees it: entry i holds (T[i], T[i+1] - T[i]) so
 // one vector load serves the lerp T[i] + f (T[i+1] - T[i]).
 template <typename R> struct LutView {
-    const typename Real2<R>::type *tab;  // shared memory
+    // 32-bit shared-memory address of the table minus lut_bias() entries: the (biased) index the
+    // lookup computes is scaled and added to it directly (unsigned arithmetic wraps, so the sum is
+    // the address of the entry)
+    unsigned tab_biased;
     const typename Real2<R>::type *gtab; // global memory instead (tables too large for shared memory)
     R scale;                             // (S - 1) / radius
     int last;                            // S - 1
@@ -79,12 +82,40 @@ constexpr int SPHB_COLUMN_LUT_GLOBAL = 4;
 
 template <int KIND> __device__ __host__ constexpr bool is_lut() { return KIND == SPHB_COLUMN_LUT || KIND == SPHB_COLUMN_LUT_GLOBAL; }
 
-template <int KIND, typename R>
-__device__ __forceinline__ typename Real2<R>::type lut_entry(const LutView<R> &lut, int i)
+__device__ __forceinline__ double2 lds_pair(unsigned addr, double)
 {
-    SPHB_ASSERT(i >= 0 && i <= lut.last);
-    if (KIND == SPHB_COLUMN_LUT_GLOBAL) return __ldg(lut.gtab + i);
-    return lut.tab[i];
+    double2 e;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(addr));
+    return e;
+}
+__device__ __forceinline__ float2 lds_pair(unsigned addr, float)
+{
+    float2 e;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e.x), "=f"(e.y) : "r"(addr));
+    return e;
+}
+
+// Index bias of lut_index(): see there.
+__device__ __forceinline__ constexpr int lut_bias(double) { return 0; }
+__device__ __forceinline__ constexpr int lut_bias(float) { return 0x4B400000; }
+
+template <typename R> __device__ __forceinline__ void lut_set_table(LutView<R> &lut, const void *shared_table)
+{
+    lut.tab_biased = (unsigned)__cvta_generic_to_shared(shared_table) -
+                     (unsigned)lut_bias(R(0)) * (unsigned)sizeof(typename Real2<R>::type);
+    // Opaque to ptxas (a shuffle result cannot be constant-folded): otherwise it re-derives the
+    // address from the shared-memory window at every lookup and pays an extra add for the bias,
+    // which does not fit an LDS immediate.  Called once per kernel by all threads.
+    lut.tab_biased = __shfl_sync(0xffffffffu, lut.tab_biased, 0);
+}
+
+// Entry of the table for a BIASED index (already clamped to last + bias).
+template <int KIND, typename R>
+__device__ __forceinline__ typename Real2<R>::type lut_entry(const LutView<R> &lut, int ib)
+{
+    SPHB_ASSERT(ib - lut_bias(R(0)) >= 0 && ib - lut_bias(R(0)) <= lut.last);
+    if (KIND == SPHB_COLUMN_LUT_GLOBAL) return __ldg(lut.gtab + (ib - lut_bias(R(0))));
+    return lds_pair(lut.tab_biased + (unsigned)ib * (unsigned)sizeof(typename Real2<R>::type), R(0));
 }
 
 // ---- square root -----------------------------------------------------------
@@ -154,9 +185,11 @@ __device__ __forceinline__ int lut_index(double q, double scale)
 {
     return __double2loint(__fma_rd(q, scale, 6755399441055744.0));
 }
+// float: the bit pattern of 1.5 * 2^23 + i is 0x4B400000 + i (i < 2^22).  The bias is not masked off:
+// it is carried through the clamp (compare against last + bias) and folds into the table address.
 __device__ __forceinline__ int lut_index(float q, float scale)
 {
-    return __float_as_int(__fmaf_rd(q, scale, 12582912.0f)) & 0x3fffff;
+    return __float_as_int(__fmaf_rd(q, scale, 12582912.0f));
 }
 // Table entry i from T (double, S samples): shared by every kernel that builds the table.
 template <typename R>
@@ -176,8 +209,8 @@ __device__ __forceinline__ typename Real2<R>::type lut_make_entry(const double *
 template <int KIND, typename R>
 __device__ __forceinline__ R lut_eval(R q, const LutView<R> &lut)
 {
-    int i = lut_index(q, lut.scale);
-    i = min(i, lut.last);
+    int i = lut_index(q, lut.scale);              // biased, see lut_bias()
+    i = min(i, lut.last + lut_bias(R(0)));
     typename Real2<R>::type e = lut_entry<KIND>(lut, i);
     return fma(e.y, q, e.x);
 }

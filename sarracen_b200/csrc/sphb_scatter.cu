@@ -358,7 +358,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     // 124, 127, 145, 216 ms, every doubling costs a resident CTA; the random index is not the
     // bottleneck.)
     LutView<R> lv;
-    lv.tab = lut_s;
+    lut_set_table(lv, lut_s);
     lv.gtab = static_cast<const R2 *>(lut_global);
     lv.scale = R(0);
     lv.last = 0;
@@ -670,7 +670,7 @@ direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
     double *outs[4] = {o0, o1, o2, o3};
 
     LutView<R> lv;
-    lv.tab = lut_s;
+    lut_set_table(lv, lut_s);
     lv.gtab = static_cast<const R2 *>(lut_global);
     lv.scale = R(0);
     lv.last = 0;
