@@ -394,7 +394,7 @@ def run_gpu(args):
     rate = contrib / (ms_render * 1e-3) if ms_render > 0 else 0.0
     if args.dtype == "f64":
         # render: 8 per evaluation in the hot loop, ~12 per useful contribution with idle lanes and the
-        # per-hit set-up (ncu: fp64 pipe 48.9 % at 86 ms, profiles/r1_proj_f64_full_v8.txt)
+        # per-hit set-up (ncu: fp64 pipe 49.5 % at 84 ms, profiles/r1_proj_f64_full_v9.txt)
         dp_per = 12.0 if dom == "ms_render" else 16.0
         compute = {"bound": "fp64 pipe + issue slots", "fp64_inst_per_contribution_est": dp_per,
                    "achieved_fp64_inst_per_s": rate * dp_per, "peak_fp64_inst_per_s": 148 * 64 * sm_clock * 1e6,
@@ -406,7 +406,10 @@ def run_gpu(args):
             compute.update({"bound": "REDG rate + issue slots", "achieved_red_per_s": rate,
                             "peak_red_per_s": red_peak, "red_frac": rate / red_peak})
     else:
-        per = 30.0
+        # thread-instruction slots per contribution: the double kernel executes 5.78e10 warp instructions
+        # for 6.2e10 contributions (29.8 slots each, ncu v9); the float loop is 11.5 instead of 14.5
+        # instructions per evaluation -- not captured by ncu itself, hence an estimate
+        per = 26.0
         compute = {"bound": "issue slots", "inst_per_contribution_est": per,
                    "achieved_inst_per_s": rate * per, "peak_inst_per_s": 148 * 128 * sm_clock * 1e6,
                    "frac_est": rate * per / (148 * 128 * sm_clock * 1e6)}

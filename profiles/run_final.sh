@@ -20,3 +20,6 @@ for f in sorted(glob.glob('gpurun_out/bench_*.json')):
     print(f.split('/')[-1], 'ms', round(d.get('ms_per_step', 0), 2), 'value %.3g' % d.get('value', 0), 'e2e ms', round((d.get('e2e') or {}).get('ms_per_step', 0), 1),
           'cpu', (d.get('cpu_baseline') or {}).get('value'), 'clk', (d.get('clocks') or {}).get('sm_mhz'), (d.get('clocks') or {}).get('reasons'))
 PY
+# ncu evidence for the same command (after it exited 0 above): launch list and one full capture
+python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/plain.json 2>gpurun_out/plain.err && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_proj.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_list.log 2>&1; echo ncu list rc=$?
+ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 1 -c 1 -o gpurun_out/proj_v9 -f python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo ncu full rc=$?
