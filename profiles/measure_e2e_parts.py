@@ -76,6 +76,9 @@ elif which in ("proj", "proj32"):
     col = s.QuinticSplineKernel().get_column_kernel_func(1000)
     call = lambda hc: s.B200Backend.interpolate_3d_projection(hc["x"], hc["y"], hc["w"], hc["h"], col, wl["radius"],
                                                               wl["nx"], wl["ny"], *wl["lim"], False)
+if "--pageable" in sys.argv:
+    ms = wall(lambda: call(cols), reps=2)
+    print(json.dumps({"what": f"{which} e2e from pageable NumPy arrays, default schedule", "ms": ms}), flush=True)
 host = {kk: torch.from_numpy(v).pin_memory() for kk, v in cols.items()}
 for first, growth, cap in ((1 << 23, 3, 1 << 24), (1 << 23, 1, 1 << 23), (1 << 22, 2, 1 << 25), (0, 0, 0)):
     if first == 0:

@@ -134,6 +134,51 @@ def _chunk_bounds(n: int):
 
 _copy_streams = {}
 
+# Pageable host columns (plain NumPy arrays -- what Sarracen passes) copy at ~10 GB/s through the
+# driver's own staging; here they are staged through small page-locked slots instead, one worker
+# thread per column (the host memcpy releases the GIL), each slot sent on as soon as it is filled.
+_STAGE_ELEMS, _STAGE_SLOTS = 1 << 21, 3
+_stage_pool = None
+
+
+class _StageRing:
+    """Page-locked staging slots of one worker (one column at a time), reused round-robin."""
+
+    def __init__(self):
+        self.slots = {}   # dtype -> [[buffer, event or None], ...]
+        self.turn = {}
+
+    def next(self, dtype):
+        ring = self.slots.get(dtype)
+        if ring is None:
+            ring = self.slots[dtype] = [[torch.empty(_STAGE_ELEMS, dtype=dtype, pin_memory=True), None]
+                                        for _ in range(_STAGE_SLOTS)]
+            self.turn[dtype] = 0
+        slot = ring[self.turn[dtype]]
+        self.turn[dtype] = (self.turn[dtype] + 1) % _STAGE_SLOTS
+        if slot[1] is not None:
+            slot[1].synchronize()   # the copy that last read this slot has finished
+        return slot
+
+
+_stage_rings = {}
+
+
+def _stage_column(j, src, dst, copy_stream):
+    """Worker: pageable `src` (host) -> `dst` (device) through worker j's page-locked slots."""
+    ring = _stage_rings.get(j)
+    if ring is None:
+        ring = _stage_rings[j] = _StageRing()
+    n = src.numel()
+    with torch.cuda.stream(copy_stream):
+        for off in range(0, n, _STAGE_ELEMS):
+            m = min(_STAGE_ELEMS, n - off)
+            slot = ring.next(src.dtype)
+            slot[0][:m].copy_(src[off:off + m])
+            dst[off:off + m].copy_(slot[0][:m], non_blocking=True)
+            slot[1] = torch.cuda.Event()
+            slot[1].record(copy_stream)
+
 
 def _host_columns(arrays):
     """1-D host tensors sharing memory with the inputs, or None if any column is not host data."""
@@ -175,13 +220,25 @@ def streamed_scatter(arrays, dev, render):
     bufs = [[torch.empty(largest, dtype=c.dtype, device=dev) for c in cols] for _ in range(2)]
     ready, free = [None, None], [None, None]
 
+    pageable = [j for j, c in enumerate(cols) if not c.is_pinned()]
+    global _stage_pool
+    if pageable and _stage_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _stage_pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix="sphb-stage")
+
     def upload(k):
         b, (lo, hi) = k % 2, bounds[k]
         with torch.cuda.stream(copy_stream):
             if free[b] is not None:
                 copy_stream.wait_event(free[b])
-            for buf, c in zip(bufs[b], cols):
-                buf[:hi - lo].copy_(c[lo:hi], non_blocking=True)
+            jobs = []
+            for j, (buf, c) in enumerate(zip(bufs[b], cols)):
+                if c.is_pinned():
+                    buf[:hi - lo].copy_(c[lo:hi], non_blocking=True)
+                else:
+                    jobs.append(_stage_pool.submit(_stage_column, j % 8, c[lo:hi], buf[:hi - lo], copy_stream))
+            for job in jobs:
+                job.result()
             ready[b] = torch.cuda.Event()
             ready[b].record(copy_stream)
 
@@ -189,13 +246,15 @@ def streamed_scatter(arrays, dev, render):
     out = None
     for k, (lo, hi) in enumerate(bounds):
         b = k % 2
-        if k + 1 < len(bounds):
-            upload(k + 1)
         main.wait_event(ready[b])
         views = [buf[:hi - lo] if buf.dtype == dtype else buf[:hi - lo].to(dtype) for buf in bufs[b]]
         out = render(views, out, k > 0)
         free[b] = torch.cuda.Event()
         free[b].record(main)
+        # after the launch: the host side of the next upload (staging copies of pageable columns)
+        # then overlaps this chunk's kernels
+        if k + 1 < len(bounds):
+            upload(k + 1)
     # the buffers go back to the caching allocator of the main stream: make it wait for the copies
     main.wait_stream(copy_stream)
     return out
