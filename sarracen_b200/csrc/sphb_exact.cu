@@ -331,7 +331,11 @@ __global__ void exact_units_kernel(ExactView v, const T *x, const T *y, const T 
 // One warp per work unit (grid-stride): the unit's particle is found by binary
 // search in the scanned unit offsets; the lanes take the unit's 32 pixels.
 template <typename T, int NW, bool PROJ3D>
-__global__ void __launch_bounds__(kExactWarps * 32)
+// 8 CTAs (32 warps) per SM at 64 registers: the kernel waits on instruction fetch (ncu: 2.9
+// 'no instruction' stalls per issue, 2 500+ SASS instructions of inlined log / atan / acos) and on
+// dependent FP64 chains, so resident warps are worth more than the ~200 bytes of spills
+// (profiles/r1_exact2d_v1.txt; 5 CTAs at 88 registers: 28.4 / 95.5 ms, 8 CTAs: 26.7 / 92.3 ms).
+__global__ void __launch_bounds__(kExactWarps * 32, 8)
 exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
              const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
              const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets, double *o0,
