@@ -207,20 +207,33 @@ emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, const 
     bool small;
     if (!particle_tiles(v, x, y, z, h, i, b, small)) return;
     {
-        T *r = recs + (size_t)i * v.rec_stride;
-        r[0] = x[i];
-        r[1] = y[i];
-        r[2] = h[i];
+        // packed record, written as 16-byte vectors (a scalar store per field touched every
+        // 32-byte sector of the record array 4-8 times)
+        T f[8] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+        f[0] = x[i];
+        f[1] = y[i];
+        f[2] = h[i];
         if (v.rec_stride == 4) {
-            r[3] = w0[i];
+            f[3] = w0[i];
         } else {
-            r[3] = z ? z[i] : T(0);
-            r[4] = w0[i];
-            r[5] = nw > 1 ? w1[i] : T(0);
-            if (v.rec_stride == 8) {
-                r[6] = nw > 2 ? w2[i] : T(0);
-                r[7] = nw > 3 ? w3[i] : T(0);
-            }
+            f[3] = z ? z[i] : T(0);
+            f[4] = w0[i];
+            f[5] = nw > 1 ? w1[i] : T(0);
+            f[6] = (v.rec_stride == 8 && nw > 2) ? w2[i] : T(0);
+            f[7] = (v.rec_stride == 8 && nw > 3) ? w3[i] : T(0);
+        }
+        T *r = recs + (size_t)i * v.rec_stride;
+        if (sizeof(T) == 8) {
+            double2 *q = reinterpret_cast<double2 *>(r);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (2 * k < v.rec_stride) q[k] = make_double2((double)f[2 * k], (double)f[2 * k + 1]);
+        } else {
+            float4 *q = reinterpret_cast<float4 *>(r);
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+                if (4 * k < v.rec_stride)
+                    q[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
         }
     }
     uint64_t o = offsets[i];
