@@ -166,39 +166,50 @@ __device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint64_t *counts,
-                   unsigned long long *n_small)
+count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint32_t *counts,
+                   unsigned long long *totals)
 {
-    // Grid-stride over the particles, so that the number of direct-path particles reaches global
-    // memory as ONE atomic per CTA of a few-hundred-CTA grid: with a CTA per 256 particles a
-    // set that is all small footprints (config 4: 2^27 particles) queued half a million atomics on
-    // one address.
-    unsigned mine = 0;
+    // Grid-stride over the particles; the two totals -- direct-path particles (totals[0]) and list
+    // entries (totals[1], 64-bit: the 32-bit per-particle counts are scanned in 32 bits, which is
+    // only valid once the host has seen that the total is below 2^31) -- reach global memory as
+    // one atomic each per CTA of a few-hundred-CTA grid.
+    unsigned mine_small = 0;
+    unsigned long long mine_all = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
         TileBox b;
-        uint64_t c = 0; // counts[n] = 0 so that the exclusive scan leaves the total there
+        uint32_t c = 0; // counts[n] = 0 so that the exclusive scan leaves the total there
         bool small = false;
         if (i < n && particle_tiles(v, x, y, z, h, i, b, small))
-            c = small ? 1
-                      : (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) * (uint64_t)(b.z1 - b.z0 + 1);
-        counts[i] = c;
-        mine += (small && c) ? 1u : 0u;
+            c = small ? 1u
+                      : (uint32_t)(b.x1 - b.x0 + 1) * (uint32_t)(b.y1 - b.y0 + 1) * (uint32_t)(b.z1 - b.z0 + 1);
+        counts[i] = c; // fits: the raster has fewer than 2^30 tiles
+        mine_small += (small && c) ? 1u : 0u;
+        mine_all += c;
     }
-    __shared__ unsigned long long block_small;
-    if (threadIdx.x == 0) block_small = 0;
+    __shared__ unsigned long long block_small, block_all;
+    if (threadIdx.x == 0) block_small = block_all = 0;
     __syncthreads();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&block_small, (unsigned long long)mine);
+    for (int o = 16; o > 0; o >>= 1) {
+        mine_small += __shfl_xor_sync(0xffffffffu, mine_small, o);
+        mine_all += __shfl_xor_sync(0xffffffffu, mine_all, o);
+    }
+    if ((threadIdx.x & 31) == 0 && mine_all) {
+        atomicAdd(&block_small, (unsigned long long)mine_small);
+        atomicAdd(&block_all, mine_all);
+    }
     __syncthreads();
-    if (threadIdx.x == 0 && block_small) atomicAdd(n_small, block_small);
+    if (threadIdx.x == 0 && block_all) {
+        if (block_small) atomicAdd(totals, block_small);
+        atomicAdd(totals + 1, block_all);
+    }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0, const T *w1,
-                  const T *w2, const T *w3, int nw, int64_t n, const uint64_t *offsets, uint32_t *keys,
+                  const T *w2, const T *w3, int nw, int64_t n, const uint32_t *offsets, uint32_t *keys,
                   uint32_t *vals, T *recs)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1117,11 +1128,11 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
 
     // ---- phase A: count and scan ------------------------------------------
     size_t scan_tmp = 0;
-    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint64_t *)nullptr, (uint64_t *)nullptr,
+    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                             n + 1, stream));
     Workspace a(ws);
-    uint64_t *offsets = a.take<uint64_t>(n + 1); // counts, scanned in place
-    unsigned long long *n_small_dev = a.take<unsigned long long>(1);
+    uint32_t *offsets = a.take<uint32_t>(n + 1); // counts, scanned in place
+    unsigned long long *n_small_dev = a.take<unsigned long long>(2); // direct-path particles, list entries
     unsigned char *scan_ws = a.take<unsigned char>(scan_tmp);
     const size_t need_a = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_a;
@@ -1133,7 +1144,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     const T *z = static_cast<const T *>(p->z), *h = static_cast<const T *>(p->h);
     const int blocks = div_up(n + 1, 256);
     if (timed) SPHB_CUDA(cudaEventRecord(ev[0], stream));
-    SPHB_CUDA(cudaMemsetAsync(n_small_dev, 0, sizeof(unsigned long long), stream));
+    SPHB_CUDA(cudaMemsetAsync(n_small_dev, 0, 2 * sizeof(unsigned long long), stream));
     {
         int sms = 0;
         SPHB_CUDA(sm_count(&sms));
@@ -1142,11 +1153,11 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     }
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
-    uint64_t total = 0;
-    unsigned long long n_small_host = 0;
-    SPHB_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-    SPHB_CUDA(cudaMemcpyAsync(&n_small_host, n_small_dev, sizeof(n_small_host), cudaMemcpyDeviceToHost, stream));
+    unsigned long long totals_host[2] = {0, 0};
+    SPHB_CUDA(cudaMemcpyAsync(totals_host, n_small_dev, sizeof(totals_host), cudaMemcpyDeviceToHost, stream));
     SPHB_CUDA(cudaStreamSynchronize(stream));
+    const unsigned long long n_small_host = totals_host[0];
+    const uint64_t total = totals_host[1]; // the 32-bit scan is meaningful only if this passes the check below
     if (stats) {
         stats->n_pairs = (int64_t)total - (int64_t)n_small_host;
         stats->n_direct = (int64_t)n_small_host;
