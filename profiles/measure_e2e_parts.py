@@ -80,7 +80,7 @@ if "--pageable" in sys.argv:
     ms = wall(lambda: call(cols), reps=2)
     print(json.dumps({"what": f"{which} e2e from pageable NumPy arrays, default schedule", "ms": ms}), flush=True)
 host = {kk: torch.from_numpy(v).pin_memory() for kk, v in cols.items()}
-for first, growth, cap in ((1 << 23, 3, 1 << 24), (1 << 23, 1, 1 << 23), (1 << 22, 2, 1 << 25), (0, 0, 0)):
+for first, growth, cap in ((1 << 23, 3, 1 << 24), (1 << 23, 16, 1 << 24), (1 << 23, 4, 1 << 25), (1 << 23, 1, 1 << 23), (1 << 22, 2, 1 << 25), (0, 0, 0)):
     if first == 0:
         backend._STREAM_MIN = 1 << 40   # single upload
     else:

@@ -111,7 +111,7 @@ def test_upload_chunk_schedule_and_host_column_views():
         assert backend._CHUNK_FIRST_MIN <= sizes[0] <= backend._CHUNK_FIRST_MAX
         assert max(sizes) <= backend._CHUNK_MAX
         assert all(sizes[i + 1] <= backend._CHUNK_GROWTH * sizes[i] for i in range(len(sizes) - 1))
-    assert len(backend._chunk_bounds(1 << 24)) == 4 and len(backend._chunk_bounds(1 << 27)) == 9
+    assert len(backend._chunk_bounds(1 << 24)) == 3 and len(backend._chunk_bounds(1 << 27)) == 9
 
     a = np.arange(6.0)
     ro = np.arange(6.0)

@@ -396,7 +396,7 @@ def test_streamed_uploads_match_single_upload(B, monkeypatch):
     monkeypatch.setattr(backend, "_STREAM_MIN", 1000)
     monkeypatch.setattr(backend, "_CHUNK_FIRST_MIN", 300)
     monkeypatch.setattr(backend, "_CHUNK_MAX", 1500)
-    assert backend._chunk_bounds(n) == [(0, 312), (312, 1248), (1248, 2748), (2748, 4248), (4248, 5003)]
+    assert backend._chunk_bounds(n) == [(0, 312), (312, 1560), (1560, 3060), (3060, 4560), (4560, 5003)]
     calls = []
     real = backend.ops.scatter2d
     monkeypatch.setattr(backend.ops, "scatter2d", lambda *a, **kw: (calls.append(kw.get("accumulate")), real(*a, **kw))[1])
