@@ -26,7 +26,6 @@ host cores over a bounded sample of the same workload.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

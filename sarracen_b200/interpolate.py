@@ -19,13 +19,13 @@ for a GPU-resident pipeline:
 CPU path -- and any other code raises `ValueError("Invalid backend")` like
 `get_backend` (:1640-1658).
 """
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import ops
-from .kernels import BaseKernel, WeightFunction
+from .kernels import BaseKernel
 
 try:  # scipy is only needed to turn a Rotation / Euler angles into a 3x3 matrix
     from scipy.spatial.transform import Rotation

@@ -7,7 +7,7 @@ missing library or a non-CUDA tensor raises.
 """
 import ctypes
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import torch
 
