@@ -467,3 +467,31 @@ def test_multi_weight_tiles_across_a_tall_raster(B, nw, dtype, tol):
         for w, o in zip(ws, outs):
             ref = OracleBackend.interpolate_2d_render(x, y, w, h, okern, 3.0, nx, ny, 0.0, 1.0, 0.0, 1.0, False)
             assert_parity(o.cpu().numpy(), ref, tol, f"{nw} weights")
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_extreme_footprints_and_degenerate_rasters(B, dtype, tol):
+    """Footprints far larger than the raster (every tile of every particle), far smaller than a
+    pixel, rasters of one pixel, one column and one row, a one-plane voxel grid."""
+    from oracle import OracleBackend, OracleKernel
+    rng = np.random.default_rng(99)
+    n = 40
+    x, y, z = rng.uniform(-0.2, 1.2, n), rng.uniform(-0.2, 1.2, n), rng.uniform(0, 1, n)
+    h = np.concatenate([rng.uniform(3.0, 12.0, n // 2), rng.uniform(1e-5, 1e-3, n - n // 2)])
+    w = rng.uniform(0.5, 1.5, n)
+    x, y, z, h, w = (a.astype(dtype) for a in (x, y, z, h, w))
+    k = _kernel("cubic")
+    ok = OracleKernel("cubic")
+    for nx, ny in ((1, 1), (1, 257), (300, 1), (333, 141)):
+        out = B.interpolate_2d_render(x, y, w, h, k.w, 2.0, nx, ny, 0.0, 1.0, 0.0, 1.0, False)
+        ref = OracleBackend.interpolate_2d_render(x, y, w, h, ok, 2.0, nx, ny, 0.0, 1.0, 0.0, 1.0, False)
+        assert out.shape == (ny, nx)
+        assert_parity(out, ref, tol, f"{nx}x{ny} raster")
+    out = B.interpolate_3d_cross(x, y, z, 0.5, w, h, k.w, 2.0, 65, 33, 0.0, 1.0, 0.0, 1.0)
+    ref = OracleBackend.interpolate_3d_cross(x, y, z, 0.5, w, h, ok, 2.0, 65, 33, 0.0, 1.0, 0.0, 1.0)
+    assert_parity(out, ref, tol, "cross-section")
+    for nz in (1, 19):
+        out = B.interpolate_3d_grid(x, y, z, w, h, k.w, 2.0, 40, 23, nz, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+        ref = OracleBackend.interpolate_3d_grid(x, y, z, w, h, ok, 2.0, 40, 23, nz, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
+        assert out.shape == (nz, 23, 40)
+        assert_parity(out, ref, tol, f"grid with {nz} planes")
