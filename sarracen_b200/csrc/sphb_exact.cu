@@ -12,13 +12,14 @@
 // (boxes range from 1 to thousands of pixels).  The work is flattened into
 // units of 32 consecutive pixels of one particle's box (count -> exclusive
 // scan); warps take units grid-stride, find the particle by binary search in
-// the scanned offsets, every lane evaluates its pixel's full boundary integral
-// and adds it to the image with red.global.add.f64.
+// the scanned offsets, every lane evaluates its item and adds it to the image
+// with red.global.add.f64.
 //
-//  - 2-D: the four edge integrals of a pixel are evaluated directly.  The
-//    reference evaluates each interior edge once and adds it to one pixel and
-//    subtracts it from the neighbour (:404-440); line_int is exactly
-//    antisymmetric under that swap, so both give the same four terms per pixel.
+//  - 2-D: the work items are the pixel EDGES of the box, not its pixels: an
+//    interior edge's flux integral is added to the pixel on one side and
+//    subtracted from the pixel on the other (line_int is odd in r0 and symmetric
+//    in d1, d2), as the reference does (:404-440) -- two integrals per pixel
+//    instead of four.  3-D projection: one lane per pixel, six face integrals.
 //  - A particle whose clamped pixel range is empty contributes nothing; the
 //    reference's lone top-row / left-column edge terms for such a particle
 //    (:370, :387) and its out-of-bounds row write (:353) are not reproduced.
@@ -315,7 +316,7 @@ __device__ __forceinline__ bool exact_box(const ExactView &v, const T *x, const 
 // of units of particle p (units[n] = 0 so the exclusive scan leaves the total
 // in units[n]).
 template <typename T>
-__global__ void exact_units_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
+__global__ void exact_units_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n, bool edges,
                                    unsigned long long *units)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,8 +324,12 @@ __global__ void exact_units_kernel(ExactView v, const T *x, const T *y, const T 
     unsigned long long c = 0;
     double xp, yp, hp;
     int i0, i1, j0, j1;
-    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1))
-        c = (unsigned long long)(((int64_t)(i1 - i0) * (j1 - j0) + 31) / 32);
+    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
+        const int64_t bw = i1 - i0, bh = j1 - j0;
+        // work items: the pixels of the box (3-D projection) or its pixel EDGES (2-D render)
+        const int64_t items = edges ? (bw + 1) * bh + bw * (bh + 1) : bw * bh;
+        c = (unsigned long long)((items + 31) / 32);
+    }
     units[p] = c;
 }
 
@@ -360,36 +365,71 @@ exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, cons
         double sx, sy, sh;
         int si0, si1, sj0, sj1;
         if (!exact_box(v, x, y, h, p, sx, sy, sh, si0, si1, sj0, sj1)) continue;
-        const int bw = si1 - si0, total_px = bw * (sj1 - sj0);
+        const int bw = si1 - si0, bh = sj1 - sj0;
         const int e = (int)(u - offsets[p]) * 32 + lane;
-        if (e >= total_px) continue;
+        if (!PROJ3D) {
+            // 2-D render (cpu_backend.py:365-440): a pixel's integral is the sum of the flux
+            // integrals over its four edges, and an interior edge serves the two pixels it
+            // separates with opposite signs (line_int is odd in r0 and symmetric in d1, d2) -- the
+            // reference shares them the same way (:404-440).  So the lanes take EDGES, not pixels:
+            // (bw + 1) bh vertical and bw (bh + 1) horizontal ones, half the integrals of four per
+            // pixel; each adds to the pixel after it and subtracts from the pixel before it.
+            const int nv = (bw + 1) * bh;
+            if (e >= nv + bw * (bh + 1)) continue;
+            double val;
+            int ia, ja, ib, jb; // pixel that gains the integral, pixel that loses it
+            bool has_a, has_b;
+            if (e < nv) {
+                const int jj = e / (bw + 1), ii = e - jj * (bw + 1);
+                const int i = si0 + ii, j = sj0 + jj;
+                const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
+                val = ex::line_int(0.5 * v.pwx - dx, 0.5 * v.pwy - dy, 0.5 * v.pwy + dy, sh); // left edge of (i, j)
+                ia = i; ja = j; ib = i - 1; jb = j;
+                has_a = ii < bw; has_b = ii > 0;
+            } else {
+                const int f = e - nv;
+                const int jj = f / bw, ii = f - jj * bw;
+                const int i = si0 + ii, j = sj0 + jj;
+                const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
+                val = ex::line_int(0.5 * v.pwy - dy, 0.5 * v.pwx + dx, 0.5 * v.pwx - dx, sh); // top edge of (i, j)
+                ia = i; ja = j; ib = i; jb = j - 1;
+                has_a = jj < bh; has_b = jj > 0;
+            }
+            // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (:333, :365)
+            val *= (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
+            if (val != 0.0) {
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const double wv = (double)__ldg(wsrc[k] + p) * val;
+                    if (has_a) {
+                        SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
+                        red_add(outs[k] + (size_t)ja * v.nx + ia, wv);
+                    }
+                    if (has_b) {
+                        SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
+                        red_add(outs[k] + (size_t)jb * v.nx + ib, -wv);
+                    }
+                }
+            }
+            continue;
+        }
+        if (e >= bw * bh) continue;
         const int jj = e / bw, ii = e - jj * bw;
         const int i = si0 + ii, j = sj0 + jj;
         const double xpix = v.x_min + (i + 0.5) * v.pwx, ypix = v.y_min + (j + 0.5) * v.pwy;
         const double dx = xpix - sx, dy = ypix - sy;
-        double val;
-        if (PROJ3D) {
-            // cpu_backend.py:673-713
-            const double q2 = (dx * dx + dy * dy) / (sh * sh);
-            if (!(q2 < 4.0 + 3.0 * v.pwx * v.pwy / (sh * sh))) continue;
-            const double pwz = 4.0 * sh;
-            double s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
-            s += ex::surface_int(ypix - sy + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
-            s += ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
-            s += ex::surface_int(xpix - sx + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
-            s += ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
-            // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (:628-629)
-            const double h3 = sh * sh * sh;
-            val = s * (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
-        } else {
-            // cpu_backend.py:365-440: top, left, bottom, right edge
-            double s = ex::line_int(0.5 * v.pwy - dy, 0.5 * v.pwx + dx, 0.5 * v.pwx - dx, sh);
-            s += ex::line_int(0.5 * v.pwx - dx, 0.5 * v.pwy - dy, 0.5 * v.pwy + dy, sh);
-            s += ex::line_int(0.5 * v.pwy + dy, 0.5 * v.pwx - dx, 0.5 * v.pwx + dx, sh);
-            s += ex::line_int(0.5 * v.pwx + dx, 0.5 * v.pwy + dy, 0.5 * v.pwy - dy, sh);
-            // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (:333, :365)
-            val = s * (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
-        }
+        // cpu_backend.py:673-713
+        const double q2 = (dx * dx + dy * dy) / (sh * sh);
+        if (!(q2 < 4.0 + 3.0 * v.pwx * v.pwy / (sh * sh))) continue;
+        const double pwz = 4.0 * sh;
+        double s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
+        s += ex::surface_int(ypix - sy + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
+        s += ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
+        s += ex::surface_int(xpix - sx + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
+        s += ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
+        // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (:628-629)
+        const double h3 = sh * sh * sh;
+        const double val = s * (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
         if (val != 0.0) {
             SPHB_ASSERT(i >= 0 && i < v.nx && j >= 0 && j < v.ny && p >= 0 && p < n);
 #pragma unroll
@@ -447,7 +487,8 @@ static int exact_typed(const ExactView &v, const sphb_particles *p, bool proj3d,
     unsigned long long *offsets = static_cast<unsigned long long *>(ws);
     void *scan_ws = static_cast<unsigned char *>(ws) + off_bytes;
     exact_units_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(
-        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), n, offsets);
+        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), n, !proj3d,
+        offsets);
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
     return proj3d ? exact_nw<T, true>(v, p, offsets, out, stream) : exact_nw<T, false>(v, p, offsets, out, stream);
