@@ -19,7 +19,9 @@
 //    interior edge's flux integral is added to the pixel on one side and
 //    subtracted from the pixel on the other (line_int is odd in r0 and symmetric
 //    in d1, d2), as the reference does (:404-440) -- two integrals per pixel
-//    instead of four.  3-D projection: one lane per pixel, six face integrals.
+//    instead of four.  3-D projection likewise: one item per pixel for the top /
+//    bottom faces, one per side face between neighbouring columns -- three
+//    surface integrals per pixel instead of five.
 //  - A particle whose clamped pixel range is empty contributes nothing; the
 //    reference's lone top-row / left-column edge terms for such a particle
 //    (:370, :387) and its out-of-bounds row write (:353) are not reproduced.
@@ -326,8 +328,10 @@ __global__ void exact_units_kernel(ExactView v, const T *x, const T *y, const T 
     int i0, i1, j0, j1;
     if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
         const int64_t bw = i1 - i0, bh = j1 - j0;
-        // work items: the pixels of the box (3-D projection) or its pixel EDGES (2-D render)
-        const int64_t items = edges ? (bw + 1) * bh + bw * (bh + 1) : bw * bh;
+        // work items: the pixel EDGES of the box (2-D render); its pixels (top / bottom faces) and the
+        // side faces between them (3-D projection)
+        const int64_t shared = (bw + 1) * bh + bw * (bh + 1);
+        const int64_t items = edges ? shared : bw * bh + shared;
         c = (unsigned long long)((items + 31) / 32);
     }
     units[p] = c;
@@ -413,28 +417,64 @@ exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, cons
             }
             continue;
         }
-        if (e >= bw * bh) continue;
-        const int jj = e / bw, ii = e - jj * bw;
-        const int i = si0 + ii, j = sj0 + jj;
-        const double xpix = v.x_min + (i + 0.5) * v.pwx, ypix = v.y_min + (j + 0.5) * v.pwy;
-        const double dx = xpix - sx, dy = ypix - sy;
-        // cpu_backend.py:673-713
-        const double q2 = (dx * dx + dy * dy) / (sh * sh);
-        if (!(q2 < 4.0 + 3.0 * v.pwx * v.pwy / (sh * sh))) continue;
-        const double pwz = 4.0 * sh;
-        double s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
-        s += ex::surface_int(ypix - sy + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
-        s += ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh);
-        s += ex::surface_int(xpix - sx + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
-        s += ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh);
+        // 3-D projection (cpu_backend.py:673-713): the column of a pixel has six faces.  Top and
+        // bottom give the same integral (one item per pixel, counted twice); a side face is shared
+        // by the two columns it separates with opposite signs (surface_int is odd in r0), so the
+        // side faces are items of their own: 3 surface integrals per pixel instead of 5.  A pixel
+        // takes part only if its centre passes the reference's cull q^2 < 4 + 3 pwx pwy / h^2 (:675).
+        const int nt = bw * bh, nv = (bw + 1) * bh;
+        if (e >= nt + nv + bw * (bh + 1)) continue;
+        const double pwz = 4.0 * sh, hinv2 = 1.0 / (sh * sh);
+        const double cull = 4.0 + 3.0 * v.pwx * v.pwy * hinv2;
+        auto passes = [&](int i, int j) {
+            const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
+            return (dx * dx + dy * dy) * hinv2 < cull;
+        };
+        double s;
+        int ia, ja, ib = 0, jb = 0;
+        bool has_a, has_b = false;
+        if (e < nt) {
+            const int jj = e / bw, ii = e - jj * bw;
+            ia = si0 + ii; ja = sj0 + jj;
+            has_a = passes(ia, ja);
+            if (!has_a) continue;
+            const double xpix = v.x_min + (ia + 0.5) * v.pwx, ypix = v.y_min + (ja + 0.5) * v.pwy;
+            s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
+        } else if (e < nt + nv) {
+            const int f = e - nt;
+            const int jj = f / (bw + 1), ii = f - jj * (bw + 1);
+            ia = si0 + ii; ja = sj0 + jj; ib = ia - 1; jb = ja;
+            has_a = ii < bw && passes(ia, ja);
+            has_b = ii > 0 && passes(ib, jb);
+            if (!has_a && !has_b) continue;
+            const double xpix = v.x_min + (ia + 0.5) * v.pwx, ypix = v.y_min + (ja + 0.5) * v.pwy;
+            s = ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh); // -x face of (ia, ja)
+        } else {
+            const int f = e - nt - nv;
+            const int jj = f / bw, ii = f - jj * bw;
+            ia = si0 + ii; ja = sj0 + jj; ib = ia; jb = ja - 1;
+            has_a = jj < bh && passes(ia, ja);
+            has_b = jj > 0 && passes(ib, jb);
+            if (!has_a && !has_b) continue;
+            const double xpix = v.x_min + (ia + 0.5) * v.pwx, ypix = v.y_min + (ja + 0.5) * v.pwy;
+            s = ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh); // -y face of (ia, ja)
+        }
         // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (:628-629)
         const double h3 = sh * sh * sh;
         const double val = s * (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
         if (val != 0.0) {
-            SPHB_ASSERT(i >= 0 && i < v.nx && j >= 0 && j < v.ny && p >= 0 && p < n);
 #pragma unroll
-            for (int k = 0; k < NW; k++)
-                red_add(outs[k] + (size_t)j * v.nx + i, (double)__ldg(wsrc[k] + p) * val);
+            for (int k = 0; k < NW; k++) {
+                const double wv = (double)__ldg(wsrc[k] + p) * val;
+                if (has_a) {
+                    SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
+                    red_add(outs[k] + (size_t)ja * v.nx + ia, wv);
+                }
+                if (has_b) {
+                    SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
+                    red_add(outs[k] + (size_t)jb * v.nx + ib, -wv);
+                }
+            }
         }
     }
 }
