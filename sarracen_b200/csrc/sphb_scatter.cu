@@ -10,19 +10,25 @@
 // over all pixel centres inside the support -- computed here in a different
 // order and a different decomposition:
 //
-//  1. bin    every particle is keyed by the raster tiles its support box
-//            covers (count -> exclusive scan -> emit (tile, particle) pairs),
+//  1. bin    every particle's support box is classified: boxes of at most
+//            small_edge pixels per axis are listed once (direct path), larger
+//            ones are keyed by every raster tile they cover (count ->
+//            exclusive scan -> emit (tile, particle) pairs); the emit pass also
+//            writes one packed record per particle,
 //  2. sort   cub::DeviceRadixSort on the tile key (only the bits in use),
 //  3. render the sorted pair list is cut into fixed chunks, one CTA per
 //            chunk.  A CTA walks the tile segments of its chunk; per tile it
 //            stages the particles' derived records into shared memory, and
 //            every warp owns an exclusive strip (2-D: rows, 3-D: z-planes) of
-//            the tile's shared-memory accumulator, so the footprint walk is a
-//            plain load-add-store without atomics.  Lanes are spread linearly
-//            over (footprint box ∩ strip).
+//            the tile, so accumulation needs no atomics: wide footprints go to
+//            per-lane register accumulators on fixed pixels, narrow ones to a
+//            plain load-add-store on the shared-memory tile (render_kernel),
 //  4. flush  a finished tile segment is added to the float64 output with
-//            red.global.add.f64 -- the only global atomics, once per tile
-//            segment, coalesced along x.
+//            red.global.add.f64 -- the only global atomics of the tile path,
+//            once per tile segment, coalesced along x,
+//  5. direct the listed small-footprint particles are rendered straight into
+//            the raster, a lane per in-plane pixel, one red.global.add.f64 per
+//            contribution (direct_kernel).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
