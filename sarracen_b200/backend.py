@@ -165,6 +165,11 @@ class _StageRing:
 _stage_rings = {}
 
 
+def release_host_buffers() -> None:
+    """Free the page-locked staging slots (up to 3 x 16 MB per column worker) kept between calls."""
+    _stage_rings.clear()
+
+
 def _stage_column(j, src, dst, copy_stream):
     """Worker: pageable `src` (host) -> `dst` (device) through worker j's page-locked slots."""
     ring = _stage_rings.get(j)
