@@ -356,14 +356,16 @@ exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, cons
     const unsigned long long total = offsets[n];
     const unsigned long long stride = (unsigned long long)gridDim.x * kExactWarps;
     for (unsigned long long u = (unsigned long long)blockIdx.x * kExactWarps + warp; u < total; u += stride) {
-        // largest p with offsets[p] <= u
-        int64_t lo = 0, hi = n;
+        // largest p with offsets[p] <= u: a 33-way search, the lanes probe 32 positions at once
+        // (5 dependent rounds of loads for 2^23 particles instead of 23)
+        int64_t lo = 0, hi = n; // offsets[lo] <= u < offsets[hi]
         while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (offsets[mid] <= u)
-                lo = mid;
-            else
-                hi = mid;
+            const int64_t step = (hi - lo + 32) / 33;
+            const int64_t probe = lo + (int64_t)(lane + 1) * step;
+            const bool le = probe < hi && __ldg(offsets + probe) <= u;
+            const int k = __popc(__ballot_sync(0xffffffffu, le)); // offsets are non-decreasing
+            hi = min(hi, lo + (int64_t)(k + 1) * step);
+            lo = lo + (int64_t)k * step;
         }
         const int64_t p = lo;
         double sx, sy, sh;
