@@ -386,7 +386,9 @@ exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, cons
             int ia, ja, ib, jb; // pixel that gains the integral, pixel that loses it
             bool has_a, has_b;
             if (e < nv) {
-                const int jj = e / (bw + 1), ii = e - jj * (bw + 1);
+                // column-major: the lanes of a warp share the edge's x, hence r0 and the q0 region
+                // of the closed forms (the horizontal edges below share y the same way)
+                const int ii = e / bh, jj = e - ii * bh;
                 const int i = si0 + ii, j = sj0 + jj;
                 const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
                 val = ex::line_int(0.5 * v.pwx - dx, 0.5 * v.pwy - dy, 0.5 * v.pwy + dy, sh); // left edge of (i, j)
@@ -444,7 +446,7 @@ exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, cons
             s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
         } else if (e < nt + nv) {
             const int f = e - nt;
-            const int jj = f / (bw + 1), ii = f - jj * (bw + 1);
+            const int ii = f / bh, jj = f - ii * bh; // column-major: one r0 per warp (see the 2-D path)
             ia = si0 + ii; ja = sj0 + jj; ib = ia - 1; jb = ja;
             has_a = ii < bw && passes(ia, ja);
             has_b = ii > 0 && passes(ib, jb);
