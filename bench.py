@@ -150,6 +150,9 @@ def cpu_baseline(wl, budget_s=15.0):
     import oracle
     from oracle import OracleBackend, OracleKernel
     cols = wl["cols"]
+    # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    oracle.set_num_threads(avail)
     threads = oracle.num_threads()
 
     def run(ns, m=None):
@@ -389,7 +392,7 @@ def run_gpu(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"{args.workload}_{args.dtype}")
 
-    base = cpu_baseline(wl) if not args.no_cpu else None
+    base = cpu_baseline(wl) if (not args.no_cpu and world == 1) else None  # rank 0 at N = 1 only
 
     # What bounds the dominant kernel in practice: at SPH-consistent smoothing
     # lengths the per-contribution arithmetic, not HBM.  Instruction counts per contribution are read
