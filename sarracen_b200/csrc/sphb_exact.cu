@@ -42,6 +42,15 @@ namespace ex {
 //   sin 3phi = 3 sin - 4 sin^3.
 // Only atan / acos (for phi) and one log per angle remain -- the same numbers
 // the reference gets from cos(atan(t)) etc., to rounding.
+// 2-D closed forms: one shared copy of each double-precision transcendental (each is ~100 SASS
+// instructions).  Inlined at every use they put the kernel far beyond the instruction cache (ncu: 3.9
+// 'no instruction' stalls per issue, profiles/r1_exact2d_v2.txt); shared: 13.8 -> 12.2 ms.  The 3-D
+// face integrals keep the inlined library calls: there the calls cost more in spills than the
+// instruction fetch saves (62.7 -> 65.3 ms).
+__device__ __noinline__ double m_log(double a) { return log(a); }
+__device__ __noinline__ double m_atan(double a) { return atan(a); }
+__device__ __noinline__ double m_acos(double a) { return acos(a); }
+
 struct Angle {
     double s, c, tn, logs, phi;
 };
@@ -54,8 +63,8 @@ __device__ __forceinline__ Angle angle_from_tan(double t)
     a.c = 1.0 / r;
     a.s = t * a.c;
     a.tn = t;
-    a.logs = log(t + r);
-    a.phi = atan(t);
+    a.logs = m_log(t + r);
+    a.phi = m_atan(t);
     return a;
 }
 
@@ -65,8 +74,8 @@ __device__ __forceinline__ Angle angle_from_cos(double c)
     a.c = c;
     a.s = sqrt(fmax(1.0 - c * c, 0.0));
     a.tn = a.s / c;
-    a.logs = log((1.0 + a.s) / c);
-    a.phi = acos(c);
+    a.logs = m_log((1.0 + a.s) / c);
+    a.phi = m_acos(c);
     return a;
 }
 
