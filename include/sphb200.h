@@ -22,8 +22,9 @@
  *    float64, row-major [y][x] / [z][y][x], like the reference's
  *    (cpu_backend.py:243).
  *  - `stream` is a cudaStream_t passed as void*.  Work is stream-ordered;
- *    the scatter calls synchronise the stream once (they read the bin count
- *    back to size the sort), the others are fully asynchronous.
+ *    the scatter calls synchronise the stream once (they read the bin totals
+ *    back to size the pair list and the cell-ordered record stream), the
+ *    others are fully asynchronous.
  *  - Return value 0 on success, negative SPHB_ERR_* otherwise;
  *    sphb_last_error() returns a thread-local message.
  *  - No global mutable state; re-entrant across streams and devices.
@@ -38,8 +39,9 @@
 extern "C" {
 #endif
 
-#define SPHB_VERSION 100
+#define SPHB_VERSION 200
 #define SPHB_MAX_WEIGHTS 4
+#define SPHB_MAX_STAGES 64
 
 enum { SPHB_F32 = 0, SPHB_F64 = 1 };
 
@@ -93,15 +95,15 @@ typedef struct sphb_raster {
 /* Optional counters filled by the scatter calls (host memory). */
 typedef struct sphb_stats {
     int64_t n_pairs;      /* out: (particle, tile) pairs binned and sorted (tile path) */
-    int64_t n_direct;     /* out: small-footprint particles rendered by the direct path */
+    int64_t n_direct;     /* out: small-footprint particles rendered by the cell path */
     int64_t n_tiles;      /* out: tiles in the raster */
     int32_t tile_x, tile_y, tile_z; /* out: tile size in pixels */
     int32_t time_phases;  /* in: non-zero -> bracket the phases with CUDA events on `stream`
                              and synchronise at the end of the call to read them */
-    float ms_bin;         /* out: count + scan + emit kernels */
-    float ms_sort;        /* out: radix sort + segment boundaries */
-    float ms_render;      /* out: the tile render kernel alone */
-    float ms_direct;      /* out: the direct (small-footprint) kernel alone */
+    float ms_bin;         /* out: count + cell scan + emit kernels */
+    float ms_sort;        /* out: radix sort of the pairs + segment boundaries */
+    float ms_render;      /* out: the tile kernel (large footprints) alone */
+    float ms_direct;      /* out: the cell kernel (small footprints) alone */
     int32_t launches;     /* out: kernels of this library launched by the call (CUB's not counted) */
 } sphb_stats;
 
@@ -140,6 +142,18 @@ int sphb_line2d(const sphb_particles *p, const sphb_kernel *k, int pixels, doubl
 int sphb_line3d(const sphb_particles *p, const sphb_kernel *k, int pixels, double x1, double x2,
                 double y1, double y2, double z1, double z2, int accumulate, double *const *out,
                 sphb_stream stream);
+
+/* Same, rendered in `n_stages` z-slab stages for the multi-GPU reduction along z
+ * (SURVEY 8(e)): stage s finishes every z-plane below stage_planes[s] (ascending; the last
+ * stage finishes the grid whatever its entry says), and right after the kernels of stage s have
+ * been enqueued on `stream` the library calls on_stage(user, s) on the calling thread -- the
+ * caller records an event there and starts reducing that slab on another stream while the later
+ * stages render.  n_stages = 1 with on_stage = NULL is sphb_scatter3d. */
+typedef void (*sphb_stage_fn)(void *user, int stage);
+int sphb_scatter3d_staged(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int accumulate,
+                          double *const *out, void *ws, size_t ws_bytes, size_t *ws_needed, sphb_stats *stats,
+                          int n_stages, const int *stage_planes, sphb_stage_fn on_stage, void *user,
+                          sphb_stream stream);
 
 /* B4 -- exact pixel-area integral of the 2-D cubic spline, replaces
  * CPUBackend._exact_2d_render (cpu_backend.py:317-447) with the integrals of

@@ -1,25 +1,43 @@
-"""Import the unmodified reference (sarracen) from /root/reference.
+"""Import the unmodified reference (sarracen).
 
-TEST INFRASTRUCTURE ONLY, and only usable in the authoring container:
-/root/reference does not exist on the GPU box, so nothing that runs there
-(-m gpu tests, smoke(), bench.py) may call this.  It is used by
-tests/golden/make_golden.py to generate the committed golden vectors and by the
-``-m "not gpu"`` oracle-vs-reference tests, which skip when the reference is
-absent.
+TEST / BENCH INFRASTRUCTURE ONLY -- nothing under sarracen_b200/ imports this.
+
+Search order: $SARRACEN_REFERENCE_ROOT, then `baseline/_ref/` (the
+reference installed by baseline/install_ref.py; git-ignored, travels to the GPU box with the
+gpurun snapshot), then `/root/reference` (authoring container only).  Users:
+tests/golden/make_golden*.py (golden vectors), the oracle-vs-reference tests, the reference
+suite routed through backend='gpu' (tests/test_reference_suite_gpu.py), and bench.py's CPU legs
+(`cpu_baseline.kind = "reference"`: Sarracen's own numba CPUBackend timed on the host cores).
 
 The reference imports matplotlib and seaborn at package import time
-(sarracen/__init__.py:22,26); neither is installed and neither is on the
-scatter path, so empty stand-in modules are registered first.
+(sarracen/__init__.py:22,26); neither is installed and neither is on the scatter path, so
+empty stand-in modules are registered first.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SARRACEN_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _candidates():
+    env = os.environ.get("SARRACEN_REFERENCE_ROOT")
+    if env:
+        yield env
+    yield os.path.join(_REPO, "baseline", "_ref")
+    yield "/root/reference"
+
+
+def reference_root():
+    """Directory that holds the `sarracen` package, or None."""
+    for root in _candidates():
+        if os.path.isfile(os.path.join(root, "sarracen", "__init__.py")):
+            return root
+    return None
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "sarracen"))
+    return reference_root() is not None
 
 
 def _stub(name, **attrs):
@@ -33,12 +51,8 @@ def _stub(name, **attrs):
     return mod
 
 
-def load_reference():
-    """Return the reference ``sarracen`` module (raises if it is absent)."""
-    if not available():
-        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
-    if "sarracen" in sys.modules:
-        return sys.modules["sarracen"]
+def stub_plotting() -> None:
+    """Register empty matplotlib / seaborn modules when the real ones are absent."""
     try:
         import matplotlib  # noqa: F401
         import seaborn  # noqa: F401
@@ -49,8 +63,18 @@ def load_reference():
         mpl.colors = _stub("matplotlib.colors", Colormap=dummy, LogNorm=dummy, SymLogNorm=dummy)
         mpl.pyplot = _stub("matplotlib.pyplot")
         _stub("seaborn")
+
+
+def load_reference():
+    """Return the reference ``sarracen`` module (raises if it is absent)."""
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference not found (looked in $SARRACEN_REFERENCE_ROOT, baseline/_ref, /root/reference)")
+    if "sarracen" in sys.modules:
+        return sys.modules["sarracen"]
+    stub_plotting()
     sys.dont_write_bytecode = True
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import sarracen
     return sarracen

@@ -15,6 +15,7 @@ SPHB_CUBIC, SPHB_QUARTIC, SPHB_QUINTIC, SPHB_COLUMN_LUT = 0, 1, 2, 3
 SPHB_OK, SPHB_ERR_ARGUMENT, SPHB_ERR_WORKSPACE, SPHB_ERR_CUDA, SPHB_ERR_TOO_MANY = 0, -1, -2, -3, -4
 
 EXPORTS = ["sphb_version", "sphb_last_error", "sphb_column_kernel", "sphb_scatter2d", "sphb_scatter3d",
+           "sphb_scatter3d_staged",
            "sphb_line2d", "sphb_line3d", "sphb_exact2d", "sphb_exact3d_proj", "sphb_normalize",
            "sphb_count_contributions"]
 
@@ -51,6 +52,10 @@ class SphbError(RuntimeError):
         self.code = code
 
 
+STAGE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int)
+SPHB_MAX_STAGES = 64
+SPHB_VERSION = 200
+
 _lib = None
 
 
@@ -76,6 +81,8 @@ def load():
     lib.sphb_scatter2d.argtypes = [P, K, R, c_int, c_dbl, c_int, outs, c_vp, c_sz,
                                    ctypes.POINTER(c_sz), S, c_vp]
     lib.sphb_scatter3d.argtypes = [P, K, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), S, c_vp]
+    lib.sphb_scatter3d_staged.argtypes = [P, K, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), S, c_int,
+                                          ctypes.POINTER(c_int), STAGE_FN, c_vp, c_vp]
     lib.sphb_line2d.argtypes = [P, K, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_int, outs, c_vp]
     lib.sphb_line3d.argtypes = [P, K, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_int, outs, c_vp]
     lib.sphb_exact2d.argtypes = [P, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), c_vp]

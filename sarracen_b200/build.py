@@ -16,8 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 BUILD_DIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(OUT_DIR, "libsphb200.so")
-SOURCES = ["sphb_scatter.cu", "sphb_misc.cu", "sphb_exact.cu"]
-HEADERS = [os.path.join(CSRC, "sphb_common.cuh"),
+SOURCES = ["sphb_scatter.cu", "sphb_render.cu", "sphb_cell.cu", "sphb_misc.cu", "sphb_exact.cu"]
+HEADERS = [os.path.join(CSRC, "sphb_common.cuh"), os.path.join(CSRC, "sphb_scatter.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "sphb200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False
                 print(o)
     objs = [os.path.join(BUILD_DIR, s.replace(".cu", suffix + ".o")) for s in SOURCES]
     if force or jobs or _stale(lib, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", lib] + objs
+        cmd = [nvcc] + ARCH + ["-shared", "--cudart", "shared", "-o", lib] + objs
         subprocess.check_call(cmd)
     return lib
 

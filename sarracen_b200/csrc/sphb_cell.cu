@@ -1,0 +1,357 @@
+// Cell kernel of the sampled scatter: small footprints (sm_100a).
+//
+// A particle whose support box is at most small_edge pixels along every axis covers a handful of
+// pixels; binning it per tile, staging it per tile and scanning it per warp costs far more than
+// its few kernel evaluations, and one global reduction per contribution is bound by the
+// reduction rate of the SM (1.29 cycles per lane).  Such particles are therefore counting-sorted
+// by the CELL that holds the origin of their box (32 x 32 pixels / 8 x 8 x 8 voxels; smaller
+// with several weight columns) -- the emit kernel writes their packed records in cell order --
+// and rendered here with a LOCAL ACCUMULATOR:
+//
+//   * a warp takes kCellChunk consecutive records of that stream (a coalesced read: the
+//     records of a cell are contiguous), 32 at a time; every lane derives one particle's box,
+//     scales and terms and parks them in the warp's staging slots;
+//   * the warp owns a private shared-memory accumulator that covers one cell plus the halo a
+//     box can reach beyond it ((cell + halo)^d values per weight).  Particles are walked one at
+//     a time with the lanes laid over the box -- in-plane pixels across lanes (several z-slices
+//     at once for narrow boxes), a loop over z -- and accumulated with plain
+//     load / fma / store: the accumulator is exclusive to the warp, lanes of one particle
+//     touch distinct pixels, so no atomics are needed;
+//   * when the stream moves on to another cell (or the chunk ends) the touched part of the
+//     accumulator is added to the float64 raster with red.global.add.f64, coalesced along x,
+//     and cleared: global atomics only at cell boundaries -- 3.4 per particle instead of 57.6
+//     for BASELINE config 4;
+//   * a batch whose boxes all hold at most 16 pixels (h <~ pixel: 4 contributions per particle)
+//     skips the accumulator: sub-groups of lanes take one particle each and reduce straight
+//     into the raster, which costs less than walking such particles one per warp pass.
+//
+// Replaces the pixel loop of CPUBackend._fast_2d (cpu_backend.py:263-308) and the per-slice loop
+// of CPUBackend.interpolate_3d_grid (:193-220) for small footprints.
+#include "sphb_scatter.cuh"
+
+namespace sphb {
+
+constexpr int kCellMaxWarps = 16;
+constexpr int kTinyVolume = 16; // a batch whose largest box holds <= this many pixels reduces directly
+
+// Staging slots of one warp: one batch of 32 particles.
+template <typename R, int NW> struct CellBatch {
+    R sx[32], sy[32], sz[32]; // pixel -> q along each axis (pixel width / h)
+    R ox[32], oy[32], oz[32]; // q-space offset of the box origin: -(centre - origin) * s
+    R cq[32];                 // dz^2 / h^2 of a cross-section + sqrt guard
+    R term[NW][32];           // norm * w / h^ndim
+    int bx[32], by[32], bz[32]; // box origin (raster pixels)
+    uint32_t dims[32];        // wx | wy << 8 | wz << 16; 0 = nothing to do
+};
+
+template <typename R> struct CellAcc {
+    R *acc;         // the warp's accumulator, NW planes of `plane` elements
+    int s1, s2;     // row and z-plane strides (elements)
+    int plane;      // elements per weight
+    // cell being accumulated (-1: none) and its origin in raster pixels
+    int cell, cx0, cy0, cz0;
+    // touched part of the accumulator, local coordinates [lo, hi)
+    int lx, hx, ly, hy, lz, hz;
+};
+
+template <typename R, int NW>
+__device__ __forceinline__ void cell_flush(CellAcc<R> &a, const View &v, int lane, double *const *outs)
+{
+    if (a.hx > a.lx) {
+        __syncwarp();
+        const int ex = a.hx - a.lx, ey = a.hy - a.ly, ez = a.hz - a.lz;
+        const int exy = ex * ey, n = exy * ez;
+        for (int e = lane; e < n; e += 32) {
+            const int iz = e / exy, r = e - iz * exy;
+            const int iy = r / ex, ix = r - iy * ex;
+            const int la = (a.lz + iz) * a.s2 + (a.ly + iy) * a.s1 + a.lx + ix;
+            const size_t o = ((size_t)(a.cz0 + a.lz + iz) * v.ny + (size_t)(a.cy0 + a.ly + iy)) * v.nx +
+                             (size_t)(a.cx0 + a.lx + ix);
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                const R val = a.acc[k * a.plane + la];
+                if (val != R(0)) {
+                    SPHB_ASSERT(o < v.n_out && la < a.plane);
+                    red_add(outs[k] + o, (double)val);
+                    a.acc[k * a.plane + la] = R(0);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    a.lx = a.ly = a.lz = 1 << 30;
+    a.hx = a.hy = a.hz = 0;
+}
+
+template <typename T, typename R, int KIND, int NW, bool DIM3>
+__global__ void __launch_bounds__(kCellMaxWarps * 32, 1)
+cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
+            const void *__restrict__ lut_global, const uint32_t *__restrict__ cell_start, int64_t cell_lo,
+            int64_t cell_hi, int plane, int lut_bytes, int warp_bytes, double *o0, double *o1, double *o2,
+            double *o3)
+{
+    using R2 = typename Real2<R>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
+    R2 *lut_s = reinterpret_cast<R2 *>(smem_raw);
+    unsigned char *mine = smem_raw + lut_bytes + (size_t)warp * warp_bytes;
+    CellBatch<R, NW> &st = *reinterpret_cast<CellBatch<R, NW> *>(mine);
+    double *outs[4] = {o0, o1, o2, o3};
+
+    LutView<R> lv;
+    lut_set_table(lv, lut_s);
+    lv.gtab = static_cast<const R2 *>(lut_global);
+    lv.scale = R(0);
+    lv.last = 0;
+    if (is_lut<KIND>()) {
+        const double lut_scale = (double)(lut_samples - 1) / v.radius;
+        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += blockDim.x)
+            lut_s[i] = lut_make_entry<R>(lut, lut_samples, i, lut_scale);
+        lv.scale = (R)lut_scale;
+        lv.last = lut_samples - 1;
+        __syncthreads();
+    }
+
+    // this warp's slice of the cell-ordered stream
+    const int64_t p_lo = cell_start[cell_lo], p_hi = cell_start[cell_hi];
+    const int64_t start = p_lo + ((int64_t)blockIdx.x * warps + warp) * kCellChunk;
+    if (start >= p_hi) return;
+    const int64_t end = min(start + (int64_t)kCellChunk, p_hi);
+
+    CellAcc<R> a;
+    a.acc = reinterpret_cast<R *>(mine + sizeof(CellBatch<R, NW>));
+    a.s1 = (1 << v.cx_log) + v.halo;
+    a.s2 = a.s1 * ((1 << v.cy_log) + v.halo);
+    a.plane = plane;
+    a.cell = -1;
+    a.cx0 = a.cy0 = a.cz0 = 0;
+    a.lx = a.ly = a.lz = 1 << 30;
+    a.hx = a.hy = a.hz = 0;
+    for (int i = lane; i < NW * plane; i += 32) a.acc[i] = R(0);
+    __syncwarp();
+
+    const R rad2 = (R)(v.radius * v.radius);
+
+    for (int64_t base = start; base < end; base += 32) {
+        // ---- every lane derives one particle ---------------------------------
+        int vol = 0;
+        {
+            uint32_t dims = 0;
+            if (base + lane < end) {
+                const Rec<T> pr = load_rec<T>(recs, v.rec_stride, base + lane, NW);
+                const double hp = (double)pr.h;
+                const double xp = (double)pr.x, yp = (double)pr.y;
+                const double rad = v.radius * hp;
+                const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
+                int x0, x1, y0, y1, z0 = 0, z1 = 1;
+                pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, x0, x1);
+                pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, y0, y1);
+                const double sx = v.pwx * hinv, sy = v.pwy * hinv;
+                st.sx[lane] = (R)sx;
+                st.sy[lane] = (R)sy;
+                st.ox[lane] = (R)(-((xp - v.x_min) * v.inv_pwx - 0.5 - x0) * sx);
+                st.oy[lane] = (R)(-((yp - v.y_min) * v.inv_pwy - 0.5 - y0) * sy);
+                double cc = 0.0;
+                if (DIM3) {
+                    const double zp = (double)pr.z;
+                    pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, z0, z1);
+                    const double sz = v.pwz * hinv;
+                    st.sz[lane] = (R)sz;
+                    st.oz[lane] = (R)(-((zp - v.z_min) * v.inv_pwz - 0.5 - z0) * sz);
+                } else if (v.use_z) {
+                    const double dz = v.z_slice - (double)pr.z;
+                    cc = dz * dz * hinv2;
+                }
+                st.cq[lane] = (R)cc + sqrt_guard(R(0));
+                const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
+#pragma unroll
+                for (int k = 0; k < NW; k++) st.term[k][lane] = (R)((double)pr.w[k] * scale);
+                st.bx[lane] = x0;
+                st.by[lane] = y0;
+                st.bz[lane] = z0;
+                const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
+                if (wx > 0 && wy > 0 && wz > 0) {
+                    SPHB_ASSERT(wx <= v.halo + 1 && wy <= v.halo + 1 && wz <= v.halo + 1);
+                    dims = (uint32_t)wx | ((uint32_t)wy << 8) | ((uint32_t)wz << 16);
+                    vol = wx * wy * wz;
+                }
+            }
+            st.dims[lane] = dims;
+        }
+        int vmax = vol;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        __syncwarp();
+        if (vmax == 0) continue;
+
+        if (vmax <= kTinyVolume) {
+            // ---- tiny boxes: a sub-group of lanes per particle, straight into the raster -----
+            int lpp_log = 0;
+            while ((1 << lpp_log) < vmax) lpp_log++;
+            const int sub = lane & ((1 << lpp_log) - 1), grp = lane >> lpp_log;
+            for (int g = 0; g < 32; g += 32 >> lpp_log) {
+                const int s = g + grp;
+                const uint32_t dims = st.dims[s];
+                const int wx = (int)(dims & 0xff), wy = (int)((dims >> 8) & 0xff), wz = (int)(dims >> 16);
+                const int wxy = wx * wy;
+                if (sub < wxy * wz) {
+                    // sub < 16: exact small divisions by multiply-shift
+                    const int iz = (int)(((unsigned)sub * (65536u / (unsigned)wxy + 1u)) >> 16), r = sub - iz * wxy;
+                    const int iy = (int)(((unsigned)r * (65536u / (unsigned)wx + 1u)) >> 16), ix = r - iy * wx;
+                    const R dxs = fma((R)ix, st.sx[s], st.ox[s]), dys = fma((R)iy, st.sy[s], st.oy[s]);
+                    R q2 = fma(dys, dys, fma(dxs, dxs, st.cq[s]));
+                    if (DIM3) {
+                        const R dzs = fma((R)iz, st.sz[s], st.oz[s]);
+                        q2 = fma(dzs, dzs, q2);
+                    }
+                    if (q2 < rad2) {
+                        const R wv = kernel_eval_pos<KIND, R>(q2, lv);
+                        const size_t o = ((size_t)(st.bz[s] + iz) * v.ny + (size_t)(st.by[s] + iy)) * v.nx +
+                                         (size_t)(st.bx[s] + ix);
+                        SPHB_ASSERT(o < v.n_out);
+#pragma unroll
+                        for (int k = 0; k < NW; k++) red_add(outs[k] + o, (double)(st.term[k][s] * wv));
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+
+        // ---- one particle per pass, lanes over its box, local accumulator --------------
+        const int nb = (int)min((int64_t)32, end - base);
+        for (int s = 0; s < nb; s++) {
+            const uint32_t dims = st.dims[s];
+            if (!dims) continue;
+            const int wx = (int)(dims & 0xff), wy = (int)((dims >> 8) & 0xff), wz = (int)(dims >> 16);
+            const int bx = st.bx[s], by = st.by[s], bz = st.bz[s];
+            const int cell = (((bz >> v.cz_log) * v.ncy) + (by >> v.cy_log)) * v.ncx + (bx >> v.cx_log);
+            if (cell != a.cell) {
+                cell_flush<R, NW>(a, v, lane, outs);
+                a.cell = cell;
+                a.cx0 = (bx >> v.cx_log) << v.cx_log;
+                a.cy0 = (by >> v.cy_log) << v.cy_log;
+                a.cz0 = (bz >> v.cz_log) << v.cz_log;
+            }
+            const int lx0 = bx - a.cx0, ly0 = by - a.cy0, lz0 = bz - a.cz0;
+            a.lx = min(a.lx, lx0); a.hx = max(a.hx, lx0 + wx);
+            a.ly = min(a.ly, ly0); a.hy = max(a.hy, ly0 + wy);
+            a.lz = min(a.lz, lz0); a.hz = max(a.hz, lz0 + wz);
+            SPHB_ASSERT(lx0 >= 0 && ly0 >= 0 && lz0 >= 0 && lx0 + wx <= a.s1 && (ly0 + wy) * a.s1 <= a.s2 &&
+                        (lz0 + wz) * a.s2 <= a.plane);
+
+            const R sx = st.sx[s], sy = st.sy[s], ox = st.ox[s], oy = st.oy[s], cq = st.cq[s];
+            R sz = R(0), oz = R(0);
+            if (DIM3) {
+                sz = st.sz[s];
+                oz = st.oz[s];
+            }
+            R term[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) term[k] = st.term[k][s];
+
+            // lanes: in-plane pixel a = lane % lpl, z-slice lane / lpl (lpl = power of two >= wx wy,
+            // at most 32; a wider plane is covered in several rounds of 32)
+            const int wxy = wx * wy;
+            const int lpl_log = min(5, 32 - __clz(wxy - 1)); // ceil(log2(wx wy)), 0 for a single pixel
+            const int lpl = 1 << lpl_log, sp = DIM3 ? (32 >> lpl_log) : 1;
+            const int zs = DIM3 ? (lane >> lpl_log) : 0;
+            const unsigned inv_wx = 65536u / (unsigned)wx + 1u;
+            for (int a0 = DIM3 ? (lane & (lpl - 1)) : lane; a0 < wxy; a0 += DIM3 ? lpl : 32) {
+                const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
+                const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
+                const R qxy = fma(dys, dys, fma(dxs, dxs, cq)); // cq carries sqrt_guard()
+                R *ap = a.acc + ((lz0 + zs) * a.s2 + (ly0 + iy) * a.s1 + lx0 + ix);
+                if (DIM3) {
+                    for (int iz = zs; iz < wz; iz += sp) {
+                        const R dzs = fma((R)iz, sz, oz);
+                        const R q2 = fma(dzs, dzs, qxy);
+                        if (q2 < rad2) {
+                            const R wv = kernel_eval_pos<KIND, R>(q2, lv);
+#pragma unroll
+                            for (int k = 0; k < NW; k++) ap[k * a.plane] = fma(term[k], wv, ap[k * a.plane]);
+                        }
+                        ap += sp * a.s2;
+                    }
+                } else if (qxy < rad2) {
+                    const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
+#pragma unroll
+                    for (int k = 0; k < NW; k++) ap[k * a.plane] = fma(term[k], wv, ap[k * a.plane]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    cell_flush<R, NW>(a, v, lane, outs);
+}
+
+// ---------------------------------------------------------------------------
+template <typename T, typename R, int KIND, int NW, bool DIM3>
+static int launch_one(const View &v, const T *recs, const sphb_kernel *k, const void *lut_global,
+                      const uint32_t *cell_start, int64_t n_small, int64_t cell_lo, int64_t cell_hi,
+                      double *const *out, cudaStream_t stream)
+{
+    using R2 = typename Real2<R>::type;
+    auto kern = cell_kernel<T, R, KIND, NW, DIM3>;
+    const int s1 = (1 << v.cx_log) + v.halo, s2 = s1 * ((1 << v.cy_log) + v.halo);
+    const int plane = DIM3 ? s2 * ((1 << v.cz_log) + v.halo) : s2;
+    size_t lut_bytes = 0;
+    if (KIND == SPHB_COLUMN_LUT) lut_bytes = align_up(sizeof(R2) * (size_t)k->lut_samples, 16);
+    const size_t warp_bytes = align_up(sizeof(CellBatch<R, NW>) + sizeof(R) * (size_t)plane * NW, 16);
+    const size_t limit = 227 * 1024;
+    if (lut_bytes + warp_bytes > limit) {
+        set_error("cell accumulator (%zu bytes) and column table (%zu bytes) do not fit in shared memory",
+                  warp_bytes, lut_bytes);
+        return SPHB_ERR_ARGUMENT;
+    }
+    int warps = (int)((limit - lut_bytes) / warp_bytes);
+    warps = warps > kCellMaxWarps ? kCellMaxWarps : warps;
+    SPHB_CUDA(allow_large_smem(kern));
+    const int64_t units = (n_small + kCellChunk - 1) / kCellChunk + 1; // upper bound for any cell range
+    const int grid = div_up(units, warps);
+    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NW; i++) o[i] = out[i];
+    kern<<<grid, warps * 32, lut_bytes + warp_bytes * warps, stream>>>(
+        v, recs, k->lut, k->lut_samples, lut_global, cell_start, cell_lo, cell_hi, plane, (int)lut_bytes,
+        (int)warp_bytes, o[0], o[1], o[2], o[3]);
+    SPHB_LAUNCH_CHECK();
+    return SPHB_OK;
+}
+
+template <typename T, typename R, int KIND, bool DIM3, typename... A> static int cells_nw(int nw, A &&...a)
+{
+    switch (nw) {
+    case 1: return launch_one<T, R, KIND, 1, DIM3>(a...);
+    case 2: return launch_one<T, R, KIND, 2, DIM3>(a...);
+    case 3: return launch_one<T, R, KIND, 3, DIM3>(a...);
+    default: return launch_one<T, R, KIND, 4, DIM3>(a...);
+    }
+}
+
+template <typename T, typename R, bool DIM3, typename... A> static int cells_kind(int kind, int nw, A &&...a)
+{
+    switch (kind) {
+    case SPHB_CUBIC: return cells_nw<T, R, SPHB_CUBIC, DIM3>(nw, a...);
+    case SPHB_QUARTIC: return cells_nw<T, R, SPHB_QUARTIC, DIM3>(nw, a...);
+    case SPHB_QUINTIC: return cells_nw<T, R, SPHB_QUINTIC, DIM3>(nw, a...);
+    case SPHB_COLUMN_LUT: return cells_nw<T, R, SPHB_COLUMN_LUT, DIM3>(nw, a...);
+    default: return cells_nw<T, R, SPHB_COLUMN_LUT_GLOBAL, DIM3>(nw, a...);
+    }
+}
+
+int launch_cells(const View &v, bool f32, int kind, int nw, const void *recs_small, const sphb_kernel *k,
+                 const void *lut_global, const uint32_t *cell_start, int64_t n_small, int64_t cell_lo,
+                 int64_t cell_hi, double *const *out, cudaStream_t stream)
+{
+    if (v.dim3)
+        return f32 ? cells_kind<float, float, true>(kind, nw, v, static_cast<const float *>(recs_small), k, lut_global,
+                                                    cell_start, n_small, cell_lo, cell_hi, out, stream)
+                   : cells_kind<double, double, true>(kind, nw, v, static_cast<const double *>(recs_small), k,
+                                                      lut_global, cell_start, n_small, cell_lo, cell_hi, out, stream);
+    return f32 ? cells_kind<float, float, false>(kind, nw, v, static_cast<const float *>(recs_small), k, lut_global,
+                                                 cell_start, n_small, cell_lo, cell_hi, out, stream)
+               : cells_kind<double, double, false>(kind, nw, v, static_cast<const double *>(recs_small), k, lut_global,
+                                                   cell_start, n_small, cell_lo, cell_hi, out, stream);
+}
+
+} // namespace sphb

@@ -15,6 +15,9 @@ namespace sphb {
 
 void set_error(const char *fmt, ...);
 
+// SM count of the current device (cached per device; sphb_scatter.cu).
+cudaError_t sm_count(int *out);
+
 #define SPHB_CUDA(call)                                                                  \
     do {                                                                                 \
         cudaError_t e_ = (call);                                                         \

@@ -496,7 +496,9 @@ template <typename T, int NW, bool PROJ3D>
 static int launch_exact(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
                         double *const *out, cudaStream_t stream)
 {
-    const int grid = 148 * 32; // grid-stride over the work units
+    int sms = 0;
+    SPHB_CUDA(sm_count(&sms));
+    const int grid = sms * 32; // grid-stride over the work units
     const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) {
@@ -554,6 +556,12 @@ static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d
         (p->dtype != SPHB_F32 && p->dtype != SPHB_F64) || r->nx <= 0 || r->ny <= 0 ||
         !(r->x_max > r->x_min) || !(r->y_max > r->y_min)) {
         set_error("invalid argument to exact render");
+        return SPHB_ERR_ARGUMENT;
+    }
+    // the work items of one particle (edges / faces of its pixel box, at most ~3 per pixel of the
+    // raster) are indexed with 32-bit integers
+    if ((int64_t)(r->nx + 1) * (int64_t)(r->ny + 1) > (1LL << 28)) {
+        set_error("raster of %d x %d pixels is too large for the exact paths (limit 2^28 pixels)", r->nx, r->ny);
         return SPHB_ERR_ARGUMENT;
     }
     for (int i = 0; i < p->n_weights; i++)

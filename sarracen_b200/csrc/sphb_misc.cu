@@ -154,8 +154,8 @@ line_kernel(LineGeom g, const T *__restrict__ x, const T *__restrict__ y, const 
                     q = sqrt((dx * dx + dy * dy) / (sh * sh));
                 }
                 const double wv = kernel_eval_any<KIND>(q, g.radius, lut, g.lut_samples);
-#pragma unroll
                 SPHB_ASSERT(i >= 0 && i < g.pixels);
+#pragma unroll
                 for (int k = 0; k < NW; k++) {
                     if (use_smem)
                         mine[k * g.pixels + i] += st[k] * wv;
@@ -180,12 +180,17 @@ static int launch_line(const LineGeom &g, const sphb_particles *p, const sphb_ke
                        cudaStream_t stream)
 {
     auto kern = line_kernel<T, KIND, NW, DIM3>;
-    const int use_smem = g.pixels <= kLineMaxSmemPixels;
-    const size_t smem = use_smem ? sizeof(double) * kLineWarps * NW * (size_t)g.pixels : 0;
+    // per-warp private lines in shared memory when they fit in the 227 KB a CTA may have (up to 4
+    // weights x 909 pixels); longer lines reduce into global memory directly
+    const size_t want = sizeof(double) * kLineWarps * NW * (size_t)g.pixels;
+    const int use_smem = g.pixels <= kLineMaxSmemPixels && want <= 227 * 1024;
+    const size_t smem = use_smem ? want : 0;
     if (smem > 48 * 1024)
         SPHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    SPHB_CUDA(sm_count(&sms));
     int grid = div_up(p->n, kLineWarps * 32 * 4);
-    grid = grid < 1 ? 1 : grid > 148 * 4 ? 148 * 4 : grid;
+    grid = grid < 1 ? 1 : grid > sms * 4 ? sms * 4 : grid;
     const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) {

@@ -1,4 +1,4 @@
-// Sampled SPH scatter onto pixel / voxel rasters for B200 (sm_100a).
+// Sampled SPH scatter onto pixel / voxel rasters for B200 (sm_100a): binning and host side.
 //
 // Replaces CPUBackend._fast_2d (sarracen/interpolate/cpu_backend.py:226-313)
 // and the per-slice loop of CPUBackend.interpolate_3d_grid (:193-220):
@@ -10,264 +10,272 @@
 // over all pixel centres inside the support -- computed here in a different
 // order and a different decomposition:
 //
-//  1. bin    every particle's support box is classified: boxes of at most
-//            small_edge pixels per axis are listed once (direct path), larger
-//            ones are keyed by every raster tile they cover (count ->
-//            exclusive scan -> emit (tile, particle) pairs); the emit pass also
-//            writes one packed record per particle,
-//  2. sort   cub::DeviceRadixSort on the tile key (only the bits in use),
-//  3. render the sorted pair list is cut into fixed chunks, one CTA per
-//            chunk.  A CTA walks the tile segments of its chunk; per tile it
-//            stages the particles' derived records into shared memory, and
-//            every warp owns an exclusive strip (2-D: rows, 3-D: z-planes) of
-//            the tile, so accumulation needs no atomics: wide footprints go to
-//            per-lane register accumulators on fixed pixels, narrow ones to a
-//            plain load-add-store on the shared-memory tile (render_kernel),
-//  4. flush  a finished tile segment is added to the float64 output with
-//            red.global.add.f64 -- the only global atomics of the tile path,
-//            once per tile segment, coalesced along x,
-//  5. direct the listed small-footprint particles are rendered straight into
-//            the raster, a lane per in-plane pixel, one red.global.add.f64 per
-//            contribution (direct_kernel).
+//  1. count  one streaming pass over x, y, z, h classifies every particle's support box.
+//            Boxes of at most small_edge pixels per axis are SMALL: they are histogrammed by
+//            the cell that holds their box origin.  Larger ones are counted by the raster tiles
+//            they cover.  Nothing per particle is written.
+//  2. emit   a second streaming pass writes one packed record per particle.  Small particles
+//            are placed directly at their final, cell-ordered position (counting sort: scanned
+//            cell histogram + one warp-aggregated atomic per cell and warp; the append
+//            frontiers of all cells stay L2-resident, so DRAM sees full-sector writes).  Large
+//            particles emit one (tile, particle) pair per covered tile into a list claimed
+//            with one atomic per warp -- no per-particle offsets, no scan over the particles.
+//  3. sort   cub::DeviceRadixSort on the tile key of the pairs only (on the bits in use).
+//  4. render large footprints: tile kernel over the sorted pairs (sphb_render.cu);
+//            small footprints: cell kernel over the cell-ordered records (sphb_cell.cu).
+//            Both accumulate locally (registers / shared memory) and touch the raster with
+//            red.global.add.f64 only when a tile segment / cell is finished.
+//
+// A voxel grid can be rendered in z-slab STAGES (sphb_scatter3d_staged): both work lists are
+// z-major, so stage s finishes every plane below its boundary and a caller can start reducing
+// that slab across GPUs while the later stages still render.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstdlib>
-#include <mutex>
-#include <set>
-#include <utility>
+#include <vector>
 
-#include "sphb_common.cuh"
+#include "sphb_scatter.cuh"
 
 namespace sphb {
 
-// CTA shape of the tile render kernel: WARPS warps, one staged particle per thread per round.
-constexpr int kChunkPairs = 2048; // sorted pairs per CTA
-
-// Geometry of one call, shared by every kernel of the pipeline.
-struct View {
-    int nx, ny, nz;
-    int tx, ty, tz;    // tile size in pixels (powers of two)
-    int tx_log, ty_log, tz_log;
-    int ntx, nty, ntz; // tiles per axis
-    double x_min, y_min, z_min;
-    double inv_pwx, inv_pwy, inv_pwz;
-    double pwx, pwy, pwz;
-    double radius;
-    double z_slice;
-    int use_z; // 2-D raster, particles carry a depth (cross-section)
-    int dim3;  // voxel raster
-    int ndim;  // exponent of h in the particle term
-    double norm;
-    int rec_stride;    // elements per packed particle record (4 or 8)
-    int small_shift;   // direct-path sort key = tile id >> small_shift (coarse buckets when nothing is tiled)
-    unsigned long long n_out;   // raster elements per weight (debug index checks)
-    int small_edge;    // footprint boxes with every edge <= this many pixels take the direct path
-    uint32_t flag_bit; // key bit that marks a direct-path particle (sorts after all tile pairs)
+struct Box {
+    int x0, x1, y0, y1, z0, z1; // pixel ranges [lo, hi)
 };
 
-// Packed particle record, written once per call by the emit kernel (which streams the
-// columns anyway) so that the render kernels fetch one particle with one or two 16-byte
-// loads from a single place instead of one 8-byte gather per column -- every random gather
-// costs a full DRAM burst, and the sorted lists visit particles in random order.
-//   stride 4 elements: { x, y, h, w0 }                    (no depth column, one weight)
-//   stride 6 elements: { x, y, h, z, w0, w1 }             (double only, up to two weights)
-//   stride 8 elements: { x, y, h, z, w0, w1, w2, w3 }
-template <typename T> struct Rec {
-    T x, y, h, z, w[4];
-};
-
+// Support box of particle i in raster pixels; false if it touches no pixel (or is degenerate:
+// h <= 0 or non-finite input -- such particles contribute nothing).
 template <typename T>
-__device__ __forceinline__ Rec<T> load_rec(const T *__restrict__ recs, int stride, int64_t p, int nw)
+__device__ __forceinline__ bool particle_box(const View &v, const T *x, const T *y, const T *z, const T *h,
+                                             int64_t i, Box &b)
 {
-    Rec<T> r;
-    const T *b = recs + (size_t)p * stride;
-    if (sizeof(T) == 8) {
-        const double2 a = __ldg(reinterpret_cast<const double2 *>(b));
-        const double2 c = __ldg(reinterpret_cast<const double2 *>(b) + 1);
-        r.x = (T)a.x; r.y = (T)a.y; r.h = (T)c.x;
-        if (stride == 4) {
-            r.z = T(0); r.w[0] = (T)c.y;
-        } else {
-            r.z = (T)c.y;
-            const double2 d = __ldg(reinterpret_cast<const double2 *>(b) + 2);
-            r.w[0] = (T)d.x; r.w[1] = (T)d.y;
-            if (stride == 8 && nw > 2) {
-                const double2 e = __ldg(reinterpret_cast<const double2 *>(b) + 3);
-                r.w[2] = (T)e.x; r.w[3] = (T)e.y;
-            }
-        }
-    } else {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(b));
-        r.x = (T)a.x; r.y = (T)a.y; r.h = (T)a.z;
-        if (stride == 4) {
-            r.z = T(0); r.w[0] = (T)a.w;
-        } else {
-            r.z = (T)a.w;
-            const float4 d = __ldg(reinterpret_cast<const float4 *>(b) + 1);
-            r.w[0] = (T)d.x; r.w[1] = (T)d.y; r.w[2] = (T)d.z; r.w[3] = (T)d.w;
-        }
+    const double hp = (double)__ldg(h + i);
+    const double xp = (double)__ldg(x + i), yp = (double)__ldg(y + i);
+    if (!(hp > 0.0) || !isfinite(hp) || !isfinite(xp) || !isfinite(yp)) return false;
+    const double rad = v.radius * hp;
+    b.z0 = 0;
+    b.z1 = 1;
+    if (v.dim3) {
+        const double zp = (double)__ldg(z + i);
+        if (!isfinite(zp)) return false;
+        pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, b.z0, b.z1);
+        if (b.z1 <= b.z0) return false;
+    } else if (v.use_z) {
+        const double dz = v.z_slice - (double)__ldg(z + i);
+        if (!(fabs(dz) < rad)) return false; // cpu_backend.py:264
     }
-    return r;
+    pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, b.x0, b.x1);
+    if (b.x1 <= b.x0) return false;
+    pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, b.y0, b.y1);
+    return b.y1 > b.y0;
+}
+
+__device__ __forceinline__ int box_edge(const Box &b)
+{
+    return max(max(b.x1 - b.x0, b.y1 - b.y0), b.z1 - b.z0);
+}
+
+__device__ __forceinline__ uint32_t box_cell(const View &v, const Box &b)
+{
+    return (uint32_t)((((b.z0 >> v.cz_log) * v.ncy) + (b.y0 >> v.cy_log)) * v.ncx + (b.x0 >> v.cx_log));
 }
 
 struct TileBox {
     int x0, x1, y0, y1, z0, z1; // tile index ranges, inclusive
 };
 
-__device__ __forceinline__ int clamp_to_int(double v, int lo, int hi)
+__device__ __forceinline__ TileBox box_tiles(const View &v, const Box &b)
 {
-    // also maps NaN to lo
-    return (int)fmin(fmax(v, (double)lo), (double)hi);
+    TileBox t;
+    t.x0 = b.x0 >> v.tx_log;
+    t.x1 = (b.x1 - 1) >> v.tx_log;
+    t.y0 = b.y0 >> v.ty_log;
+    t.y1 = (b.y1 - 1) >> v.ty_log;
+    t.z0 = b.z0 >> v.tz_log;
+    t.z1 = (b.z1 - 1) >> v.tz_log;
+    return t;
 }
 
-// Pixel box [lo, hi) that holds every pixel centre within rad of c.
-__device__ __forceinline__ void pixel_range(double c, double rad, double origin, double inv_pw, int n,
-                                            int &lo, int &hi)
+__device__ __forceinline__ uint32_t tile_count(const TileBox &t)
 {
-    // centre of pixel i sits at origin + (i + 1/2) pw
-    lo = clamp_to_int(ceil((c - rad - origin) * inv_pw - 0.5), 0, n);
-    hi = clamp_to_int(floor((c + rad - origin) * inv_pw - 0.5) + 1.0, 0, n);
+    return (uint32_t)(t.x1 - t.x0 + 1) * (uint32_t)(t.y1 - t.y0 + 1) * (uint32_t)(t.z1 - t.z0 + 1);
 }
 
-// Tiles covered by a particle's support box; false if it touches no pixel.
-// `small` is set when the whole box is at most small_edge pixels along every
-// axis: such a particle is not binned per tile but listed once (under the tile
-// of its box origin) for the direct path.
-template <typename T>
-__device__ __forceinline__ bool particle_tiles(const View &v, const T *x, const T *y, const T *z,
-                                               const T *h, int64_t i, TileBox &b, bool &small)
-{
-    double hp = (double)__ldg(h + i);
-    double xp = (double)__ldg(x + i), yp = (double)__ldg(y + i);
-    if (!(hp > 0.0) || !isfinite(hp) || !isfinite(xp) || !isfinite(yp)) return false;
-    double rad = v.radius * hp;
-    int lo, hi, edge = 0;
-    b.z0 = b.z1 = 0;
-    if (v.dim3) {
-        double zp = (double)__ldg(z + i);
-        if (!isfinite(zp)) return false;
-        pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, lo, hi);
-        if (hi <= lo) return false;
-        b.z0 = lo >> v.tz_log;
-        b.z1 = (hi - 1) >> v.tz_log;
-        edge = hi - lo;
-    } else if (v.use_z) {
-        double dz = v.z_slice - (double)__ldg(z + i);
-        if (!(fabs(dz) < rad)) return false; // cpu_backend.py:264
-    }
-    pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, lo, hi);
-    if (hi <= lo) return false;
-    b.x0 = lo >> v.tx_log;
-    b.x1 = (hi - 1) >> v.tx_log;
-    edge = max(edge, hi - lo);
-    pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, lo, hi);
-    if (hi <= lo) return false;
-    b.y0 = lo >> v.ty_log;
-    b.y1 = (hi - 1) >> v.ty_log;
-    edge = max(edge, hi - lo);
-    small = edge <= v.small_edge;
-    return true;
-}
+// totals[0] small particles, [1] (tile, particle) pairs, [2] largest small box edge,
+// [3] cursor of the pair list (emit), [4] large particles
+enum { kTotSmall = 0, kTotPairs = 1, kTotEdge = 2, kTotCursor = 3, kTotLarge = 4, kTotCount = 8 };
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-count_tiles_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint32_t *counts,
-                   unsigned long long *totals)
+count_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, uint32_t *cell_count,
+             unsigned long long *totals)
 {
-    // Grid-stride over the particles; the two totals -- direct-path particles (totals[0]) and list
-    // entries (totals[1], 64-bit: the 32-bit per-particle counts are scanned in 32 bits, which is
-    // only valid once the host has seen that the total is below 2^31) -- reach global memory as
-    // one atomic each per CTA of a few-hundred-CTA grid.
-    unsigned mine_small = 0;
-    unsigned long long mine_all = 0;
+    unsigned mine_small = 0, mine_large = 0, mine_edge = 0;
+    unsigned long long mine_pairs = 0;
+    const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
-        TileBox b;
-        uint32_t c = 0; // counts[n] = 0 so that the exclusive scan leaves the total there
-        bool small = false;
-        if (i < n && particle_tiles(v, x, y, z, h, i, b, small))
-            c = small ? 1u
-                      : (uint32_t)(b.x1 - b.x0 + 1) * (uint32_t)(b.y1 - b.y0 + 1) * (uint32_t)(b.z1 - b.z0 + 1);
-        counts[i] = c; // fits: the raster has fewer than 2^30 tiles
-        mine_small += (small && c) ? 1u : 0u;
-        mine_all += c;
+    const int64_t n_up = (n + 31) / 32 * 32; // whole warps stay in the loop (match_any below)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += stride) {
+        Box b;
+        const bool seen = i < n && particle_box(v, x, y, z, h, i, b);
+        const int edge = seen ? box_edge(b) : 0;
+        const bool small = seen && edge <= v.small_edge;
+        // histogram of the small particles by cell, one atomic per distinct cell and warp
+        const uint32_t key = small ? box_cell(v, b) : (0x80000000u | (uint32_t)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (small) {
+            if (lane == __ffs(peers) - 1) atomicAdd(cell_count + key, (uint32_t)__popc(peers));
+            mine_small++;
+            mine_edge = max(mine_edge, (unsigned)edge);
+        } else if (seen) {
+            mine_pairs += tile_count(box_tiles(v, b));
+            mine_large++;
+        }
     }
-    __shared__ unsigned long long block_small, block_all;
-    if (threadIdx.x == 0) block_small = block_all = 0;
+    __shared__ unsigned long long block_tot[kTotCount];
+    if (threadIdx.x < kTotCount) block_tot[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mine_small += __shfl_xor_sync(0xffffffffu, mine_small, o);
-        mine_all += __shfl_xor_sync(0xffffffffu, mine_all, o);
+        mine_large += __shfl_xor_sync(0xffffffffu, mine_large, o);
+        mine_pairs += __shfl_xor_sync(0xffffffffu, mine_pairs, o);
+        mine_edge = max(mine_edge, __shfl_xor_sync(0xffffffffu, mine_edge, o));
     }
-    if ((threadIdx.x & 31) == 0 && mine_all) {
-        atomicAdd(&block_small, (unsigned long long)mine_small);
-        atomicAdd(&block_all, mine_all);
+    if (lane == 0 && (mine_small | mine_large)) {
+        atomicAdd(&block_tot[kTotSmall], (unsigned long long)mine_small);
+        atomicAdd(&block_tot[kTotLarge], (unsigned long long)mine_large);
+        atomicAdd(&block_tot[kTotPairs], mine_pairs);
+        atomicMax(&block_tot[kTotEdge], (unsigned long long)mine_edge);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && block_all) {
-        if (block_small) atomicAdd(totals, block_small);
-        atomicAdd(totals + 1, block_all);
+    if (threadIdx.x == 0 && (block_tot[kTotSmall] | block_tot[kTotLarge])) {
+        if (block_tot[kTotSmall]) {
+            atomicAdd(totals + kTotSmall, block_tot[kTotSmall]);
+            atomicMax(totals + kTotEdge, block_tot[kTotEdge]);
+        }
+        if (block_tot[kTotLarge]) {
+            atomicAdd(totals + kTotLarge, block_tot[kTotLarge]);
+            atomicAdd(totals + kTotPairs, block_tot[kTotPairs]);
+        }
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
-emit_pairs_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0, const T *w1,
-                  const T *w2, const T *w3, int nw, int64_t n, const uint32_t *offsets, uint32_t *keys,
-                  uint32_t *vals, T *recs)
+__device__ __forceinline__ void write_rec(const View &v, T *r, const T *x, const T *y, const T *z, const T *h,
+                                          const T *w0, const T *w1, const T *w2, const T *w3, int nw, int64_t i)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    TileBox b;
-    bool small;
-    if (!particle_tiles(v, x, y, z, h, i, b, small)) return;
-    {
-        // packed record, written as 16-byte vectors (a scalar store per field touched every
-        // 32-byte sector of the record array 4-8 times)
-        T f[8] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
-        f[0] = x[i];
-        f[1] = y[i];
-        f[2] = h[i];
-        if (v.rec_stride == 4) {
-            f[3] = w0[i];
-        } else {
-            f[3] = z ? z[i] : T(0);
-            f[4] = w0[i];
-            f[5] = nw > 1 ? w1[i] : T(0);
-            f[6] = (v.rec_stride == 8 && nw > 2) ? w2[i] : T(0);
-            f[7] = (v.rec_stride == 8 && nw > 3) ? w3[i] : T(0);
-        }
-        T *r = recs + (size_t)i * v.rec_stride;
-        if (sizeof(T) == 8) {
-            double2 *q = reinterpret_cast<double2 *>(r);
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (2 * k < v.rec_stride) q[k] = make_double2((double)f[2 * k], (double)f[2 * k + 1]);
-        } else {
-            float4 *q = reinterpret_cast<float4 *>(r);
-#pragma unroll
-            for (int k = 0; k < 2; k++)
-                if (4 * k < v.rec_stride)
-                    q[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
-        }
+    // packed record, written as 16-byte vectors (a scalar store per field touched every
+    // 32-byte sector of the record array 4-8 times)
+    T f[8] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+    f[0] = x[i];
+    f[1] = y[i];
+    f[2] = h[i];
+    if (v.rec_stride == 4) {
+        f[3] = w0[i];
+    } else {
+        f[3] = z ? z[i] : T(0);
+        f[4] = w0[i];
+        f[5] = nw > 1 ? w1[i] : T(0);
+        f[6] = (v.rec_stride == 8 && nw > 2) ? w2[i] : T(0);
+        f[7] = (v.rec_stride == 8 && nw > 3) ? w3[i] : T(0);
     }
-    uint64_t o = offsets[i];
-    SPHB_ASSERT(o < offsets[n]);
+    if (sizeof(T) == 8) {
+        double2 *q = reinterpret_cast<double2 *>(r);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (2 * k < v.rec_stride) q[k] = make_double2((double)f[2 * k], (double)f[2 * k + 1]);
+    } else {
+        float4 *q = reinterpret_cast<float4 *>(r);
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (4 * k < v.rec_stride)
+                q[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
+    }
+}
+
+// Pairs of one particle are written by its own lane up to this many; a particle that covers
+// more tiles (h >> tile: up to every tile of the raster) is written by the whole warp.
+constexpr uint32_t kOwnPairs = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0, const T *w1, const T *w2,
+            const T *w3, int nw, int64_t n, const uint32_t *cell_start, uint32_t *cell_cursor,
+            unsigned long long *totals, uint32_t *keys, uint32_t *vals, T *recs_large, T *recs_small,
+            int64_t n_pairs, int64_t n_small)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // whole warps: n is rounded up by the grid
+    Box b;
+    const bool seen = i < n && particle_box(v, x, y, z, h, i, b);
+    const bool small = seen && box_edge(b) <= v.small_edge;
+
+    // ---- small: final position in the cell-ordered record stream ------------------------
+    const uint32_t key = small ? box_cell(v, b) : (0x80000000u | (uint32_t)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    uint32_t slot = 0;
+    const int leader = __ffs(peers) - 1;
+    if (small && lane == leader) slot = atomicAdd(cell_cursor + key, (uint32_t)__popc(peers));
+    slot = __shfl_sync(0xffffffffu, slot, leader);
     if (small) {
-        keys[o] = ((uint32_t)((b.z0 * v.nty + b.y0) * v.ntx + b.x0) >> v.small_shift) | v.flag_bit;
-        vals[o] = (uint32_t)i;
-        return;
+        const int64_t pos = (int64_t)__ldg(cell_start + key) + slot + __popc(peers & ((1u << lane) - 1u));
+        SPHB_ASSERT(pos < n_small);
+        write_rec<T>(v, recs_small + (size_t)pos * v.rec_stride, x, y, z, h, w0, w1, w2, w3, nw, i);
     }
-    for (int tz = b.z0; tz <= b.z1; tz++)
-        for (int ty = b.y0; ty <= b.y1; ty++)
-            for (int tx = b.x0; tx <= b.x1; tx++) {
-                SPHB_ASSERT(o < offsets[n] && tx < v.ntx && ty < v.nty && tz < v.ntz);
-                keys[o] = (uint32_t)((tz * v.nty + ty) * v.ntx + tx);
-                vals[o] = (uint32_t)i;
-                o++;
-            }
+
+    // ---- large: (tile, particle) pairs ----------------------------------------------------
+    const bool large = seen && !small;
+    TileBox t = {0, 0, 0, 0, 0, 0};
+    uint32_t c = 0;
+    if (large) {
+        t = box_tiles(v, b);
+        c = tile_count(t);
+        write_rec<T>(v, recs_large + (size_t)i * v.rec_stride, x, y, z, h, w0, w1, w2, w3, nw, i);
+    }
+    if (!__any_sync(0xffffffffu, large)) return;
+    // the warp claims one range of the list: exclusive scan of the counts + one atomic
+    unsigned long long incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(totals + kTotCursor, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const uint64_t o0 = base + incl - c;
+    if (large && c <= kOwnPairs) {
+        uint64_t o = o0;
+        for (int tz = t.z0; tz <= t.z1; tz++)
+            for (int ty = t.y0; ty <= t.y1; ty++)
+                for (int tx = t.x0; tx <= t.x1; tx++) {
+                    SPHB_ASSERT((int64_t)o < n_pairs && tx < v.ntx && ty < v.nty && tz < v.ntz);
+                    keys[o] = (uint32_t)((tz * v.nty + ty) * v.ntx + tx);
+                    vals[o] = (uint32_t)i;
+                    o++;
+                }
+    }
+    unsigned wide = __ballot_sync(0xffffffffu, large && c > kOwnPairs);
+    while (wide) {
+        const int src = __ffs(wide) - 1;
+        wide &= wide - 1;
+        const uint64_t ob = __shfl_sync(0xffffffffu, o0, src);
+        const uint32_t cc = __shfl_sync(0xffffffffu, c, src);
+        const int tx0 = __shfl_sync(0xffffffffu, t.x0, src), ty0 = __shfl_sync(0xffffffffu, t.y0, src);
+        const int tz0 = __shfl_sync(0xffffffffu, t.z0, src);
+        const int nx_ = __shfl_sync(0xffffffffu, t.x1, src) - tx0 + 1;
+        const int ny_ = __shfl_sync(0xffffffffu, t.y1, src) - ty0 + 1;
+        const uint32_t pid = (uint32_t)__shfl_sync(0xffffffffu, (unsigned long long)i, src);
+        for (uint32_t e = lane; e < cc; e += 32) {
+            const uint32_t tz = e / (uint32_t)(nx_ * ny_), r = e - tz * (uint32_t)(nx_ * ny_);
+            const uint32_t ty = r / (uint32_t)nx_, tx = r - ty * (uint32_t)nx_;
+            SPHB_ASSERT((int64_t)(ob + e) < n_pairs);
+            keys[ob + e] = (uint32_t)(((tz0 + tz) * v.nty + (ty0 + ty)) * v.ntx + (tx0 + tx));
+            vals[ob + e] = pid;
+        }
+    }
 }
 
 __global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t *tile_end)
@@ -277,10 +285,20 @@ __global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t 
     if (i == n_pairs - 1 || keys[i] != keys[i + 1]) tile_end[keys[i]] = (uint32_t)(i + 1);
 }
 
-// Column tables of up to kLutSharedMax samples are staged in shared memory by every CTA; larger
-// ones (integral_samples is a user argument, base_kernel.py:68) are expanded once per call into
-// segment lines (A_i, B_i) (sphb_common.cuh, lut_index) in the workspace and read through L1/L2.
-constexpr int kLutSharedMax = 2048;
+// bounds[s] = first sorted pair whose tile id is >= first_tile[s] (s = 0 .. n_bounds-1)
+__global__ void stage_bounds_kernel(const uint32_t *keys, int64_t n_pairs, const uint32_t *first_tile, int n_bounds,
+                                    uint32_t *bounds)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_bounds) return;
+    const uint32_t want = first_tile[s];
+    int64_t lo = 0, hi = n_pairs;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    bounds[s] = (uint32_t)lo;
+}
 
 template <typename R>
 __global__ void lut_pairs_kernel(const double *lut, int samples, double scale, typename Real2<R>::type *out)
@@ -291,559 +309,9 @@ __global__ void lut_pairs_kernel(const double *lut, int samples, double scale, t
 }
 
 // ---------------------------------------------------------------------------
-// Render.
-
-// Staged particle record, tile-local.  Coordinates are in pixel units with the
-// tile origin subtracted; in float mode the centre is split into the nearest
-// pixel (ic) and a fraction in [-1/2, 1/2] so that position differences keep
-// full float precision however large the raster is.
-template <typename R, int NW, int BATCH, bool DIM3> struct Staged {
-    using R2 = typename Real2<R>::type;
-    // read one per lane when a warp scans the batch for its strip: the box along the split axis
-    // (rows in 2-D, z-planes in 3-D), lo | hi << 16 -- kept as its own array so that the scan is
-    // conflict-free
-    uint32_t key[BATCH];
-    // the rest is read by whole warps (broadcast) when a particle hits: packed so that a hit costs
-    // 4 (2-D) or 6 (3-D) 16-byte loads instead of 10-14 scalar ones
-    int4 ibox[BATCH];            // bx, by (lo | hi << 16), cx, cy (nearest pixel in float mode, else 0)
-    int4 ibox3[DIM3 ? BATCH : 1]; // bz, cz, -, -   (3-D only)
-    R2 fxy[BATCH];               // centre (double mode) / fraction (float mode), tile-local pixel units
-    R2 sxy[BATCH];               // (pixel width / h)^2
-    R2 fsz[DIM3 ? BATCH : 1];    // fz, sz         (3-D only)
-    R2 ct[(NW + 2) / 2][BATCH];  // c (dz^2/h^2 of a cross-section), term[0] | term[1], term[2] | term[3], -
-};
-
-template <typename R> struct Split;
-template <> struct Split<double> {
-    static __device__ __forceinline__ void apply(double u, double &f, int &ic)
-    {
-        f = u;
-        ic = 0;
-    }
-};
-template <> struct Split<float> {
-    static __device__ __forceinline__ void apply(double u, float &f, int &ic)
-    {
-        double r = rint(u);
-        r = fmin(fmax(r, -2097152.0), 2097152.0);
-        ic = (int)r;
-        f = (float)(u - r);
-    }
-};
-
-// Tile render.  Work split inside a CTA of kWarps warps:
-//   2-D tile TX x TY pixels: warp w owns the strip of rows [w TY/8, (w+1) TY/8);
-//   3-D tile TX x TY x TZ voxels with TZ == kWarps: warp w owns z-plane w.
-// Ownership is exclusive, so accumulation needs no atomics.  Per (warp,
-// particle) hit there are two code paths:
-//   wide   (footprint box wider than TX/2 inside the tile): lanes sit on fixed
-//          pixels of the warp's box -- column lane % TX, rows lane / TX + k RI --
-//          and accumulate in REGISTERS (K values per lane and weight);
-//   narrow lanes are laid over the footprint box as LW x (32 / LW) pixels, LW the
-//          power of two >= box width, and accumulate into the warp's part of the
-//          shared-memory tile (plain load / fma / store).
-// Registers and shared memory are merged when the tile segment is flushed.
-// Particles staged per round: one per thread.
-template <typename R, bool DIM3, int WARPS> struct RenderBatch {
-    static constexpr int value = WARPS * 32;
-};
-
-// Row padding of the shared-memory tile.  2-D (32 pixels per row): 4 elements, so that consecutive
-// rows start 8 banks apart in double -- as good for the narrow path's few-rows-by-few-columns
-// accesses as the former 8, and what lets two CTAs of the two-weight double kernel (2 x 36.9 KB of
-// tile each) share an SM.
-template <bool DIM3> struct RowPad {
-    static constexpr int value = DIM3 ? 8 : 4;
-};
-
-template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (DIM3 || NW > 2 || (NW > 1 && sizeof(R) == 8)) ? 2 : 3)
-render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
-              const void *__restrict__ lut_global, const uint32_t *__restrict__ keys,
-              const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_end, int64_t n_pairs,
-              double *o0, double *o1, double *o2, double *o3)
-{
-    using R2 = typename Real2<R>::type;
-    constexpr int kWarps = WARPS, kThreads = WARPS * 32, kBatch = RenderBatch<R, DIM3, WARPS>::value;
-    constexpr int SX = TX + RowPad<DIM3>::value;  // padded row stride
-    constexpr int PLANE = SX * TY;                // elements per z-plane
-    constexpr int ACC = PLANE * TZ;               // elements per weight
-    constexpr int ROWS = DIM3 ? TY : TY / kWarps; // rows of the warp's box
-    constexpr int RI = 32 / TX;                   // rows one warp iteration covers in the wide path
-    constexpr int K = ROWS / RI;                  // register accumulators per lane and weight
-    static_assert(!DIM3 || TZ == kWarps, "one z-plane per warp");
-    static_assert(DIM3 || TY % kWarps == 0, "strip split");
-    static_assert(32 % TX == 0 && ROWS % RI == 0, "lane layout");
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    R *acc = reinterpret_cast<R *>(smem_raw);
-    Staged<R, NW, kBatch, DIM3> *st = reinterpret_cast<Staged<R, NW, kBatch, DIM3> *>(acc + (size_t)ACC * NW);
-    R2 *lut_s = reinterpret_cast<R2 *>(st + 1);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *outs[4] = {o0, o1, o2, o3};
-
-    // Column table in shared memory as segment lines (A_i, B_i), see lut_index().  (Replicating it so that every
-    // lane of an access phase owns a bank group was measured on config 2: 1, 2, 4, 8 copies ->
-    // 124, 127, 145, 216 ms, every doubling costs a resident CTA; the random index is not the
-    // bottleneck.)
-    LutView<R> lv;
-    lut_set_table(lv, lut_s);
-    lv.gtab = static_cast<const R2 *>(lut_global);
-    lv.scale = R(0);
-    lv.last = 0;
-    if (is_lut<KIND>()) {
-        const double lut_scale = (double)(lut_samples - 1) / v.radius;
-        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kThreads)
-            lut_s[i] = lut_make_entry<R>(lut, lut_samples, i, lut_scale);
-        lv.scale = (R)lut_scale;
-        lv.last = lut_samples - 1;
-    }
-    for (int i = tid; i < ACC * NW; i += kThreads) acc[i] = R(0);
-    __syncthreads();
-
-    const R rad2 = (R)(v.radius * v.radius);
-    // the warp's box inside the tile
-    const int own_y0 = DIM3 ? 0 : warp * ROWS;
-    const int own_lo = DIM3 ? warp : own_y0, own_hi = DIM3 ? warp + 1 : own_y0 + ROWS;
-    R *const my_acc = acc + (DIM3 ? warp * PLANE : 0);
-    // wide-path lane position
-    const int lx = lane % TX, ly = lane / TX;
-
-    R racc[NW][K];
-#pragma unroll
-    for (int k = 0; k < NW; k++)
-#pragma unroll
-        for (int r = 0; r < K; r++) racc[k][r] = R(0);
-
-    const int64_t chunk_lo = (int64_t)blockIdx.x * kChunkPairs;
-    const int64_t chunk_hi = min(chunk_lo + (int64_t)kChunkPairs, n_pairs);
-    int64_t pos = chunk_lo;
-
-    while (pos < chunk_hi) {
-        const uint32_t tile = keys[pos];
-        SPHB_ASSERT(tile < (uint32_t)(v.ntx * v.nty * v.ntz) && (int64_t)tile_end[tile] > pos);
-        const int64_t seg_hi = min((int64_t)tile_end[tile], chunk_hi);
-        const int ttx = tile % v.ntx, tty = (tile / v.ntx) % v.nty, ttz = tile / (v.ntx * v.nty);
-        const int ox = ttx * TX, oy = tty * TY, oz = ttz * TZ; // tile origin in pixels
-        const int lim_x = min(TX, v.nx - ox), lim_y = min(TY, v.ny - oy), lim_z = min(TZ, v.nz - oz);
-
-        for (int64_t base = pos; base < seg_hi; base += kBatch) {
-            const int nb = (int)min((int64_t)kBatch, seg_hi - base);
-            // ---- stage: one particle per thread --------------------------------
-            if (tid < nb) {
-                const int64_t p = vals[base + tid];
-                const Rec<T> pr = load_rec<T>(recs, v.rec_stride, p, NW);
-                const double hp = (double)pr.h;
-                const double xp = (double)pr.x, yp = (double)pr.y;
-                const double rad = v.radius * hp;
-                const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
-                int lo, hi;
-                // pixel-unit coordinate in which pixel i has its centre at i
-                const double ux = (xp - v.x_min) * v.inv_pwx - 0.5 - ox;
-                const double uy = (yp - v.y_min) * v.inv_pwy - 0.5 - oy;
-                pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, lo, hi);
-                lo = max(lo - ox, 0);
-                hi = min(hi - ox, lim_x);
-                const uint32_t bx = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
-                pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, lo, hi);
-                lo = max(lo - oy, 0);
-                hi = min(hi - oy, lim_y);
-                const uint32_t by = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
-                R2 f, sc;
-                int cx, cy;
-                Split<R>::apply(ux, f.x, cx);
-                Split<R>::apply(uy, f.y, cy);
-                sc.x = (R)(v.pwx * hinv); // pixel -> q along x and y
-                sc.y = (R)(v.pwy * hinv);
-                st->ibox[tid] = make_int4((int)bx, (int)by, cx, cy);
-                st->fxy[tid] = f;
-                st->sxy[tid] = sc;
-                uint32_t key = by;
-                double cc = 0.0;
-                if (DIM3) {
-                    const double zp = (double)pr.z;
-                    const double uz = (zp - v.z_min) * v.inv_pwz - 0.5 - oz;
-                    pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, lo, hi);
-                    lo = max(lo - oz, 0);
-                    hi = min(hi - oz, lim_z);
-                    key = (uint32_t)lo | ((uint32_t)max(hi, lo) << 16);
-                    R2 fz;
-                    int cz;
-                    Split<R>::apply(uz, fz.x, cz);
-                    fz.y = (R)(v.pwz * v.pwz * hinv2);
-                    st->fsz[tid] = fz;
-                    st->ibox3[tid] = make_int4((int)key, cz, 0, 0);
-                } else if (v.use_z) {
-                    const double dz = v.z_slice - (double)pr.z;
-                    cc = dz * dz * hinv2;
-                }
-                SPHB_ASSERT(tid < kBatch && p >= 0);
-                st->key[tid] = key;
-                const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
-                R tv[4] = {R(0), R(0), R(0), R(0)};
-#pragma unroll
-                for (int k = 0; k < NW; k++) tv[k] = (R)((double)pr.w[k] * scale);
-                R2 e0;
-                e0.x = (R)cc + sqrt_guard(R(0)); // every q^2 built on it is > 0 (sqrt_pos)
-                e0.y = tv[0];
-                st->ct[0][tid] = e0;
-                if (NW > 1) {
-                    R2 e1;
-                    e1.x = tv[1];
-                    e1.y = tv[2];
-                    st->ct[1][tid] = e1;
-                }
-                if (NW > 3) {
-                    R2 e2;
-                    e2.x = tv[3];
-                    e2.y = R(0);
-                    st->ct[2][tid] = e2;
-                }
-            }
-            __syncthreads();
-
-            // ---- accumulate: each warp scans the batch for its box --------------
-            for (int g = 0; g < nb; g += 32) {
-                const int me = g + lane;
-                bool hit = false;
-                if (me < nb) {
-                    const uint32_t b = st->key[me];
-                    const int lo = (int)(b & 0xffff), hi = (int)(b >> 16);
-                    hit = max(lo, own_lo) < min(hi, own_hi);
-                }
-                unsigned mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int s = g + __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int4 ib = st->ibox[s];
-                    const uint32_t bx = (uint32_t)ib.x, by = (uint32_t)ib.y;
-                    const int x0 = (int)(bx & 0xffff), x1 = (int)(bx >> 16);
-                    const int y0 = max((int)(by & 0xffff), own_y0), y1 = min((int)(by >> 16), own_y0 + ROWS);
-                    const int wx = x1 - x0;
-                    if (wx <= 0 || y1 <= y0) continue;
-                    const R2 f = st->fxy[s], sc = st->sxy[s], e0 = st->ct[0][s];
-                    const R fx = f.x, fy = f.y, sx = sc.x, sy = sc.y;
-                    // double mode stages whole coordinates (Split<double>: nearest pixel 0): keeping that
-                    // a compile-time fact makes the lane's own pixel coordinate loop-invariant
-                    const int cx = sizeof(R) == 8 ? 0 : ib.z, cy = sizeof(R) == 8 ? 0 : ib.w;
-                    R cc = e0.x;
-                    if (DIM3) {
-                        const R2 fz = st->fsz[s];
-                        const R dz = int_to_real(warp - st->ibox3[s].y, R(0)) - fz.x;
-                        cc = fma(dz * dz, fz.y, sqrt_guard(R(0)));
-                    }
-                    R term[NW];
-                    term[0] = e0.y;
-                    if (NW > 1) {
-                        const R2 e1 = st->ct[1][s];
-                        term[1] = e1.x;
-                        if (NW > 2) term[2] = e1.y;
-                    }
-                    if (NW > 3) term[3] = st->ct[2][s].x;
-
-                    // wide when the box spans more than half the tile width (a quarter in float mode,
-                    // where idle lanes are cheaper than the narrow path's shared-memory updates:
-                    // 65.5 -> 63.0 ms on config 2; no gain in double)
-                    if (wx > TX / (sizeof(R) == 4 ? 4 : 2)) {
-                        // ---- wide: fixed pixels, register accumulators -------------
-                        // Every lane evaluates its own pixels: a pixel outside the
-                        // footprint box has q >= R and W(q) = 0 there (the table is
-                        // clamped to its zero last entry, the analytic shapes are
-                        // selected to 0), so no box tests are needed.  Rows are handled G at
-                        // a time without branches so the G dependent square-root /
-                        // table chains overlap; groups that cannot contribute are skipped.
-                        const R dx = (int_to_real(lx - cx, R(0)) - fx) * sx;
-                        const R qx = fma(dx, dx, cc); // cc carries sqrt_guard()
-                        const R dy0 = (int_to_real(own_y0 + ly - cy, R(0)) - fy) * sy;
-                        constexpr int G = K % 4 == 0 ? 4 : (K % 2 == 0 ? 2 : 1);
-#pragma unroll
-                        for (int r0 = 0; r0 < K; r0 += G) {
-                            R q[G];
-                            bool any = false;
-#pragma unroll
-                            for (int j = 0; j < G; j++) {
-                                // q^2 is evaluated directly per row.  Second differences down the
-                                // strip (one add less) carry an absolute error of ulp(q^2_max of the
-                                // strip): too much for float against the 1e-5 budget, and in double
-                                // it shows as an error of sqrt(1e-14) in q right at q = 0, which a
-                                // coarse column table (integral_samples = 2: a cusp at 0) turns into
-                                // 4e-9 -- found by tests/test_gpu_fuzz.py.
-                                const R dy = (r0 + j) == 0 ? dy0 : fma(R((r0 + j) * RI), sy, dy0);
-                                q[j] = fma(dy, dy, qx);
-                                if (sizeof(R) == 4) any = any || (q[j] < rad2);
-                            }
-                            // Skip a group that cannot contribute.  double: rows that miss the
-                            // footprint box (warp-uniform integer test; a DSETP per row costs more
-                            // than the rare all-outside group).  float: exact warp vote on q^2
-                            // (comparisons are cheap there, skipped corners are not).  Measured on
-                            // config 2: 124 -> 117 ms (double), 78 vs 83 ms (float).
-                            bool live;
-                            if (sizeof(R) == 4)
-                                live = __any_sync(0xffffffffu, any);
-                            else
-                                live = own_y0 + r0 * RI < y1 && own_y0 + (r0 + G) * RI > y0;
-                            if (live) {
-#pragma unroll
-                                for (int j = 0; j < G; j++) {
-                                    const R wv = kernel_eval_unguarded<KIND, R>(q[j], rad2, lv);
-#pragma unroll
-                                    for (int k = 0; k < NW; k++)
-                                        racc[k][r0 + j] = fma(term[k], wv, racc[k][r0 + j]);
-                                }
-                            }
-                        }
-                    } else {
-                        // ---- narrow: lanes over the footprint box, shared memory ----
-                        const int lw_log = 32 - __clz(wx - 1); // smallest power of two >= wx (wx >= 1)
-                        const int rows_per_it = 32 >> lw_log;
-                        const int px = x0 + (lane & ((1 << lw_log) - 1));
-                        const int pr = lane >> lw_log;
-                        const bool in_x = px < x1;
-                        const R dx = (int_to_real(px - cx, R(0)) - fx) * sx;
-                        const R qx = fma(dx, dx, cc); // cc carries sqrt_guard()
-                        R dy = int_to_real(y0 + pr - cy, R(0)) - fy;
-                        const R dstep = int_to_real(rows_per_it, R(0));
-                        R *a = my_acc + ((y0 + pr) * SX + px);
-                        for (int py = y0 + pr; py < y1; py += rows_per_it) {
-                            if (in_x) {
-                                const R dys = dy * sy;
-                                const R q2 = fma(dys, dys, qx);
-                                if (q2 < rad2) {
-                                    const R wv = kernel_eval_pos<KIND, R>(q2, lv);
-                                    SPHB_ASSERT(px >= 0 && px < TX && py >= own_y0 && py < own_y0 + ROWS &&
-                                                a >= acc && a + (NW - 1) * ACC < acc + (size_t)ACC * NW);
-#pragma unroll
-                                    for (int k = 0; k < NW; k++) a[k * ACC] = fma(term[k], wv, a[k * ACC]);
-                                }
-                            }
-                            dy += dstep;
-                            a += rows_per_it * SX;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- merge registers into the tile, flush it, clear both ---------------
-#pragma unroll
-        for (int r = 0; r < K; r++) {
-            R *a = my_acc + ((own_y0 + ly + r * RI) * SX + lx);
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                // lanes beyond the raster edge hold values of pixels that do not exist
-                if (racc[k][r] != R(0) && lx < lim_x && own_y0 + ly + r * RI < lim_y) a[k * ACC] += racc[k][r];
-                racc[k][r] = R(0);
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < TX * TY * TZ; i += kThreads) {
-            const int ix = i % TX, iy = (i / TX) % TY, iz = i / (TX * TY);
-            if (ix < lim_x && iy < lim_y && iz < lim_z) {
-                const int a = iz * PLANE + iy * SX + ix;
-                const size_t o = ((size_t)(oz + iz) * v.ny + (oy + iy)) * v.nx + (ox + ix);
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const R val = acc[k * ACC + a];
-                    if (val != R(0)) {
-                        SPHB_ASSERT(o < v.n_out && a < ACC);
-                        red_add(outs[k] + o, (double)val);
-                        acc[k * ACC + a] = R(0);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        pos = seg_hi;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Direct path for small footprints.
-//
-// A particle whose support box is at most small_edge pixels along every axis
-// covers a handful of pixels; binning it per tile, staging it per tile and
-// scanning it per warp costs far more than its few kernel evaluations.  Such
-// particles are listed once (sorted by the tile of their box origin, so that
-// consecutive particles touch the same few kilobytes of the raster and the
-// reductions are served by L2) and rendered here: one warp takes 32 of them,
-// every lane works out the record of one, then sub-groups of LPP lanes -- LPP
-// the power of two >= the largest in-plane box area in the batch -- walk one
-// particle each, a lane per in-plane pixel and a loop over z, adding each
-// contribution to the float64 raster with red.global.add.f64.
-constexpr int kDirectWarps = 8;
-
-template <typename R, int NW> struct DirectRec {
-    R fx[32], fy[32], fz[32]; // centre in pixel units relative to the box origin
-    R sx[32], sy[32], sz[32];
-    R cq[32];                 // dz^2 / h^2 of a cross-section + sqrt guard
-    R term[NW][32];
-    unsigned long long base[32]; // raster offset of the box origin
-    uint32_t inv_wx[32];         // 65536 / wx + 1
-    uint32_t dims[32];           // wx | wy << 8 | wz << 16 ; 0 = nothing to do
-};
-
-template <typename T, typename R, int KIND, int NW, bool DIM3>
-__global__ void __launch_bounds__(kDirectWarps * 32)
-direct_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
-              const void *__restrict__ lut_global, const uint32_t *__restrict__ order, int64_t n_small, double *o0, double *o1, double *o2,
-              double *o3)
-{
-    using R2 = typename Real2<R>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    DirectRec<R, NW> *drecs = reinterpret_cast<DirectRec<R, NW> *>(smem_raw);
-    R2 *lut_s = reinterpret_cast<R2 *>(drecs + kDirectWarps);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    DirectRec<R, NW> &rec = drecs[warp];
-    double *outs[4] = {o0, o1, o2, o3};
-
-    LutView<R> lv;
-    lut_set_table(lv, lut_s);
-    lv.gtab = static_cast<const R2 *>(lut_global);
-    lv.scale = R(0);
-    lv.last = 0;
-    if (is_lut<KIND>()) {
-        const double lut_scale = (double)(lut_samples - 1) / v.radius;
-        for (int i = tid; i < (KIND == SPHB_COLUMN_LUT_GLOBAL ? 0 : lut_samples); i += kDirectWarps * 32)
-            lut_s[i] = lut_make_entry<R>(lut, lut_samples, i, lut_scale);
-        lv.scale = (R)lut_scale;
-        lv.last = lut_samples - 1;
-        __syncthreads();
-    }
-    const R rad2 = (R)(v.radius * v.radius);
-    const int64_t warps_total = (int64_t)gridDim.x * kDirectWarps;
-
-    for (int64_t base = ((int64_t)blockIdx.x * kDirectWarps + warp) * 32; base < n_small;
-         base += warps_total * 32) {
-        // ---- every lane prepares one particle --------------------------------
-        int area = 0;
-        {
-            uint32_t dims = 0;
-            if (base + lane < n_small) {
-                const int64_t p = order[base + lane];
-                const Rec<T> pr = load_rec<T>(recs, v.rec_stride, p, NW);
-                const double hp = (double)pr.h;
-                const double xp = (double)pr.x, yp = (double)pr.y;
-                const double rad = v.radius * hp;
-                const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
-                int x0, x1, y0, y1, z0 = 0, z1 = 1;
-                pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, x0, x1);
-                pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, y0, y1);
-                rec.fx[lane] = (R)((xp - v.x_min) * v.inv_pwx - 0.5 - x0);
-                rec.fy[lane] = (R)((yp - v.y_min) * v.inv_pwy - 0.5 - y0);
-                rec.sx[lane] = (R)(v.pwx * v.pwx * hinv2);
-                rec.sy[lane] = (R)(v.pwy * v.pwy * hinv2);
-                double cc = 0.0;
-                if (DIM3) {
-                    const double zp = (double)pr.z;
-                    pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, z0, z1);
-                    rec.fz[lane] = (R)((zp - v.z_min) * v.inv_pwz - 0.5 - z0);
-                    rec.sz[lane] = (R)(v.pwz * v.pwz * hinv2);
-                } else if (v.use_z) {
-                    const double dz = v.z_slice - (double)pr.z;
-                    cc = dz * dz * hinv2;
-                }
-                rec.cq[lane] = (R)cc + sqrt_guard(R(0));
-                const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
-#pragma unroll
-                for (int k = 0; k < NW; k++) rec.term[k][lane] = (R)((double)pr.w[k] * scale);
-                rec.base[lane] = ((unsigned long long)z0 * v.ny + (unsigned long long)y0) * v.nx + x0;
-                const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
-                rec.inv_wx[lane] = 65536u / (unsigned)max(wx, 1) + 1u;
-                if (wx > 0 && wy > 0 && wz > 0) {
-                    dims = (uint32_t)wx | ((uint32_t)wy << 8) | ((uint32_t)wz << 16);
-                    area = wx * wy;
-                }
-            }
-            rec.dims[lane] = dims;
-        }
-        // largest in-plane area of the batch -> lanes per particle
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) area = max(area, __shfl_xor_sync(0xffffffffu, area, o));
-        __syncwarp();
-        if (area == 0) continue;
-        int lpp_log = 0;
-        while ((1 << lpp_log) < area && lpp_log < 5) lpp_log++;
-        const int lpp = 1 << lpp_log, sub = lane & (lpp - 1), grp = lane >> lpp_log;
-
-        for (int g = 0; g < 32; g += 32 >> lpp_log) {
-            const int s = g + grp;
-            const uint32_t dims = rec.dims[s];
-            if (dims) {
-                const int wx = (int)(dims & 0xff), wy = (int)((dims >> 8) & 0xff), wz = (int)(dims >> 16);
-                const R fx = rec.fx[s], fy = rec.fy[s], sx = rec.sx[s], sy = rec.sy[s], cq = rec.cq[s];
-                R fz = R(0), sz = R(0);
-                if (DIM3) {
-                    fz = rec.fz[s];
-                    sz = rec.sz[s];
-                }
-                R term[NW];
-#pragma unroll
-                for (int k = 0; k < NW; k++) term[k] = rec.term[k][s];
-                const unsigned inv_wx = rec.inv_wx[s];
-                const unsigned long long base_o = rec.base[s];
-                for (int e = sub; e < wx * wy; e += lpp) {
-                    const int iy = (int)(((unsigned)e * inv_wx) >> 16), ix = e - iy * wx;
-                    const R dx = int_to_real(ix, R(0)) - fx, dy = int_to_real(iy, R(0)) - fy;
-                    const R qxy = fma(dy * dy, sy, fma(dx * dx, sx, cq));
-                    const size_t o = (size_t)base_o + (size_t)(iy * v.nx + ix);
-                    if (DIM3) {
-                        size_t oo = o;
-                        for (int iz = 0; iz < wz; iz++) {
-                            const R dz = int_to_real(iz, R(0)) - fz; // direct evaluation (see render_kernel)
-                            const R q2 = fma(dz * dz, sz, qxy);
-                            if (q2 < rad2) {
-                                const R wv = kernel_eval_pos<KIND, R>(q2, lv);
-                                SPHB_ASSERT(oo < v.n_out);
-#pragma unroll
-                                for (int k = 0; k < NW; k++) red_add(outs[k] + oo, (double)(term[k] * wv));
-                            }
-                            oo += (size_t)v.ny * v.nx;
-                        }
-                    } else if (qxy < rad2) {
-                        const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
-                        SPHB_ASSERT(o < v.n_out);
-#pragma unroll
-                        for (int k = 0; k < NW; k++) red_add(outs[k] + o, (double)(term[k] * wv));
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------
 // Host side.
 
-// Opt a kernel in to the full 227 KB of dynamic shared memory, once per instantiation and
-// device (driver calls per launch are kept to a minimum: they serialise with other
-// driver clients such as NVML monitors).
-template <typename K> static cudaError_t allow_large_smem(K kern)
-{
-    // keyed by (device, kernel address): instantiations share their function-pointer type
-    static std::mutex mu;
-    static std::set<std::pair<int, const void *>> done;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    const std::pair<int, const void *> key(dev, reinterpret_cast<const void *>(kern));
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (done.count(key)) return cudaSuccess;
-    }
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) {
-        std::lock_guard<std::mutex> lock(mu);
-        done.insert(key);
-    }
-    return e;
-}
-
-// SM count of the current device (cached per device).
-static cudaError_t sm_count(int *out)
+cudaError_t sm_count(int *out)
 {
     static std::mutex mu;
     static int cached[64] = {0};
@@ -883,6 +351,23 @@ static cudaError_t phase_events(cudaEvent_t *ev, int count)
     return cudaSuccess;
 }
 
+// Page-locked landing zone of the bin totals, one per host thread and device.
+static cudaError_t totals_landing(unsigned long long **out)
+{
+    static thread_local unsigned long long *cache[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidValue;
+    if (!cache[dev]) {
+        e = cudaHostAlloc(reinterpret_cast<void **>(&cache[dev]), kTotCount * sizeof(unsigned long long),
+                          cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+    }
+    *out = cache[dev];
+    return cudaSuccess;
+}
+
 struct Workspace {
     unsigned char *base;
     size_t used;
@@ -896,124 +381,32 @@ struct Workspace {
     }
 };
 
-template <typename T, typename R, int KIND, int NW, bool DIM3, int TX, int TY, int TZ, int WARPS>
-static int launch_render(const View &v, const T *recs, const sphb_kernel *k, const void *lut_global,
-                         const uint32_t *keys, const uint32_t *vals, const uint32_t *tile_end, int64_t n_pairs,
-                         double *const *out, cudaStream_t stream)
+// Footprint boxes up to this many pixels per edge take the cell path.  Bounded by the
+// shared-memory accumulator of a warp ((cell + edge - 1)^d values per weight); the
+// default can be lowered with SPHB_SMALL_EDGE (0 sends everything through the tile path).
+static int small_edge_setting(bool dim3, bool f32)
 {
-    using R2 = typename Real2<R>::type;
-    auto kern = render_kernel<T, R, KIND, NW, DIM3, TX, TY, TZ, WARPS>;
-    const size_t fixed = sizeof(R) * (size_t)(TX + RowPad<DIM3>::value) * TY * TZ * NW + sizeof(Staged<R, NW, RenderBatch<R, DIM3, WARPS>::value, DIM3>);
-    const size_t limit = 227 * 1024;
-    size_t smem = fixed;
-    if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
-    if (smem > limit) {
-        set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
-        return SPHB_ERR_ARGUMENT;
-    }
-    SPHB_CUDA(allow_large_smem(kern));
-    const int grid = div_up(n_pairs, kChunkPairs);
-    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < NW; i++) o[i] = out[i];
-    kern<<<grid, WARPS * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, keys, vals,
-                                             tile_end, n_pairs, o[0], o[1], o[2], o[3]);
-    SPHB_LAUNCH_CHECK();
-    return SPHB_OK;
-}
-
-template <typename T, typename R, int KIND, int NW, bool DIM3>
-static int launch_direct(const View &v, const T *recs, const sphb_kernel *k, const void *lut_global,
-                         const uint32_t *order, int64_t n_small, double *const *out, cudaStream_t stream)
-{
-    using R2 = typename Real2<R>::type;
-    auto kern = direct_kernel<T, R, KIND, NW, DIM3>;
-    size_t smem = sizeof(DirectRec<R, NW>) * kDirectWarps;
-    if (KIND == SPHB_COLUMN_LUT) smem += sizeof(R2) * (size_t)k->lut_samples;
-    if (smem > 227 * 1024) {
-        set_error("column table of %d samples does not fit in shared memory", k->lut_samples);
-        return SPHB_ERR_ARGUMENT;
-    }
-    SPHB_CUDA(allow_large_smem(kern));
-    int grid = div_up(n_small, kDirectWarps * 32);
-    grid = grid > 148 * 64 ? 148 * 64 : grid;
-    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < NW; i++) o[i] = out[i];
-    kern<<<grid, kDirectWarps * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, order, n_small,
-                                                    o[0], o[1], o[2], o[3]);
-    SPHB_LAUNCH_CHECK();
-    return SPHB_OK;
-}
-
-template <typename T, typename R, int KIND, bool DIM3, typename... A>
-static int direct_nw(int nw, A &&...a)
-{
-    switch (nw) {
-    case 1: return launch_direct<T, R, KIND, 1, DIM3>(a...);
-    case 2: return launch_direct<T, R, KIND, 2, DIM3>(a...);
-    case 3: return launch_direct<T, R, KIND, 3, DIM3>(a...);
-    default: return launch_direct<T, R, KIND, 4, DIM3>(a...);
-    }
-}
-
-template <typename T, typename R, bool DIM3, typename... A> static int direct_kind(int kind, int nw, A &&...a)
-{
-    switch (kind) {
-    case SPHB_CUBIC: return direct_nw<T, R, SPHB_CUBIC, DIM3>(nw, a...);
-    case SPHB_QUARTIC: return direct_nw<T, R, SPHB_QUARTIC, DIM3>(nw, a...);
-    case SPHB_QUINTIC: return direct_nw<T, R, SPHB_QUINTIC, DIM3>(nw, a...);
-    case SPHB_COLUMN_LUT: return direct_nw<T, R, SPHB_COLUMN_LUT, DIM3>(nw, a...);
-    default: return direct_nw<T, R, SPHB_COLUMN_LUT_GLOBAL, DIM3>(nw, a...);
-    }
-}
-
-template <typename T, typename R, int KIND, bool DIM3, int TX, int TY, int TZ, int WARPS, typename... A>
-static int dispatch_nw(int nw, A &&...a)
-{
-    switch (nw) {
-    case 1: return launch_render<T, R, KIND, 1, DIM3, TX, TY, TZ, WARPS>(a...);
-    case 2: return launch_render<T, R, KIND, 2, DIM3, TX, TY, TZ, WARPS>(a...);
-    // three and four weights in double: half-height 2-D tiles (see tile2y())
-    case 3: return launch_render<T, R, KIND, 3, DIM3, TX, (!DIM3 && sizeof(R) == 8) ? TY / 2 : TY, TZ, WARPS>(a...);
-    default: return launch_render<T, R, KIND, 4, DIM3, TX, (!DIM3 && sizeof(R) == 8) ? TY / 2 : TY, TZ, WARPS>(a...);
-    }
-}
-
-template <typename T, typename R, bool DIM3, int TX, int TY, int TZ, int WARPS, typename... A>
-static int dispatch_kind(int kind, int nw, A &&...a)
-{
-    switch (kind) {
-    case SPHB_CUBIC: return dispatch_nw<T, R, SPHB_CUBIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
-    case SPHB_QUARTIC: return dispatch_nw<T, R, SPHB_QUARTIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
-    case SPHB_QUINTIC: return dispatch_nw<T, R, SPHB_QUINTIC, DIM3, TX, TY, TZ, WARPS>(nw, a...);
-    case SPHB_COLUMN_LUT: return dispatch_nw<T, R, SPHB_COLUMN_LUT, DIM3, TX, TY, TZ, WARPS>(nw, a...);
-    default: return dispatch_nw<T, R, SPHB_COLUMN_LUT_GLOBAL, DIM3, TX, TY, TZ, WARPS>(nw, a...);
-    }
-}
-
-// 2-D tiles: 32 x 128 pixels, 8 warps with a 16-row strip each (16 register accumulators per lane
-// and weight): per-hit set-up is amortised over twice the rows of a 32 x 64 tile and the pair list
-// shrinks by 28 %; measured 104 -> 99.5 ms (double), 68.9 -> 63.6 ms (float) on config 2 at
-// 3 CTAs/SM (80 registers).  16 warps x 8 rows on the same tile was 20 % slower.
-constexpr int kTile2X = 32, kTile2Y = 128;
-
-// Footprint boxes up to this many pixels per edge take the direct path.  The
-// default can be overridden with SPHB_SMALL_EDGE (0 sends everything through
-// the tile path) for experiments.
-static int small_edge_setting()
-{
+    int cap = dim3 ? (f32 ? 8 : 6) : 8;
     const char *e = getenv("SPHB_SMALL_EDGE");
     if (e && *e) {
         int val = atoi(e);
-        return val < 0 ? 0 : val > 15 ? 15 : val;
+        cap = val < 0 ? 0 : val > cap ? cap : val;
     }
-    return 8;
+    return cap;
 }
-constexpr int kTile3X = 16, kTile3Y = 16, kTile3Z = 8;
 
-// Height of the 2-D tile.  With three or four weight columns in double a 32 x 128 tile needs
-// 111 / 148 KB of accumulators and 96 / 128 accumulator registers per lane: one CTA per SM, with
-// spills.  Half the height brings back two CTAs per SM and spill-free code.
-static int tile2y(bool f32, int n_weights) { return (!f32 && n_weights >= 3) ? kTile2Y / 2 : kTile2Y; }
+// Cell size (log2) of the small-footprint path: the largest of 32 / 16 (images) or 8 / 4 (grids)
+// for which a warp's accumulator, at the largest admissible box edge, stays below 28 KB.
+static int cell_log(bool dim3, bool f32, int nw, int small_edge)
+{
+    const size_t elem = f32 ? 4 : 8;
+    for (int lg = dim3 ? 3 : 5; lg > (dim3 ? 2 : 4); lg--) {
+        const size_t s = (size_t)(1 << lg) + (small_edge > 0 ? small_edge - 1 : 0);
+        const size_t bytes = (dim3 ? s * s * s : s * s) * elem * nw;
+        if (bytes <= 28 * 1024) return lg;
+    }
+    return dim3 ? 2 : 4;
+}
 
 static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
                     int use_z, double *const *out)
@@ -1048,6 +441,11 @@ static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_ra
         set_error("invalid raster");
         return SPHB_ERR_ARGUMENT;
     }
+    if ((int64_t)r->nx * r->ny * (dim3 ? r->nz : 1) > 0x7fffffff00LL || r->nx > 0x7fff00 || r->ny > 0x7fff00 ||
+        (dim3 && r->nz > 0x7fff00)) {
+        set_error("raster too large");
+        return SPHB_ERR_ARGUMENT;
+    }
     if (k->kind < SPHB_CUBIC || k->kind > SPHB_COLUMN_LUT || !(k->radius > 0.0)) {
         set_error("invalid kernel");
         return SPHB_ERR_ARGUMENT;
@@ -1063,17 +461,26 @@ static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_ra
     return SPHB_OK;
 }
 
+struct Stages {
+    int n;                    // 1 = one launch covers everything
+    const int *planes;        // planes[s] = first z-plane NOT finished by stage s (ascending; last >= nz)
+    sphb_stage_fn fn;
+    void *user;
+};
+
 template <typename T>
 static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
                         int use_z, double z_slice, int accumulate, double *const *out, void *ws,
-                        size_t ws_bytes, size_t *ws_needed, sphb_stats *stats, cudaStream_t stream)
+                        size_t ws_bytes, size_t *ws_needed, sphb_stats *stats, const Stages &stages,
+                        cudaStream_t stream)
 {
+    const bool f32 = p->dtype == SPHB_F32;
     View v;
     v.nx = r->nx;
     v.ny = r->ny;
     v.nz = dim3 ? r->nz : 1;
     v.tx = dim3 ? kTile3X : kTile2X;
-    v.ty = dim3 ? kTile3Y : tile2y(p->dtype == SPHB_F32, p->n_weights);
+    v.ty = dim3 ? kTile3Y : tile2y(f32, p->n_weights);
     v.tz = dim3 ? kTile3Z : 1;
     auto ilog2 = [](int t) { int l = 0; while ((1 << l) < t) l++; return l; };
     v.tx_log = ilog2(v.tx);
@@ -1097,18 +504,23 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     v.dim3 = dim3 ? 1 : 0;
     v.ndim = k->ndim;
     v.norm = kernel_norm(k->kind, k->ndim);
-    v.small_edge = small_edge_setting();
+    v.small_edge = small_edge_setting(dim3, f32);
     v.rec_stride = (!dim3 && !use_z && p->n_weights == 1) ? 4 : (sizeof(T) == 8 && p->n_weights <= 2) ? 6 : 8;
+    const int clog = cell_log(dim3, f32, p->n_weights, v.small_edge);
+    v.cx_log = v.cy_log = clog;
+    v.cz_log = dim3 ? clog : 0;
+    v.ncx = div_up(v.nx, 1 << v.cx_log);
+    v.ncy = div_up(v.ny, 1 << v.cy_log);
+    v.ncz = dim3 ? div_up(v.nz, 1 << v.cz_log) : 1;
+    v.halo = v.small_edge > 0 ? v.small_edge - 1 : 0; // tightened below to the largest box seen
     const int64_t n_tiles = (int64_t)v.ntx * v.nty * v.ntz;
-    if (n_tiles > 0x3fffffffLL) {
+    const int64_t n_cells = (int64_t)v.ncx * v.ncy * v.ncz;
+    if (n_tiles > 0x3fffffffLL || n_cells > 0x3fffffffLL) {
         set_error("raster has too many tiles");
         return SPHB_ERR_ARGUMENT;
     }
     int end_bit = 1;
     while ((1LL << end_bit) < n_tiles) end_bit++;
-    v.flag_bit = 1u << end_bit; // direct-path entries sort behind every tile pair
-    v.small_shift = 0;
-    end_bit++;
     const int64_t n = p->n;
     const size_t n_out = (size_t)v.nx * v.ny * v.nz;
     v.n_out = n_out;
@@ -1130,15 +542,26 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     }
     if (timed) SPHB_CUDA(phase_events(ev, 5));
     if (ws_needed) *ws_needed = 0;
-    if (n == 0) return SPHB_OK;
+    auto all_stages_done = [&]() {
+        if (stages.fn)
+            for (int s = 0; s < stages.n; s++) stages.fn(stages.user, s);
+    };
+    if (n == 0) {
+        all_stages_done();
+        return SPHB_OK;
+    }
 
-    // ---- phase A: count and scan ------------------------------------------
+    // ---- phase A: count -------------------------------------------------------
     size_t scan_tmp = 0;
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                            n + 1, stream));
+                                            n_cells + 1, stream));
     Workspace a(ws);
-    uint32_t *offsets = a.take<uint32_t>(n + 1); // counts, scanned in place
-    unsigned long long *n_small_dev = a.take<unsigned long long>(2); // direct-path particles, list entries
+    // one contiguous block cleared by one memset: totals, cell histogram, cell cursors
+    const size_t zero_words = 2 * kTotCount + (size_t)(n_cells + 1) + (size_t)n_cells;
+    uint32_t *zero_block = a.take<uint32_t>(zero_words);
+    unsigned long long *totals = reinterpret_cast<unsigned long long *>(zero_block);
+    uint32_t *cell_start = zero_block + 2 * kTotCount; // histogram, scanned in place
+    uint32_t *cell_cursor = cell_start + (n_cells + 1);
     unsigned char *scan_ws = a.take<unsigned char>(scan_tmp);
     const size_t need_a = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_a;
@@ -1148,97 +571,79 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     }
     const T *x = static_cast<const T *>(p->x), *y = static_cast<const T *>(p->y);
     const T *z = static_cast<const T *>(p->z), *h = static_cast<const T *>(p->h);
-    const int blocks = div_up(n + 1, 256);
+    const int blocks = div_up(n, 256);
+    int sms = 0;
+    SPHB_CUDA(sm_count(&sms));
     if (timed) SPHB_CUDA(cudaEventRecord(ev[0], stream));
-    SPHB_CUDA(cudaMemsetAsync(n_small_dev, 0, 2 * sizeof(unsigned long long), stream));
-    {
-        int sms = 0;
-        SPHB_CUDA(sm_count(&sms));
-        const int count_blocks = std::min<int64_t>(blocks, (int64_t)sms * 16);
-        count_tiles_kernel<T><<<count_blocks, 256, 0, stream>>>(v, x, y, z, h, n, offsets, n_small_dev);
-    }
+    SPHB_CUDA(cudaMemsetAsync(zero_block, 0, zero_words * sizeof(uint32_t), stream));
+    count_kernel<T><<<std::min<int64_t>(blocks, (int64_t)sms * 16), 256, 0, stream>>>(v, x, y, z, h, n, cell_start,
+                                                                                    totals);
     SPHB_LAUNCH_CHECK();
-    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
-    unsigned long long totals_host[2] = {0, 0};
-    SPHB_CUDA(cudaMemcpyAsync(totals_host, n_small_dev, sizeof(totals_host), cudaMemcpyDeviceToHost, stream));
+    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, cell_start, cell_start, n_cells + 1, stream));
+    unsigned long long *totals_host = nullptr;
+    SPHB_CUDA(totals_landing(&totals_host));
+    SPHB_CUDA(cudaMemcpyAsync(totals_host, totals, kTotCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                              stream));
     SPHB_CUDA(cudaStreamSynchronize(stream));
-    const unsigned long long n_small_host = totals_host[0];
-    const uint64_t total = totals_host[1]; // the 32-bit scan is meaningful only if this passes the check below
+    const int64_t n_small = (int64_t)totals_host[kTotSmall];
+    const int64_t n_large = (int64_t)totals_host[kTotLarge];
+    const uint64_t total_pairs = totals_host[kTotPairs];
+    if (totals_host[kTotEdge] > 0) v.halo = (int)totals_host[kTotEdge] - 1;
     if (stats) {
-        stats->n_pairs = (int64_t)total - (int64_t)n_small_host;
-        stats->n_direct = (int64_t)n_small_host;
+        stats->n_pairs = (int64_t)total_pairs;
+        stats->n_direct = n_small;
     }
-    if (total == 0) return SPHB_OK;
-    if (total > 0x7fffffffULL) {
+    if (total_pairs == 0 && n_small == 0) {
+        all_stages_done();
+        return SPHB_OK;
+    }
+    if (total_pairs > 0x7fffffffULL) {
         set_error("%llu (particle, tile) pairs exceed 2^31-1: split the particle set",
-                  (unsigned long long)total);
+                  (unsigned long long)total_pairs);
         if (ws_needed) *ws_needed = 0;
         return SPHB_ERR_TOO_MANY;
     }
-    const int64_t n_pairs = (int64_t)total;                     // entries in the sorted list
-    const int64_t n_small = (int64_t)n_small_host;              // its tail: direct-path particles
-    const int64_t n_large = n_pairs - n_small;                  // its head: (tile, particle) pairs
+    const int64_t n_pairs = (int64_t)total_pairs;
 
     // ---- phase B: emit, sort, segment ------------------------------------
-    // Key bits to sort on.  The flag is the top bit: with no direct-path entries it is never set.
-    // With ONLY direct-path entries the order matters just for the locality of the reductions in
-    // L2, so the flag is dropped and the keys are coarsened to buckets of tiles covering at most
-    // 128 KiB of raster (SPHB_SMALL_BUCKET_KB overrides).  Measured on config 4 (1 GiB grid, 16-bit
-    // tile ids + flag = three 8-bit radix passes): 16 / 128 KiB buckets = two passes, sort 2.64 ->
-    // 1.9 ms, direct kernel unchanged; 1 MiB: hmin variant's direct kernel 5.2 -> 8.5 ms; 4 MiB (one
-    // pass): 5.2 -> 14.4 ms and the float32 grid 28.7 -> 66 ms -- the reductions of neighbouring
-    // particles must meet in the same L2 sectors.  A raster of <= 128 KiB is not sorted at all.
-    v.small_shift = 0;
-    if (n_small == 0) {
-        end_bit--;
-    } else if (n_large == 0) {
-        const int tile_bits = end_bit - 1;
-        const char *bk = getenv("SPHB_SMALL_BUCKET_KB");
-        const double bucket_bytes = 1024.0 * (bk && *bk ? atof(bk) : 128.0);
-        const double buckets = (double)n_out * 8.0 * p->n_weights / bucket_bytes;
-        int want = 0;
-        while ((double)(1 << want) < buckets && want < tile_bits) want++;
-        v.small_shift = tile_bits - want;
-        v.flag_bit = 0;
-        end_bit = want;
-    }
-    const bool sorted = end_bit > 0;
     size_t sort_tmp = 0;
-    SPHB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                              (uint32_t *)nullptr, (uint32_t *)nullptr, n_pairs, 0,
-                                              sorted ? end_bit : 1, stream));
+    if (n_pairs > 0)
+        SPHB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                  (uint32_t *)nullptr, (uint32_t *)nullptr, n_pairs, 0, end_bit,
+                                                  stream));
     uint32_t *keys_a = a.take<uint32_t>(n_pairs);
     uint32_t *vals_a = a.take<uint32_t>(n_pairs);
     uint32_t *keys_b = a.take<uint32_t>(n_pairs);
     uint32_t *vals_b = a.take<uint32_t>(n_pairs);
-    uint32_t *tile_end = a.take<uint32_t>(n_tiles);
-    T *recs = a.take<T>((size_t)n * v.rec_stride);
+    uint32_t *tile_end = a.take<uint32_t>(n_pairs > 0 ? n_tiles : 0);
+    uint32_t *stage_tile = a.take<uint32_t>(2 * (stages.n + 1)); // first tile of each stage, then pair bounds
+    uint32_t *stage_pos = stage_tile + (stages.n + 1);
+    T *recs_large = a.take<T>(n_large > 0 ? (size_t)n * v.rec_stride : 0);
+    T *recs_small = a.take<T>((size_t)n_small * v.rec_stride);
     const bool big_lut = k->kind == SPHB_COLUMN_LUT && k->lut_samples > kLutSharedMax;
     void *lut_global = big_lut ? static_cast<void *>(a.take<double2>(k->lut_samples)) : nullptr;
     unsigned char *sort_ws = a.take<unsigned char>(sort_tmp);
     const size_t need_b = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_b;
     if (ws_bytes < need_b) {
-        set_error("workspace of %zu bytes needed for %lld pairs, %zu given", need_b, (long long)n_pairs,
-                  ws_bytes);
+        set_error("workspace of %zu bytes needed for %lld pairs and %lld cell-path particles, %zu given", need_b,
+                  (long long)n_pairs, (long long)n_small, ws_bytes);
         return SPHB_ERR_WORKSPACE;
     }
-    emit_pairs_kernel<T><<<blocks, 256, 0, stream>>>(
+    emit_kernel<T><<<blocks, 256, 0, stream>>>(
         v, x, y, z, h, static_cast<const T *>(p->w[0]), static_cast<const T *>(p->w[1]),
-        static_cast<const T *>(p->w[2]), static_cast<const T *>(p->w[3]), p->n_weights, n, offsets, keys_a, vals_a,
-        recs);
+        static_cast<const T *>(p->w[2]), static_cast<const T *>(p->w[3]), p->n_weights, n, cell_start, cell_cursor,
+        totals, keys_a, vals_a, recs_large, recs_small, n_pairs, n_small);
     SPHB_LAUNCH_CHECK();
     if (timed) SPHB_CUDA(cudaEventRecord(ev[1], stream));
-    if (sorted)
+    if (n_pairs > 0) {
         SPHB_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sort_tmp, keys_a, keys_b, vals_a, vals_b, n_pairs, 0,
                                                   end_bit, stream));
-    if (n_large > 0) {
-        tile_end_kernel<<<div_up(n_large, 256), 256, 0, stream>>>(keys_b, n_large, tile_end);
+        tile_end_kernel<<<div_up(n_pairs, 256), 256, 0, stream>>>(keys_b, n_pairs, tile_end);
         SPHB_LAUNCH_CHECK();
     }
-
     if (big_lut) {
-        if (p->dtype == SPHB_F32)
+        if (f32)
             lut_pairs_kernel<float><<<div_up(k->lut_samples, 256), 256, 0, stream>>>(
                 k->lut, k->lut_samples, (double)(k->lut_samples - 1) / v.radius, static_cast<float2 *>(lut_global));
         else
@@ -1247,41 +652,54 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         SPHB_LAUNCH_CHECK();
     }
 
+    // ---- stages: z-planes -> tile and cell boundaries ---------------------------
+    // Stage s renders every tile / cell whose lowest plane lies below planes[s]; a box listed under
+    // a tile / cell never reaches planes below it, so the planes below the boundary are final.
+    int launches = 2 + (n_pairs > 0 ? 1 : 0);
+    std::vector<int64_t> cell_bound(stages.n + 1, 0);
+    if (stages.n > 1) {
+        std::vector<uint32_t> first(stages.n + 1, 0);
+        for (int s = 0; s < stages.n; s++) {
+            const int plane = s + 1 < stages.n ? std::min(std::max(stages.planes[s], 0), v.nz) : v.nz;
+            const int64_t tz = std::min<int64_t>(div_up(plane, v.tz), v.ntz);
+            const int64_t cz = std::min<int64_t>(div_up(plane, 1 << v.cz_log), v.ncz);
+            first[s + 1] = (uint32_t)(tz * v.nty * v.ntx);
+            cell_bound[s + 1] = cz * v.ncy * v.ncx;
+        }
+        first[stages.n] = (uint32_t)n_tiles;
+        cell_bound[stages.n] = n_cells;
+        if (n_pairs > 0) {
+            SPHB_CUDA(cudaMemcpyAsync(stage_tile, first.data(), (stages.n + 1) * sizeof(uint32_t),
+                                      cudaMemcpyHostToDevice, stream));
+            stage_bounds_kernel<<<1, 64, 0, stream>>>(keys_b, n_pairs, stage_tile, stages.n + 1, stage_pos);
+            SPHB_LAUNCH_CHECK();
+            launches++;
+        }
+    } else {
+        cell_bound[1] = n_cells;
+    }
+
     // ---- phase C: render ---------------------------------------------------
     if (timed) SPHB_CUDA(cudaEventRecord(ev[2], stream));
-    const bool f32 = p->dtype == SPHB_F32;
     const int kind = big_lut ? SPHB_COLUMN_LUT_GLOBAL : k->kind;
-    int rc = SPHB_OK;
-    if (n_large > 0) {
-        if (dim3) {
-            if (f32)
-                rc = dispatch_kind<T, float, true, kTile3X, kTile3Y, kTile3Z, 8>(
-                    kind, p->n_weights, v, recs, k, lut_global, keys_b, vals_b, tile_end, n_large, out, stream);
-            else
-                rc = dispatch_kind<T, double, true, kTile3X, kTile3Y, kTile3Z, 8>(
-                    kind, p->n_weights, v, recs, k, lut_global, keys_b, vals_b, tile_end, n_large, out, stream);
-        } else {
-            if (f32)
-                rc = dispatch_kind<T, float, false, kTile2X, kTile2Y, 1, 8>(kind, p->n_weights, v, recs, k, lut_global, keys_b,
-                                                                           vals_b, tile_end, n_large, out, stream);
-            else
-                rc = dispatch_kind<T, double, false, kTile2X, kTile2Y, 1, 8>(kind, p->n_weights, v, recs, k, lut_global, keys_b,
-                                                                            vals_b, tile_end, n_large, out, stream);
+    // the two kernels of a stage; with one stage the tile kernel's time is bracketed on its own
+    for (int s = 0; s < stages.n; s++) {
+        if (n_pairs > 0) {
+            int rc = launch_render(v, f32, kind, p->n_weights, recs_large, k, lut_global, keys_b, vals_b, tile_end,
+                                   n_pairs, stages.n > 1 ? stage_pos + s : nullptr, out, stream);
+            if (rc) return rc;
+            launches++;
         }
-        if (rc) return rc;
+        if (timed && s == 0) SPHB_CUDA(cudaEventRecord(ev[4], stream));
+        if (n_small > 0 && cell_bound[s + 1] > cell_bound[s]) {
+            int rc = launch_cells(v, f32, kind, p->n_weights, recs_small, k, lut_global, cell_start, n_small,
+                                  cell_bound[s], cell_bound[s + 1], out, stream);
+            if (rc) return rc;
+            launches++;
+        }
+        if (stages.fn) stages.fn(stages.user, s);
     }
-    if (timed) SPHB_CUDA(cudaEventRecord(ev[4], stream));
-    if (n_small > 0) {
-        const uint32_t *order = (sorted ? vals_b : vals_a) + n_large;
-        if (dim3)
-            rc = f32 ? direct_kind<T, float, true>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream)
-                     : direct_kind<T, double, true>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream);
-        else
-            rc = f32 ? direct_kind<T, float, false>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream)
-                     : direct_kind<T, double, false>(kind, p->n_weights, v, recs, k, lut_global, order, n_small, out, stream);
-    }
-    if (rc) return rc;
-    if (stats) stats->launches = 2 + (n_large > 0 ? 2 : 0) + (n_small > 0 ? 1 : 0); // count, emit, tile_end, render, direct
+    if (stats) stats->launches = launches;
     if (timed) {
         SPHB_CUDA(cudaEventRecord(ev[3], stream));
         SPHB_CUDA(cudaEventSynchronize(ev[3]));
@@ -1304,21 +722,41 @@ extern "C" int sphb_scatter2d(const sphb_particles *p, const sphb_kernel *k, con
     int rc = validate(p, k, r, false, use_z, out);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Stages one = {1, nullptr, nullptr, nullptr};
     if (p->dtype == SPHB_F32)
         return scatter_impl<float>(p, k, r, false, use_z, z_slice, accumulate, out, ws, ws_bytes, ws_needed,
-                                   stats, s);
+                                   stats, one, s);
     return scatter_impl<double>(p, k, r, false, use_z, z_slice, accumulate, out, ws, ws_bytes, ws_needed,
-                                stats, s);
+                                stats, one, s);
+}
+
+extern "C" int sphb_scatter3d_staged(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r,
+                                     int accumulate, double *const *out, void *ws, size_t ws_bytes,
+                                     size_t *ws_needed, sphb_stats *stats, int n_stages, const int *stage_planes,
+                                     sphb_stage_fn on_stage, void *user, sphb_stream stream)
+{
+    int rc = validate(p, k, r, true, 0, out);
+    if (rc) return rc;
+    if (n_stages < 1 || n_stages > SPHB_MAX_STAGES || (n_stages > 1 && !stage_planes)) {
+        set_error("n_stages must be 1..%d (with the stage planes given)", SPHB_MAX_STAGES);
+        return SPHB_ERR_ARGUMENT;
+    }
+    for (int s = 1; s < n_stages; s++)
+        if (stage_planes[s] < stage_planes[s - 1]) {
+            set_error("stage planes must ascend");
+            return SPHB_ERR_ARGUMENT;
+        }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Stages st = {n_stages, stage_planes, on_stage, user};
+    if (p->dtype == SPHB_F32)
+        return scatter_impl<float>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, st, s);
+    return scatter_impl<double>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, st, s);
 }
 
 extern "C" int sphb_scatter3d(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r,
                               int accumulate, double *const *out, void *ws, size_t ws_bytes,
                               size_t *ws_needed, sphb_stats *stats, sphb_stream stream)
 {
-    int rc = validate(p, k, r, true, 0, out);
-    if (rc) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (p->dtype == SPHB_F32)
-        return scatter_impl<float>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, s);
-    return scatter_impl<double>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, s);
+    return sphb_scatter3d_staged(p, k, r, accumulate, out, ws, ws_bytes, ws_needed, stats, 1, nullptr, nullptr,
+                                 nullptr, stream);
 }

@@ -102,8 +102,11 @@ def _particles(x, y, z, h, weights: Sequence[torch.Tensor], lo: int = 0, hi: Opt
 def _kernel(weight_function, radius: float, ndim: int, device):
     kind = getattr(weight_function, "kind", None)
     if kind not in _KIND:
-        raise TypeError("weight_function must be a sarracen_b200.kernels.WeightFunction "
-                        "(or a Sarracen kernel function resolved by sarracen_b200.backend)")
+        # one of Sarracen's own numba dispatchers (kernel.w, or the column-table closure of
+        # BaseKernel.get_column_kernel_func): map it to a device code path, or raise TypeError
+        from .backend import resolve_weight_function
+        weight_function = resolve_weight_function(weight_function, radius)
+        kind = weight_function.kind
     k = SphbKernel()
     k.kind = _KIND[kind]
     k.ndim = int(ndim)
@@ -135,7 +138,8 @@ def column_kernel(kind: str, samples: int, device=None) -> torch.Tensor:
 
 
 def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, raster: Raster, use_z=False,
-             z_slice=0.0, out: Optional[List[torch.Tensor]] = None, accumulate=False) -> List[torch.Tensor]:
+             z_slice=0.0, out: Optional[List[torch.Tensor]] = None, accumulate=False, stage_planes=None,
+             on_stage=None) -> List[torch.Tensor]:
     lib = _lib.load()
     device = x.device
     n = x.numel()
@@ -156,6 +160,16 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
     total_direct = 0
     ms = [0.0, 0.0, 0.0, 0.0]
     launches = 0
+    # z-slab stages (voxel grids only): the library calls back right after the kernels of stage s have
+    # been enqueued, and `on_stage(s)` runs there, on this thread, so that an event recorded by it sits
+    # between stage s and stage s + 1 in the stream.  A particle set that has to be split into batches
+    # (workspace) cannot be staged: every batch adds to all slabs, so the stages are reported at the end.
+    staged = dim3 and stage_planes is not None and len(stage_planes) > 1
+    split = False
+    if staged:
+        n_stages = len(stage_planes)
+        planes_c = (ctypes.c_int * n_stages)(*[int(v) for v in stage_planes])
+        stage_cb = _lib.STAGE_FN((lambda _user, s: on_stage(s)) if on_stage is not None else (lambda _user, s: None))
     with torch.cuda.device(device):
         stream = _stream(device)
         budget = None  # worked out only if the workspace has to grow
@@ -171,7 +185,11 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
             while True:
                 wptr = ctypes.c_void_p(ws.data_ptr()) if ws is not None else None
                 wlen = ws.numel() if ws is not None else 0
-                if dim3:
+                if staged and not split:
+                    rc = lib.sphb_scatter3d_staged(ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast), acc,
+                                                   optr, wptr, wlen, ctypes.byref(need), ctypes.byref(stats),
+                                                   n_stages, planes_c, stage_cb, None, stream)
+                elif dim3:
                     rc = lib.sphb_scatter3d(ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast), acc, optr,
                                             wptr, wlen, ctypes.byref(need), ctypes.byref(stats), stream)
                 else:
@@ -191,6 +209,7 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
                 mid = (lo + hi) // 2  # bin list too large for this device: halve the batch
                 todo.append((mid, hi))
                 todo.append((lo, mid))
+                split = True
                 continue
             _lib.check(rc)
             done_any = True
@@ -198,6 +217,9 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
             total_direct += stats.n_direct
             launches += stats.launches
             ms = [ms[0] + stats.ms_bin, ms[1] + stats.ms_sort, ms[2] + stats.ms_render, ms[3] + stats.ms_direct]
+        if staged and split and on_stage is not None:
+            for s_done in range(n_stages):
+                on_stage(s_done)
     last_stats.clear()
     last_stats.update(n_pairs=int(total_pairs), n_direct=int(total_direct), n_tiles=int(stats.n_tiles),
                       tile=(int(stats.tile_x), int(stats.tile_y), int(stats.tile_z)),
@@ -219,9 +241,15 @@ def scatter2d(x, y, h, weights, weight_function, radius, ndim, raster: Raster, z
 
 
 def scatter3d(x, y, z, h, weights, weight_function, radius, raster: Raster, out=None,
-              accumulate=False) -> List[torch.Tensor]:
-    """B2/B3: sampled scatter onto a voxel grid in one pass (cpu_backend.py:193-220)."""
-    return _scatter(True, x, y, z, h, weights, weight_function, radius, 3, raster, False, 0.0, out, accumulate)
+              accumulate=False, stage_planes=None, on_stage=None) -> List[torch.Tensor]:
+    """B2/B3: sampled scatter onto a voxel grid in one pass (cpu_backend.py:193-220).
+
+    `stage_planes` (ascending z-plane indices, the last one >= nz) renders the grid in z-slab
+    stages: stage s finishes every plane below stage_planes[s], and `on_stage(s)` is called right
+    after its kernels have been enqueued on the current stream (sarracen_b200.parallel records an
+    event there and reduces that slab across GPUs while the later stages render)."""
+    return _scatter(True, x, y, z, h, weights, weight_function, radius, 3, raster, False, 0.0, out, accumulate,
+                    stage_planes, on_stage)
 
 
 def line2d(x, y, h, weights, weight_function, radius, pixels, x1, x2, y1, y2) -> List[torch.Tensor]:

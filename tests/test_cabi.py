@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in sphb200.h but not exported"
     assert sorted(_lib.EXPORTS) == names
-    assert lib.sphb_version() == 100
+    assert lib.sphb_version() == _lib.SPHB_VERSION == 200
 
 
 def test_struct_layouts_match_the_header(tmp_path):
