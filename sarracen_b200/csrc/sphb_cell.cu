@@ -17,7 +17,7 @@
 //     at once for narrow boxes), a loop over z -- and accumulated with plain
 //     load / fma / store: the accumulator is exclusive to the warp, lanes of one particle
 //     touch distinct pixels, so no atomics are needed;
-//   * when the stream moves on to another cell (or the chunk ends) the touched part of the
+//   * when the stream moves on to another cell (or the chunk ends) the non-zero part of the
 //     accumulator is added to the float64 raster with red.global.add.f64, coalesced along x,
 //     and cleared: global atomics only at cell boundaries -- 3.4 per particle instead of 57.6
 //     for BASELINE config 4;
@@ -31,60 +31,109 @@
 
 namespace sphb {
 
-constexpr int kCellMaxWarps = 16;
+#ifndef SPHB_CELL_MAXW
+#define SPHB_CELL_MAXW 16
+#endif
+constexpr int kCellMaxWarps = SPHB_CELL_MAXW;
 constexpr int kTinyVolume = 16; // a batch whose largest box holds <= this many pixels reduces directly
 
-// Staging slots of one warp: one batch of 32 particles.
+// Staging slots of one warp: one batch of 32 particles.  Everything a particle's pass needs is
+// derived here once, lane-parallel, so that the pass itself starts with a few broadcast loads.
 template <typename R, int NW> struct CellBatch {
     R sx[32], sy[32], sz[32]; // pixel -> q along each axis (pixel width / h)
     R ox[32], oy[32], oz[32]; // q-space offset of the box origin: -(centre - origin) * s
     R cq[32];                 // dz^2 / h^2 of a cross-section + sqrt guard
     R term[NW][32];           // norm * w / h^ndim
+    // x: box origin inside its cell, lx | ly << 8 | lz << 16;  y: box size wx | wy << 8 | wz << 16
+    // (0 = nothing to do);  z: cell id;  w: lanes per z-slice (log2) | (65536 / wx + 1) << 8
+    int4 geo[32];
     int bx[32], by[32], bz[32]; // box origin (raster pixels)
-    uint32_t dims[32];        // wx | wy << 8 | wz << 16; 0 = nothing to do
 };
 
 template <typename R> struct CellAcc {
     R *acc;         // the warp's accumulator, NW planes of `plane` elements
     int s1, s2;     // row and z-plane strides (elements)
+    int rows;       // rows of one weight: plane / s1
     int plane;      // elements per weight
-    // cell being accumulated (-1: none) and its origin in raster pixels
-    int cell, cx0, cy0, cz0;
-    // touched part of the accumulator, local coordinates [lo, hi)
-    int lx, hx, ly, hy, lz, hz;
+    int cell;       // cell being accumulated (-1: none)
+    int cx0, cy0, cz0; // its origin in raster pixels
+    bool dirty;
 };
 
+// Add the warp's accumulator to the raster and clear it.  Lanes are laid over x (several rows per
+// pass when a row is shorter than a warp) and walk the rows of the accumulator; only non-zero
+// entries reach the raster, so untouched entries -- including those that would lie outside it -- cost a
+// shared-memory read and nothing else.
 template <typename R, int NW>
 __device__ __forceinline__ void cell_flush(CellAcc<R> &a, const View &v, int lane, double *const *outs)
 {
-    if (a.hx > a.lx) {
-        __syncwarp();
-        const int ex = a.hx - a.lx, ey = a.hy - a.ly, ez = a.hz - a.lz;
-        const int exy = ex * ey, n = exy * ez;
-        for (int e = lane; e < n; e += 32) {
-            const int iz = e / exy, r = e - iz * exy;
-            const int iy = r / ex, ix = r - iy * ex;
-            const int la = (a.lz + iz) * a.s2 + (a.ly + iy) * a.s1 + a.lx + ix;
-            const size_t o = ((size_t)(a.cz0 + a.lz + iz) * v.ny + (size_t)(a.cy0 + a.ly + iy)) * v.nx +
-                             (size_t)(a.cx0 + a.lx + ix);
+    if (!a.dirty) return;
+    __syncwarp();
+    const int xlog = min(5, 32 - __clz(a.s1 - 1)); // lanes per row: power of two >= s1 (at most 32)
+    const int rp = 32 >> xlog;                     // rows per pass
+    const int sy = a.s2 / a.s1;                    // rows per z-plane
+    for (int ix = lane & ((1 << xlog) - 1); ix < a.s1; ix += 32) {
+        int iy = lane >> xlog, iz = 0;
+        for (int r = iy; r < a.rows; r += rp) {
+            while (iy >= sy) {
+                iy -= sy;
+                iz++;
+            }
+            const int la = r * a.s1 + ix;
 #pragma unroll
             for (int k = 0; k < NW; k++) {
                 const R val = a.acc[k * a.plane + la];
                 if (val != R(0)) {
+                    const size_t o = ((size_t)(a.cz0 + iz) * v.ny + (size_t)(a.cy0 + iy)) * v.nx + (size_t)(a.cx0 + ix);
                     SPHB_ASSERT(o < v.n_out && la < a.plane);
                     red_add(outs[k] + o, (double)val);
                     a.acc[k * a.plane + la] = R(0);
                 }
             }
+            iy += rp;
         }
-        __syncwarp();
     }
-    a.lx = a.ly = a.lz = 1 << 30;
-    a.hx = a.hy = a.hz = 0;
+    __syncwarp();
+    a.dirty = false;
 }
 
-template <typename T, typename R, int KIND, int NW, bool DIM3>
-__global__ void __launch_bounds__(kCellMaxWarps * 32, 1)
+// One lane's column of a particle's box: U z-slices (iz = zs, zs + sp, ...) evaluated without
+// branches, so that the U dependent chains (q^2 -> square root -> polynomial / table) overlap; a
+// slice outside the support evaluates to W = 0 and is not stored.
+template <typename R, int KIND, int NW, int U>
+__device__ __forceinline__ void cell_column(R qxy, R dz0, R step, int zs, int sp, int wz, R rad2, const R *term,
+                                            R *ap, int zstride, int plane, const LutView<R> &lv)
+{
+    // opaque copies: without them ptxas evaluates the multiples of step and zstride for all eight
+    // instantiations ahead of the switch that selects one
+    if (sizeof(R) == 8)
+        asm volatile("" : "+d"(*reinterpret_cast<double *>(&step)));
+    else
+        asm volatile("" : "+f"(*reinterpret_cast<float *>(&step)));
+    asm volatile("" : "+r"(zstride));
+    R q2[U], wv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const R dzs = u == 0 ? dz0 : fma(R(u), step, dz0);
+        q2[u] = fma(dzs, dzs, qxy); // qxy carries sqrt_guard()
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) wv[u] = kernel_eval_unguarded<KIND, R>(q2[u], rad2, lv);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (zs + u * sp < wz && q2[u] < rad2) {
+            R *p = ap + u * zstride;
+#pragma unroll
+            for (int k = 0; k < NW; k++) p[k * plane] = fma(term[k], wv[u], p[k * plane]);
+        }
+    }
+}
+
+// ACC = false: every box of the call holds at most kTinyVolume pixels, so the accumulator is never
+// used; that variant is built without it (fewer registers, 8-warp CTAs, several CTAs per SM: the
+// direct reductions need many warps in flight, not shared memory).
+template <typename T, typename R, int KIND, int NW, bool DIM3, bool ACC>
+__global__ void __launch_bounds__(ACC ? kCellMaxWarps * 32 : 256, ACC ? 1 : 4)
 cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, int lut_samples,
             const void *__restrict__ lut_global, const uint32_t *__restrict__ cell_start, int64_t cell_lo,
             int64_t cell_hi, int plane, int lut_bytes, int warp_bytes, double *o0, double *o1, double *o2,
@@ -123,22 +172,25 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
     a.s1 = (1 << v.cx_log) + v.halo;
     a.s2 = a.s1 * ((1 << v.cy_log) + v.halo);
     a.plane = plane;
+    a.rows = plane / a.s1;
     a.cell = -1;
     a.cx0 = a.cy0 = a.cz0 = 0;
-    a.lx = a.ly = a.lz = 1 << 30;
-    a.hx = a.hy = a.hz = 0;
-    for (int i = lane; i < NW * plane; i += 32) a.acc[i] = R(0);
-    __syncwarp();
+    a.dirty = false;
+    if (ACC) {
+        for (int i = lane; i < NW * plane; i += 32) a.acc[i] = R(0);
+        __syncwarp();
+    }
 
     const R rad2 = (R)(v.radius * v.radius);
+    const int cmx = (1 << v.cx_log) - 1, cmy = (1 << v.cy_log) - 1, cmz = (1 << v.cz_log) - 1;
 
     for (int64_t base = start; base < end; base += 32) {
         // ---- every lane derives one particle ---------------------------------
         int vol = 0;
         {
-            uint32_t dims = 0;
+            int4 geo = make_int4(0, 0, -1, 0);
             if (base + lane < end) {
-                const Rec<T> pr = load_rec<T>(recs, v.rec_stride, base + lane, NW);
+                const Rec<T> pr = load_rec(recs, v.rec_stride, base + lane, NW);
                 const double hp = (double)pr.h;
                 const double xp = (double)pr.x, yp = (double)pr.y;
                 const double rad = v.radius * hp;
@@ -172,11 +224,15 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                 const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
                 if (wx > 0 && wy > 0 && wz > 0) {
                     SPHB_ASSERT(wx <= v.halo + 1 && wy <= v.halo + 1 && wz <= v.halo + 1);
-                    dims = (uint32_t)wx | ((uint32_t)wy << 8) | ((uint32_t)wz << 16);
                     vol = wx * wy * wz;
+                    geo.x = (x0 & cmx) | ((y0 & cmy) << 8) | ((z0 & cmz) << 16);
+                    geo.y = wx | (wy << 8) | (wz << 16);
+                    geo.z = (((z0 >> v.cz_log) * v.ncy) + (y0 >> v.cy_log)) * v.ncx + (x0 >> v.cx_log);
+                    const int lpl_log = DIM3 ? min(5, 32 - __clz(wx * wy - 1)) : 5; // ceil(log2(wx wy))
+                    geo.w = lpl_log | (int)((65536u / (unsigned)wx + 1u) << 8);
                 }
             }
-            st.dims[lane] = dims;
+            st.geo[lane] = geo;
         }
         int vmax = vol;
 #pragma unroll
@@ -184,15 +240,15 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
         __syncwarp();
         if (vmax == 0) continue;
 
-        if (vmax <= kTinyVolume) {
+        if (!ACC || vmax <= kTinyVolume) {
             // ---- tiny boxes: a sub-group of lanes per particle, straight into the raster -----
             int lpp_log = 0;
             while ((1 << lpp_log) < vmax) lpp_log++;
             const int sub = lane & ((1 << lpp_log) - 1), grp = lane >> lpp_log;
             for (int g = 0; g < 32; g += 32 >> lpp_log) {
                 const int s = g + grp;
-                const uint32_t dims = st.dims[s];
-                const int wx = (int)(dims & 0xff), wy = (int)((dims >> 8) & 0xff), wz = (int)(dims >> 16);
+                const int dims = st.geo[s].y;
+                const int wx = dims & 0xff, wy = (dims >> 8) & 0xff, wz = dims >> 16;
                 const int wxy = wx * wy;
                 if (sub < wxy * wz) {
                     // sub < 16: exact small divisions by multiply-shift
@@ -219,70 +275,68 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
         }
 
         // ---- one particle per pass, lanes over its box, local accumulator --------------
-        const int nb = (int)min((int64_t)32, end - base);
+        const int nb = ACC ? (int)min((int64_t)32, end - base) : 0;
         for (int s = 0; s < nb; s++) {
-            const uint32_t dims = st.dims[s];
-            if (!dims) continue;
-            const int wx = (int)(dims & 0xff), wy = (int)((dims >> 8) & 0xff), wz = (int)(dims >> 16);
-            const int bx = st.bx[s], by = st.by[s], bz = st.bz[s];
-            const int cell = (((bz >> v.cz_log) * v.ncy) + (by >> v.cy_log)) * v.ncx + (bx >> v.cx_log);
-            if (cell != a.cell) {
+            const int4 geo = st.geo[s];
+            if (!geo.y) continue;
+            if (geo.z != a.cell) {
                 cell_flush<R, NW>(a, v, lane, outs);
-                a.cell = cell;
-                a.cx0 = (bx >> v.cx_log) << v.cx_log;
-                a.cy0 = (by >> v.cy_log) << v.cy_log;
-                a.cz0 = (bz >> v.cz_log) << v.cz_log;
+                a.cell = geo.z;
+                a.cx0 = st.bx[s] - (geo.x & 0xff);
+                a.cy0 = st.by[s] - ((geo.x >> 8) & 0xff);
+                a.cz0 = st.bz[s] - (geo.x >> 16);
             }
-            const int lx0 = bx - a.cx0, ly0 = by - a.cy0, lz0 = bz - a.cz0;
-            a.lx = min(a.lx, lx0); a.hx = max(a.hx, lx0 + wx);
-            a.ly = min(a.ly, ly0); a.hy = max(a.hy, ly0 + wy);
-            a.lz = min(a.lz, lz0); a.hz = max(a.hz, lz0 + wz);
-            SPHB_ASSERT(lx0 >= 0 && ly0 >= 0 && lz0 >= 0 && lx0 + wx <= a.s1 && (ly0 + wy) * a.s1 <= a.s2 &&
-                        (lz0 + wz) * a.s2 <= a.plane);
-
+            a.dirty = true;
+            const int wx = geo.y & 0xff, wy = (geo.y >> 8) & 0xff, wz = geo.y >> 16;
+            const int lx0 = geo.x & 0xff, ly0 = (geo.x >> 8) & 0xff, lz0 = geo.x >> 16;
+            SPHB_ASSERT(lx0 + wx <= a.s1 && (ly0 + wy) * a.s1 <= a.s2 && (lz0 + wz) * a.s2 <= a.plane);
             const R sx = st.sx[s], sy = st.sy[s], ox = st.ox[s], oy = st.oy[s], cq = st.cq[s];
-            R sz = R(0), oz = R(0);
-            if (DIM3) {
-                sz = st.sz[s];
-                oz = st.oz[s];
-            }
             R term[NW];
 #pragma unroll
             for (int k = 0; k < NW; k++) term[k] = st.term[k][s];
-
-            // lanes: in-plane pixel a = lane % lpl, z-slice lane / lpl (lpl = power of two >= wx wy,
-            // at most 32; a wider plane is covered in several rounds of 32)
             const int wxy = wx * wy;
-            const int lpl_log = min(5, 32 - __clz(wxy - 1)); // ceil(log2(wx wy)), 0 for a single pixel
-            const int lpl = 1 << lpl_log, sp = DIM3 ? (32 >> lpl_log) : 1;
-            const int zs = DIM3 ? (lane >> lpl_log) : 0;
-            const unsigned inv_wx = 65536u / (unsigned)wx + 1u;
-            for (int a0 = DIM3 ? (lane & (lpl - 1)) : lane; a0 < wxy; a0 += DIM3 ? lpl : 32) {
-                const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
-                const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
-                const R qxy = fma(dys, dys, fma(dxs, dxs, cq)); // cq carries sqrt_guard()
-                R *ap = a.acc + ((lz0 + zs) * a.s2 + (ly0 + iy) * a.s1 + lx0 + ix);
-                if (DIM3) {
-                    for (int iz = zs; iz < wz; iz += sp) {
-                        const R dzs = fma((R)iz, sz, oz);
-                        const R q2 = fma(dzs, dzs, qxy);
-                        if (q2 < rad2) {
-                            const R wv = kernel_eval_pos<KIND, R>(q2, lv);
-#pragma unroll
-                            for (int k = 0; k < NW; k++) ap[k * a.plane] = fma(term[k], wv, ap[k * a.plane]);
-                        }
-                        ap += sp * a.s2;
+            const unsigned inv_wx = (unsigned)geo.w >> 8;
+            if (DIM3) {
+                // lanes: in-plane pixel lane % lpl, z-slice lane / lpl (lpl = power of two >= wx wy, at
+                // most 32; a wider plane is covered in several rounds)
+                const R sz = st.sz[s], oz = st.oz[s];
+                const int lpl_log = geo.w & 0xff, lpl = 1 << lpl_log, sp = 32 >> lpl_log, zs = lane >> lpl_log;
+                const int nit = (wz + sp - 1) >> (5 - lpl_log);
+                const R dz0 = fma((R)zs, sz, oz), step = (R)sp * sz;
+                const int zstride = sp * a.s2;
+                for (int a0 = lane & (lpl - 1); a0 < wxy; a0 += lpl) {
+                    const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
+                    const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
+                    const R qxy = fma(dys, dys, fma(dxs, dxs, cq)); // cq carries sqrt_guard()
+                    R *ap = a.acc + ((lz0 + zs) * a.s2 + (ly0 + iy) * a.s1 + lx0 + ix);
+                    switch (nit) {
+                    case 1: cell_column<R, KIND, NW, 1>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+                    case 2: cell_column<R, KIND, NW, 2>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+                    case 3: cell_column<R, KIND, NW, 3>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+                    case 4: cell_column<R, KIND, NW, 4>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+                    case 5: cell_column<R, KIND, NW, 5>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+                    case 6: cell_column<R, KIND, NW, 6>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+                    case 7: cell_column<R, KIND, NW, 7>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+                    default: cell_column<R, KIND, NW, 8>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
                     }
-                } else if (qxy < rad2) {
-                    const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
+                }
+            } else {
+                for (int a0 = lane; a0 < wxy; a0 += 32) {
+                    const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
+                    const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
+                    const R qxy = fma(dys, dys, fma(dxs, dxs, cq));
+                    if (qxy < rad2) {
+                        const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
+                        R *ap = a.acc + ((ly0 + iy) * a.s1 + lx0 + ix);
 #pragma unroll
-                    for (int k = 0; k < NW; k++) ap[k * a.plane] = fma(term[k], wv, ap[k * a.plane]);
+                        for (int k = 0; k < NW; k++) ap[k * plane] = fma(term[k], wv, ap[k * plane]);
+                    }
                 }
             }
             __syncwarp();
         }
     }
-    cell_flush<R, NW>(a, v, lane, outs);
+    if (ACC) cell_flush<R, NW>(a, v, lane, outs);
 }
 
 // ---------------------------------------------------------------------------
@@ -292,9 +346,10 @@ static int launch_one(const View &v, const T *recs, const sphb_kernel *k, const 
                       double *const *out, cudaStream_t stream)
 {
     using R2 = typename Real2<R>::type;
-    auto kern = cell_kernel<T, R, KIND, NW, DIM3>;
     const int s1 = (1 << v.cx_log) + v.halo, s2 = s1 * ((1 << v.cy_log) + v.halo);
-    const int plane = DIM3 ? s2 * ((1 << v.cz_log) + v.halo) : s2;
+    const int edge = v.halo + 1;
+    const bool acc = (DIM3 ? edge * edge * edge : edge * edge) > kTinyVolume;
+    const int plane = !acc ? 0 : DIM3 ? s2 * ((1 << v.cz_log) + v.halo) : s2;
     size_t lut_bytes = 0;
     if (KIND == SPHB_COLUMN_LUT) lut_bytes = align_up(sizeof(R2) * (size_t)k->lut_samples, 16);
     const size_t warp_bytes = align_up(sizeof(CellBatch<R, NW>) + sizeof(R) * (size_t)plane * NW, 16);
@@ -305,15 +360,26 @@ static int launch_one(const View &v, const T *recs, const sphb_kernel *k, const 
         return SPHB_ERR_ARGUMENT;
     }
     int warps = (int)((limit - lut_bytes) / warp_bytes);
-    warps = warps > kCellMaxWarps ? kCellMaxWarps : warps;
-    SPHB_CUDA(allow_large_smem(kern));
+    const int cap = acc ? kCellMaxWarps : 8;
+    warps = warps > cap ? cap : warps;
     const int64_t units = (n_small + kCellChunk - 1) / kCellChunk + 1; // upper bound for any cell range
     const int grid = div_up(units, warps);
     double *o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < NW; i++) o[i] = out[i];
-    kern<<<grid, warps * 32, lut_bytes + warp_bytes * warps, stream>>>(
-        v, recs, k->lut, k->lut_samples, lut_global, cell_start, cell_lo, cell_hi, plane, (int)lut_bytes,
-        (int)warp_bytes, o[0], o[1], o[2], o[3]);
+    const size_t smem = lut_bytes + warp_bytes * warps;
+    if (acc) {
+        auto kern = cell_kernel<T, R, KIND, NW, DIM3, true>;
+        SPHB_CUDA(allow_large_smem(kern));
+        kern<<<grid, warps * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, cell_start, cell_lo,
+                                                 cell_hi, plane, (int)lut_bytes, (int)warp_bytes, o[0], o[1], o[2],
+                                                 o[3]);
+    } else {
+        auto kern = cell_kernel<T, R, KIND, NW, DIM3, false>;
+        SPHB_CUDA(allow_large_smem(kern));
+        kern<<<grid, warps * 32, smem, stream>>>(v, recs, k->lut, k->lut_samples, lut_global, cell_start, cell_lo,
+                                                 cell_hi, plane, (int)lut_bytes, (int)warp_bytes, o[0], o[1], o[2],
+                                                 o[3]);
+    }
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }

@@ -158,7 +158,7 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
             // ---- stage: one particle per thread --------------------------------
             if (tid < nb) {
                 const int64_t p = vals[base + tid];
-                const Rec<T> pr = load_rec<T>(recs, v.rec_stride, p, NW);
+                const Rec<T> pr = load_rec(recs, v.rec_stride, p, NW);
                 const double hp = (double)pr.h;
                 const double xp = (double)pr.x, yp = (double)pr.y;
                 const double rad = v.radius * hp;

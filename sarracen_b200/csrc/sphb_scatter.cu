@@ -44,25 +44,20 @@ struct Box {
     int x0, x1, y0, y1, z0, z1; // pixel ranges [lo, hi)
 };
 
-// Support box of particle i in raster pixels; false if it touches no pixel (or is degenerate:
+// Support box of a particle in raster pixels; false if it touches no pixel (or is degenerate:
 // h <= 0 or non-finite input -- such particles contribute nothing).
-template <typename T>
-__device__ __forceinline__ bool particle_box(const View &v, const T *x, const T *y, const T *z, const T *h,
-                                             int64_t i, Box &b)
+__device__ __forceinline__ bool particle_box(const View &v, double xp, double yp, double zp, double hp, Box &b)
 {
-    const double hp = (double)__ldg(h + i);
-    const double xp = (double)__ldg(x + i), yp = (double)__ldg(y + i);
     if (!(hp > 0.0) || !isfinite(hp) || !isfinite(xp) || !isfinite(yp)) return false;
     const double rad = v.radius * hp;
     b.z0 = 0;
     b.z1 = 1;
     if (v.dim3) {
-        const double zp = (double)__ldg(z + i);
         if (!isfinite(zp)) return false;
         pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, b.z0, b.z1);
         if (b.z1 <= b.z0) return false;
     } else if (v.use_z) {
-        const double dz = v.z_slice - (double)__ldg(z + i);
+        const double dz = v.z_slice - zp;
         if (!(fabs(dz) < rad)) return false; // cpu_backend.py:264
     }
     pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, b.x0, b.x1);
@@ -118,7 +113,10 @@ count_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, 
     const int64_t n_up = (n + 31) / 32 * 32; // whole warps stay in the loop (match_any below)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += stride) {
         Box b;
-        const bool seen = i < n && particle_box(v, x, y, z, h, i, b);
+        bool seen = false;
+        if (i < n)
+            seen = particle_box(v, (double)__ldg(x + i), (double)__ldg(y + i),
+                                (v.dim3 || v.use_z) ? (double)__ldg(z + i) : 0.0, (double)__ldg(h + i), b);
         const int edge = seen ? box_edge(b) : 0;
         const bool small = seen && edge <= v.small_edge;
         // histogram of the small particles by cell, one atomic per distinct cell and warp
@@ -163,117 +161,146 @@ count_kernel(View v, const T *x, const T *y, const T *z, const T *h, int64_t n, 
 }
 
 template <typename T>
-__device__ __forceinline__ void write_rec(const View &v, T *r, const T *x, const T *y, const T *z, const T *h,
-                                          const T *w0, const T *w1, const T *w2, const T *w3, int nw, int64_t i)
+__device__ __forceinline__ void write_rec(const View &v, T *r, T xv, T yv, T zv, T hv, const T *w0, const T *w1,
+                                          const T *w2, const T *w3, int nw, int64_t i)
 {
-    // packed record, written as 16-byte vectors (a scalar store per field touched every
-    // 32-byte sector of the record array 4-8 times)
+    // whole 32-byte sectors, one 256-bit store each (see Rec)
     T f[8] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
-    f[0] = x[i];
-    f[1] = y[i];
-    f[2] = h[i];
+    f[0] = xv;
+    f[1] = yv;
+    f[2] = hv;
     if (v.rec_stride == 4) {
-        f[3] = w0[i];
+        f[3] = __ldg(w0 + i);
     } else {
-        f[3] = z ? z[i] : T(0);
-        f[4] = w0[i];
-        f[5] = nw > 1 ? w1[i] : T(0);
-        f[6] = (v.rec_stride == 8 && nw > 2) ? w2[i] : T(0);
-        f[7] = (v.rec_stride == 8 && nw > 3) ? w3[i] : T(0);
+        f[3] = zv;
+        f[4] = __ldg(w0 + i);
+        f[5] = nw > 1 ? __ldg(w1 + i) : T(0);
+        f[6] = nw > 2 ? __ldg(w2 + i) : T(0);
+        f[7] = nw > 3 ? __ldg(w3 + i) : T(0);
     }
-    if (sizeof(T) == 8) {
-        double2 *q = reinterpret_cast<double2 *>(r);
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (2 * k < v.rec_stride) q[k] = make_double2((double)f[2 * k], (double)f[2 * k + 1]);
-    } else {
-        float4 *q = reinterpret_cast<float4 *>(r);
-#pragma unroll
-        for (int k = 0; k < 2; k++)
-            if (4 * k < v.rec_stride)
-                q[k] = make_float4((float)f[4 * k], (float)f[4 * k + 1], (float)f[4 * k + 2], (float)f[4 * k + 3]);
-    }
+    stg256(r, f);
+    if (sizeof(T) == 8 && v.rec_stride == 8) stg256(r + 4, f + 4);
 }
 
 // Pairs of one particle are written by its own lane up to this many; a particle that covers
 // more tiles (h >> tile: up to every tile of the raster) is written by the whole warp.
 constexpr uint32_t kOwnPairs = 16;
 
+// Particles per thread of the emit kernel: their column loads, and then their cell-cursor atomics,
+// are issued back to back, so that several global round trips are in flight per thread (with
+// one particle per thread the kernel sat at 15 % issue utilisation waiting for them).
+constexpr int kEmitPer = 4;
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0, const T *w1, const T *w2,
             const T *w3, int nw, int64_t n, const uint32_t *cell_start, uint32_t *cell_cursor,
             unsigned long long *totals, uint32_t *keys, uint32_t *vals, T *recs_large, T *recs_small,
-            int64_t n_pairs, int64_t n_small)
+            int64_t n_pairs, int64_t n_small, int dbg_mode)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // whole warps: n is rounded up by the grid
-    Box b;
-    const bool seen = i < n && particle_box(v, x, y, z, h, i, b);
-    const bool small = seen && box_edge(b) <= v.small_edge;
-
+    // whole warps: the grid rounds n up; particle k of this thread is base + 256 k (coalesced columns)
+    const int64_t base = (int64_t)blockIdx.x * (256 * kEmitPer) + threadIdx.x;
+    const bool has_z = v.dim3 || v.use_z;
+    T xs[kEmitPer], ys[kEmitPer], zs[kEmitPer], hs[kEmitPer];
+#pragma unroll
+    for (int k = 0; k < kEmitPer; k++) {
+        const int64_t i = base + 256 * k;
+        const bool in = i < n;
+        xs[k] = in ? __ldg(x + i) : T(0);
+        ys[k] = in ? __ldg(y + i) : T(0);
+        zs[k] = (in && has_z) ? __ldg(z + i) : T(0);
+        hs[k] = in ? __ldg(h + i) : T(0); // h = 0: not seen
+    }
+    Box b[kEmitPer];
+    bool seen[kEmitPer], small[kEmitPer];
+    uint32_t key[kEmitPer], slot[kEmitPer], start[kEmitPer];
+    unsigned peers[kEmitPer];
+#pragma unroll
+    for (int k = 0; k < kEmitPer; k++) {
+        seen[k] = particle_box(v, (double)xs[k], (double)ys[k], (double)zs[k], (double)hs[k], b[k]);
+        small[k] = seen[k] && box_edge(b[k]) <= v.small_edge;
+        key[k] = small[k] ? box_cell(v, b[k]) : (0x80000000u | (uint32_t)lane);
+    }
     // ---- small: final position in the cell-ordered record stream ------------------------
-    const uint32_t key = small ? box_cell(v, b) : (0x80000000u | (uint32_t)lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    uint32_t slot = 0;
-    const int leader = __ffs(peers) - 1;
-    if (small && lane == leader) slot = atomicAdd(cell_cursor + key, (uint32_t)__popc(peers));
-    slot = __shfl_sync(0xffffffffu, slot, leader);
-    if (small) {
-        const int64_t pos = (int64_t)__ldg(cell_start + key) + slot + __popc(peers & ((1u << lane) - 1u));
-        SPHB_ASSERT(pos < n_small);
-        write_rec<T>(v, recs_small + (size_t)pos * v.rec_stride, x, y, z, h, w0, w1, w2, w3, nw, i);
+#pragma unroll
+    for (int k = 0; k < kEmitPer; k++) {
+        peers[k] = __match_any_sync(0xffffffffu, key[k]);
+        slot[k] = 0;
+        start[k] = 0;
+        if (small[k]) {
+            if (lane == __ffs(peers[k]) - 1 && dbg_mode != 1)
+                slot[k] = atomicAdd(cell_cursor + key[k], (uint32_t)__popc(peers[k]));
+            start[k] = __ldg(cell_start + key[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kEmitPer; k++) {
+        slot[k] = __shfl_sync(0xffffffffu, slot[k], __ffs(peers[k]) - 1);
+        if (small[k]) {
+            int64_t pos = (int64_t)start[k] + slot[k] + __popc(peers[k] & ((1u << lane) - 1u));
+            if (dbg_mode == 1) pos = (int64_t)(((uint64_t)(base + 256 * k) * 2654435761ull) % (uint64_t)n_small);
+            if (dbg_mode == 3) pos = (base + 256 * k) % n_small;
+            SPHB_ASSERT(pos < n_small);
+            if (dbg_mode != 2)
+            write_rec<T>(v, recs_small + (size_t)pos * v.rec_stride, xs[k], ys[k], zs[k], hs[k], w0, w1, w2, w3, nw,
+                         base + 256 * k);
+        }
     }
 
     // ---- large: (tile, particle) pairs ----------------------------------------------------
-    const bool large = seen && !small;
-    TileBox t = {0, 0, 0, 0, 0, 0};
-    uint32_t c = 0;
-    if (large) {
-        t = box_tiles(v, b);
-        c = tile_count(t);
-        write_rec<T>(v, recs_large + (size_t)i * v.rec_stride, x, y, z, h, w0, w1, w2, w3, nw, i);
-    }
-    if (!__any_sync(0xffffffffu, large)) return;
-    // the warp claims one range of the list: exclusive scan of the counts + one atomic
-    unsigned long long incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-    }
-    unsigned long long base = 0;
-    if (lane == 31) base = atomicAdd(totals + kTotCursor, incl);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    const uint64_t o0 = base + incl - c;
-    if (large && c <= kOwnPairs) {
-        uint64_t o = o0;
-        for (int tz = t.z0; tz <= t.z1; tz++)
-            for (int ty = t.y0; ty <= t.y1; ty++)
-                for (int tx = t.x0; tx <= t.x1; tx++) {
-                    SPHB_ASSERT((int64_t)o < n_pairs && tx < v.ntx && ty < v.nty && tz < v.ntz);
-                    keys[o] = (uint32_t)((tz * v.nty + ty) * v.ntx + tx);
-                    vals[o] = (uint32_t)i;
-                    o++;
-                }
-    }
-    unsigned wide = __ballot_sync(0xffffffffu, large && c > kOwnPairs);
-    while (wide) {
-        const int src = __ffs(wide) - 1;
-        wide &= wide - 1;
-        const uint64_t ob = __shfl_sync(0xffffffffu, o0, src);
-        const uint32_t cc = __shfl_sync(0xffffffffu, c, src);
-        const int tx0 = __shfl_sync(0xffffffffu, t.x0, src), ty0 = __shfl_sync(0xffffffffu, t.y0, src);
-        const int tz0 = __shfl_sync(0xffffffffu, t.z0, src);
-        const int nx_ = __shfl_sync(0xffffffffu, t.x1, src) - tx0 + 1;
-        const int ny_ = __shfl_sync(0xffffffffu, t.y1, src) - ty0 + 1;
-        const uint32_t pid = (uint32_t)__shfl_sync(0xffffffffu, (unsigned long long)i, src);
-        for (uint32_t e = lane; e < cc; e += 32) {
-            const uint32_t tz = e / (uint32_t)(nx_ * ny_), r = e - tz * (uint32_t)(nx_ * ny_);
-            const uint32_t ty = r / (uint32_t)nx_, tx = r - ty * (uint32_t)nx_;
-            SPHB_ASSERT((int64_t)(ob + e) < n_pairs);
-            keys[ob + e] = (uint32_t)(((tz0 + tz) * v.nty + (ty0 + ty)) * v.ntx + (tx0 + tx));
-            vals[ob + e] = pid;
+    for (int k = 0; k < kEmitPer; k++) {
+        const int64_t i = base + 256 * k;
+        const bool large = seen[k] && !small[k];
+        if (!__any_sync(0xffffffffu, large)) continue;
+        TileBox t = {0, 0, 0, 0, 0, 0};
+        uint32_t c = 0;
+        if (large) {
+            t = box_tiles(v, b[k]);
+            c = tile_count(t);
+            write_rec<T>(v, recs_large + (size_t)i * v.rec_stride, xs[k], ys[k], zs[k], hs[k], w0, w1, w2, w3, nw, i);
+        }
+        // the warp claims one range of the list: exclusive scan of the counts + one atomic
+        unsigned long long incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        unsigned long long first = 0;
+        if (lane == 31) first = atomicAdd(totals + kTotCursor, incl);
+        first = __shfl_sync(0xffffffffu, first, 31);
+        const uint64_t o0 = first + incl - c;
+        if (large && c <= kOwnPairs) {
+            uint64_t o = o0;
+            for (int tz = t.z0; tz <= t.z1; tz++)
+                for (int ty = t.y0; ty <= t.y1; ty++)
+                    for (int tx = t.x0; tx <= t.x1; tx++) {
+                        SPHB_ASSERT((int64_t)o < n_pairs && tx < v.ntx && ty < v.nty && tz < v.ntz);
+                        keys[o] = (uint32_t)((tz * v.nty + ty) * v.ntx + tx);
+                        vals[o] = (uint32_t)i;
+                        o++;
+                    }
+        }
+        unsigned wide = __ballot_sync(0xffffffffu, large && c > kOwnPairs);
+        while (wide) {
+            const int src = __ffs(wide) - 1;
+            wide &= wide - 1;
+            const uint64_t ob = __shfl_sync(0xffffffffu, o0, src);
+            const uint32_t cc = __shfl_sync(0xffffffffu, c, src);
+            const int tx0 = __shfl_sync(0xffffffffu, t.x0, src), ty0 = __shfl_sync(0xffffffffu, t.y0, src);
+            const int tz0 = __shfl_sync(0xffffffffu, t.z0, src);
+            const int nx_ = __shfl_sync(0xffffffffu, t.x1, src) - tx0 + 1;
+            const int ny_ = __shfl_sync(0xffffffffu, t.y1, src) - ty0 + 1;
+            const uint32_t pid = (uint32_t)__shfl_sync(0xffffffffu, (unsigned long long)i, src);
+            for (uint32_t e = lane; e < cc; e += 32) {
+                const uint32_t tz = e / (uint32_t)(nx_ * ny_), r = e - tz * (uint32_t)(nx_ * ny_);
+                const uint32_t ty = r / (uint32_t)nx_, tx = r - ty * (uint32_t)nx_;
+                SPHB_ASSERT((int64_t)(ob + e) < n_pairs);
+                keys[ob + e] = (uint32_t)(((tz0 + tz) * v.nty + (ty0 + ty)) * v.ntx + (tx0 + tx));
+                vals[ob + e] = pid;
+            }
         }
     }
 }
@@ -395,17 +422,19 @@ static int small_edge_setting(bool dim3, bool f32)
     return cap;
 }
 
-// Cell size (log2) of the small-footprint path: the largest of 32 / 16 (images) or 8 / 4 (grids)
-// for which a warp's accumulator, at the largest admissible box edge, stays below 28 KB.
+// Cell size (log2) of the small-footprint path.  Images: 32 x 32 pixels (16 x 16 with three or four
+// weights in double).  Grids: 4 x 4 x 4 voxels -- with 8 x 8 x 8 a warp's accumulator is 14-27 KB
+// and only 8-13 warps fit on an SM; 4 x 4 x 4 (4 KB at the 5-voxel boxes of BASELINE config 4)
+// runs 16 register-rich warps: 53 -> 43 ms there, although it flushes 8 instead of 3.4
+// reductions per voxel.
 static int cell_log(bool dim3, bool f32, int nw, int small_edge)
 {
+    const char *e = getenv("SPHB_CELL_LOG");
+    if (e && *e) return std::min(std::max(atoi(e), 1), 5);
+    if (dim3) return 2;
     const size_t elem = f32 ? 4 : 8;
-    for (int lg = dim3 ? 3 : 5; lg > (dim3 ? 2 : 4); lg--) {
-        const size_t s = (size_t)(1 << lg) + (small_edge > 0 ? small_edge - 1 : 0);
-        const size_t bytes = (dim3 ? s * s * s : s * s) * elem * nw;
-        if (bytes <= 28 * 1024) return lg;
-    }
-    return dim3 ? 2 : 4;
+    const size_t s = 32 + (small_edge > 0 ? small_edge - 1 : 0);
+    return s * s * elem * nw <= 28 * 1024 ? 5 : 4;
 }
 
 static int validate(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
@@ -505,7 +534,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     v.ndim = k->ndim;
     v.norm = kernel_norm(k->kind, k->ndim);
     v.small_edge = small_edge_setting(dim3, f32);
-    v.rec_stride = (!dim3 && !use_z && p->n_weights == 1) ? 4 : (sizeof(T) == 8 && p->n_weights <= 2) ? 6 : 8;
+    v.rec_stride = rec_stride_for(f32, dim3 || use_z, p->n_weights);
     const int clog = cell_log(dim3, f32, p->n_weights, v.small_edge);
     v.cx_log = v.cy_log = clog;
     v.cz_log = dim3 ? clog : 0;
@@ -630,10 +659,11 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
                   (long long)n_pairs, (long long)n_small, ws_bytes);
         return SPHB_ERR_WORKSPACE;
     }
-    emit_kernel<T><<<blocks, 256, 0, stream>>>(
+    emit_kernel<T><<<div_up(n, 256 * kEmitPer), 256, 0, stream>>>(
         v, x, y, z, h, static_cast<const T *>(p->w[0]), static_cast<const T *>(p->w[1]),
         static_cast<const T *>(p->w[2]), static_cast<const T *>(p->w[3]), p->n_weights, n, cell_start, cell_cursor,
-        totals, keys_a, vals_a, recs_large, recs_small, n_pairs, n_small);
+        totals, keys_a, vals_a, recs_large, recs_small, n_pairs, n_small,
+        getenv("SPHB_EMIT_MODE") ? atoi(getenv("SPHB_EMIT_MODE")) : 0);
     SPHB_LAUNCH_CHECK();
     if (timed) SPHB_CUDA(cudaEventRecord(ev[1], stream));
     if (n_pairs > 0) {

@@ -36,7 +36,7 @@ def _kernel(kind):
 
 def test_library_is_loaded():
     from sarracen_b200 import _lib
-    assert _lib.load().sphb_version() == 100
+    assert _lib.load().sphb_version() == _lib.SPHB_VERSION
 
 
 def test_column_table_on_device():
