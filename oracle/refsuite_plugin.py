@@ -15,15 +15,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# Reference tests that assert BIT-EXACT equality with the CPU formula on a single-contribution
-# pixel.  The B200 path folds the kernel normalisation into the per-particle term and
-# takes the double square root as MUFU.RSQ64H + one Goldschmidt step (relative error <= 1.6e-12),
-# so these may differ from the reference's value in the last bits; they hold to 1e-12 instead
-# (restated with that tolerance in tests/test_gpu_reference_suite.py).  Listed here so that a
-# last-bit difference is reported as xfail, not as a failure; everything else must pass.
-BIT_EXACT = ("test_default_kernel", "test_column_samples", "test_density_weighted",
-             "test_normalize_interpolation", "test_minimum_smoothing_length_2d",
-             "test_minimum_smoothing_length_3d", "test_minimum_smoothing_length_1d_lines")
+# Reference tests that assert ARRAY-EXACT equality of two multi-particle renders (hmin on / h clamped by
+# hand, test_interpolate.py:1420-1563).  The B200 path adds tile / cell partial sums with
+# red.global.add.f64, whose arrival order is not fixed, so two runs agree to rounding, not always
+# bit for bit (like the reference's own thread-count dependence).  They pass in practice
+# (70 of 70 instances on the B200, profiles/r2_reference_suite_gpu.txt); marked non-strict xfail so that
+# a last-bit difference is reported as such.  Every other test -- including the bit-exact
+# single-contribution ones (test_default_kernel, test_column_samples, test_density_weighted,
+# test_normalize_interpolation) -- must pass.
+BIT_EXACT = ("test_minimum_smoothing_length_2d", "test_minimum_smoothing_length_3d",
+             "test_minimum_smoothing_length_1d_lines")
 
 
 def pytest_configure(config):
@@ -45,7 +46,7 @@ def pytest_collection_modifyitems(config, items):
         (keep if params.get("backend") == "gpu" else drop).append(it)
     for it in keep:
         if it.originalname in BIT_EXACT:
-            it.add_marker(pytest.mark.xfail(reason="bit-exact comparison with the CPU formula (see plugin header)",
+            it.add_marker(pytest.mark.xfail(reason="array-exact comparison of two multi-particle renders (see plugin header)",
                                             strict=False))
     if drop:
         config.hook.pytest_deselected(items=drop)

@@ -121,8 +121,11 @@ def test_real_frontend_2d_and_exact_on_gpu():
     kw = dict(x_pixels=64, y_pixels=48, xlim=(0, 1), ylim=(0, 1))
     assert_parity(front.interpolate_2d(sdf, "A", backend="gpu", **kw),
                   front.interpolate_2d(sdf, "A", backend="cpu", **kw), 1e-10, "interpolate_2d")
-    assert_parity(front.interpolate_2d(sdf, "A", exact=True, backend="gpu", **kw),
-                  front.interpolate_2d(sdf, "A", exact=True, backend="cpu", **kw), 1e-10, "interpolate_2d exact")
+    # exact: without the normalisation pass (outside the particles' supports both backends hold only
+    # the rounding residue of cancelling edge integrals, and the ratio of two residues is noise)
+    assert_parity(front.interpolate_2d(sdf, "A", exact=True, normalize=False, backend="gpu", **kw),
+                  front.interpolate_2d(sdf, "A", exact=True, normalize=False, backend="cpu", **kw), 1e-10,
+                  "interpolate_2d exact")
     assert_parity(front.interpolate_2d_line(sdf, "A", pixels=128, backend="gpu"),
                   front.interpolate_2d_line(sdf, "A", pixels=128, backend="cpu"), 1e-10, "interpolate_2d_line")
     # our own front-end fed with the reference's data frame and kernel objects (numba dispatchers)

@@ -39,5 +39,6 @@ def test_reference_interpolate_suite_through_backend_gpu(tmp_path):
     errors = int((re.search(r"(\d+) error", summary) or [0, 0])[1])
     assert res.returncode == 0 and failed == 0 and errors == 0, tail
     # 64 backend=gpu instances in test_interpolate.py (test_pixel_arguments is cpu-only) and 6 in
-    # test_rotation.py; only the bit-exact ones may xfail
-    assert passed >= 40, tail
+    # test_rotation.py; only the three array-exact hmin tests may xfail
+    xpassed = int((re.search(r"(\d+) xpassed", summary) or [0, 0])[1])
+    assert passed + xpassed >= 67 and passed >= 64, tail
