@@ -20,7 +20,7 @@ from typing import Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, parallel
 from .kernels import WeightFunction
 
 _RADIUS_KIND = {2.0: "cubic", 2.5: "quartic", 3.0: "quintic"}
@@ -281,20 +281,42 @@ def _host(t: torch.Tensor) -> np.ndarray:
     return t.cpu().numpy()
 
 
+def _shard(arrays):
+    """Multi-GPU mode (sarracen_b200.parallel.enable): this rank's slice of the columns."""
+    mode = parallel.active()
+    if mode is None:
+        return list(arrays), None
+    return parallel.shard_columns([a if isinstance(a, torch.Tensor) else np.asarray(a) for a in arrays], mode), mode
+
+
+def _images(rasters, mode):
+    """Device rasters of one call -> host arrays; in multi-GPU mode summed over the ranks first
+    (all components packed into one collective)."""
+    rasters = list(rasters)
+    if mode is not None:
+        rasters = parallel.finish_images(rasters, mode)
+    return [_host(r) for r in rasters]
+
+
 class B200Backend:
-    """SPH interpolation on a B200 behind Sarracen's backend interface."""
+    """SPH interpolation on a B200 behind Sarracen's backend interface.
+
+    With `sarracen_b200.parallel.enable()` (one process per GPU under torch.distributed) every
+    method renders this rank's shard of the particles and combines the partial rasters over NCCL:
+    all ranks pass the same columns and receive the combined result."""
 
     @staticmethod
     def interpolate_2d_render(x, y, weight, h, weight_function, kernel_radius, x_pixels, y_pixels,
                               x_min, x_max, y_min, y_max, exact) -> np.ndarray:
         dev = _device()
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
+        (x, y, weight, h), mode = _shard([x, y, weight, h])
         if exact:
             xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
-            return _host(ops.exact2d(xd, yd, hd, [wd], r)[0])
+            return _images(ops.exact2d(xd, yd, hd, [wd], r), mode)[0]
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
-            c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc))[0])
+        return _images(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc)), mode)[0]
 
     @staticmethod
     def interpolate_2d_render_vec(x, y, weight_x, weight_y, h, weight_function, kernel_radius, x_pixels,
@@ -302,42 +324,46 @@ class B200Backend:
                                   exact) -> Tuple[np.ndarray, np.ndarray]:
         dev = _device()
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
+        (x, y, weight_x, weight_y, h), mode = _shard([x, y, weight_x, weight_y, h])
         if exact:
             xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
-            a, b = ops.exact2d(xd, yd, hd, [wx, wy], r)
+            a, b = _images(ops.exact2d(xd, yd, hd, [wx, wy], r), mode)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
-            a, b = streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
-                c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc))
-        return _host(a), _host(b)
+            a, b = _images(streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+                c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc)), mode)
+        return a, b
 
     @staticmethod
     def interpolate_2d_line(x, y, weight, h, weight_function, kernel_radius, pixels, x1, x2, y1,
                             y2) -> np.ndarray:
         dev = _device()
+        (x, y, weight, h), mode = _shard([x, y, weight, h])
         xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(ops.line2d(xd, yd, hd, [wd], wf, kernel_radius, pixels, x1, x2, y1, y2)[0])
+        return _images(ops.line2d(xd, yd, hd, [wd], wf, kernel_radius, pixels, x1, x2, y1, y2), mode)[0]
 
     @staticmethod
     def interpolate_3d_line(x, y, z, weight, h, weight_function, kernel_radius, pixels, x1, x2, y1, y2,
                             z1, z2) -> np.ndarray:
         dev = _device()
+        (x, y, z, weight, h), mode = _shard([x, y, z, weight, h])
         xd, yd, zd, wd, hd = _to_device([x, y, z, weight, h], dev)
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(ops.line3d(xd, yd, zd, hd, [wd], wf, kernel_radius, pixels, x1, x2, y1, y2, z1, z2)[0])
+        return _images(ops.line3d(xd, yd, zd, hd, [wd], wf, kernel_radius, pixels, x1, x2, y1, y2, z1, z2), mode)[0]
 
     @staticmethod
     def interpolate_3d_projection(x, y, weight, h, weight_function, kernel_radius, x_pixels, y_pixels,
                                   x_min, x_max, y_min, y_max, exact) -> np.ndarray:
         dev = _device()
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
+        (x, y, weight, h), mode = _shard([x, y, weight, h])
         if exact:
             xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
-            return _host(ops.exact3d_proj(xd, yd, hd, [wd], r)[0])
+            return _images(ops.exact3d_proj(xd, yd, hd, [wd], r), mode)[0]
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
-            c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc))[0])
+        return _images(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc)), mode)[0]
 
     @staticmethod
     def interpolate_3d_projection_vec(x, y, weight_x, weight_y, h, weight_function, kernel_radius,
@@ -345,14 +371,15 @@ class B200Backend:
                                       exact) -> Tuple[np.ndarray, np.ndarray]:
         dev = _device()
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
+        (x, y, weight_x, weight_y, h), mode = _shard([x, y, weight_x, weight_y, h])
         if exact:
             xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
-            a, b = ops.exact3d_proj(xd, yd, hd, [wx, wy], r)
+            a, b = _images(ops.exact3d_proj(xd, yd, hd, [wx, wy], r), mode)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
-            a, b = streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
-                c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc))
-        return _host(a), _host(b)
+            a, b = _images(streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+                c[0], c[1], c[4], [c[2], c[3]], wf, kernel_radius, 2, r, out=out, accumulate=acc)), mode)
+        return a, b
 
     @staticmethod
     def interpolate_3d_cross(x, y, z, z_slice, weight, h, weight_function, kernel_radius, x_pixels,
@@ -361,8 +388,10 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
         zs = float(z_slice)
-        return _host(streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter2d(
-            c[0], c[1], c[4], [c[3]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc))[0])
+        (x, y, z, weight, h), mode = _shard([x, y, z, weight, h])
+        return _images(streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[4], [c[3]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc)),
+            mode)[0]
 
     @staticmethod
     def interpolate_3d_cross_vec(x, y, z, z_slice, weight_x, weight_y, h, weight_function, kernel_radius,
@@ -372,9 +401,11 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
         zs = float(z_slice)
-        a, b = streamed_scatter([x, y, z, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
-            c[0], c[1], c[5], [c[3], c[4]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc))
-        return _host(a), _host(b)
+        (x, y, z, weight_x, weight_y, h), mode = _shard([x, y, z, weight_x, weight_y, h])
+        a, b = _images(streamed_scatter([x, y, z, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
+            c[0], c[1], c[5], [c[3], c[4]], wf, kernel_radius, 3, r, z=c[2], z_slice=zs, out=out, accumulate=acc)),
+            mode)
+        return a, b
 
     @staticmethod
     def interpolate_3d_grid(x, y, z, weight, h, weight_function, kernel_radius, x_pixels, y_pixels,
@@ -382,8 +413,26 @@ class B200Backend:
         dev = _device()
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max, z_pixels, z_min, z_max)
         wf = resolve_weight_function(weight_function, kernel_radius)
-        return _host(streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter3d(
-            c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r, out=out, accumulate=acc))[0])
+        (x, y, z, weight, h), mode = _shard([x, y, z, weight, h])
+        if mode is None:
+            return _host(streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter3d(
+                c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r, out=out, accumulate=acc))[0])
+        # multi-GPU: this rank's shard -> partial grid, summed along z onto the slab owners.  A shard that
+        # goes up in one piece is rendered slab by slab with the reduction of each finished slab overlapping
+        # the render of the next ones; a shard streamed in chunks adds to every slab until its last chunk,
+        # so its reduction starts when the render is over.
+        cols = _host_columns([x, y, z, weight, h])
+        if cols is None or cols[0].numel() < _STREAM_MIN:
+            c = _to_device([x, y, z, weight, h], dev)
+            slab = parallel.scatter3d_sharded(c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r,
+                                              group=mode.group)[0]
+        else:
+            part = streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter3d(
+                c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r, out=out, accumulate=acc))[0]
+            slab = parallel.reduce_along_z(part, mode.group)
+        if mode.grids == "slab":
+            return _host(slab)
+        return _host(parallel.gather_slabs(slab, int(z_pixels), mode))
 
 
 def install() -> None:

@@ -50,13 +50,18 @@ def _rank(group=None) -> int:
     return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
 
 
+def _global(group, k: int) -> int:
+    """Global rank of rank k of `group` (torch.distributed addresses dst / src by global rank)."""
+    return k if group is None else dist.get_global_rank(group, k)
+
+
 def combine_image(img: torch.Tensor, dst: Optional[int] = 0, group=None) -> torch.Tensor:
     """Sum the partial images onto rank `dst` (valid there only); dst=None: onto every rank."""
     if _world(group) > 1:
         if dst is None:
             dist.all_reduce(img, op=dist.ReduceOp.SUM, group=group)
         else:
-            dist.reduce(img, dst=dst, op=dist.ReduceOp.SUM, group=group)
+            dist.reduce(img, dst=_global(group, dst), op=dist.ReduceOp.SUM, group=group)
     return img
 
 
@@ -90,7 +95,7 @@ def combine_grid_along_z(grid: torch.Tensor, slab: torch.Tensor, group=None) -> 
             klo, khi = slab_range(grid.shape[0], k, world)
             if khi > klo:
                 part = grid[klo:khi].clone() if not grid.is_cuda else grid[klo:khi]
-                dist.reduce(part, dst=k, op=dist.ReduceOp.SUM, group=group)
+                dist.reduce(part, dst=_global(group, k), op=dist.ReduceOp.SUM, group=group)
                 if k == _rank(group):
                     slab.copy_(part)
     return slab
@@ -115,7 +120,8 @@ def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=
         if world > 1:
             for k, (lo, hi) in enumerate(bounds):
                 for o in out:
-                    works.append(dist.reduce(o[lo:hi], dst=k, op=dist.ReduceOp.SUM, group=group, async_op=True))
+                    works.append(dist.reduce(o[lo:hi], dst=_global(group, k), op=dist.ReduceOp.SUM, group=group,
+                                                 async_op=True))
     else:
         dev = x.device
         main = torch.cuda.current_stream(dev)
@@ -147,7 +153,7 @@ def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=
                 side.wait_event(events[k])
                 for o in out:
                     if hi > lo:
-                        works.append(dist.reduce(o[lo:hi], dst=k, op=dist.ReduceOp.SUM, group=group,
+                        works.append(dist.reduce(o[lo:hi], dst=_global(group, k), op=dist.ReduceOp.SUM, group=group,
                                                  async_op=True))
     for w in works:
         w.wait()   # the current stream waits for the NCCL stream
@@ -158,6 +164,20 @@ def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=
             s.copy_(m)
         return list(slabs)
     return mine
+
+
+def reduce_along_z(grid: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum a finished (nz, ny, nx) partial grid along z onto the slab owners (one reduce per slab, in
+    place); returns this rank's slab as a view of `grid`."""
+    world, rank = _world(group), _rank(group)
+    bounds = [slab_range(grid.shape[0], k, world) for k in range(world)]
+    if world > 1:
+        works = [dist.reduce(grid[lo:hi], dst=_global(group, k), op=dist.ReduceOp.SUM, group=group, async_op=True)
+                 for k, (lo, hi) in enumerate(bounds) if hi > lo]
+        for w in works:
+            w.wait()
+    lo, hi = bounds[rank]
+    return grid[lo:hi]
 
 
 _side_streams = {}
@@ -235,5 +255,5 @@ def gather_slabs(slab: torch.Tensor, nz: int, mode: _Mode) -> torch.Tensor:
         for k, p in enumerate(parts):   # unequal slabs: one broadcast per owner
             if k == _rank(mode.group):
                 p.copy_(slab)
-            dist.broadcast(p, src=k, group=mode.group)
+            dist.broadcast(p, src=_global(mode.group, k), group=mode.group)
     return full

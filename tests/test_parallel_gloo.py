@@ -41,6 +41,25 @@ def _worker(rank, world, port, q):
         q.put(("img", float(np.abs(img.numpy() - full).max() / np.abs(full).max())))
     gfull = OracleBackend.interpolate_3d_grid(x, y, z, w, h, k, 2, 10, 9, 8, 0, 1, 0, 1, 0, 1)
     q.put((f"slab{rank}", float(np.abs(slab.numpy() - gfull[zl:zh]).max() / np.abs(gfull).max())))
+    # the pieces of the backend's multi-GPU mode that do not need a device: in-place reduction along z with
+    # UNEQUAL slabs (nz = 9 over 2 ranks), gathering the slabs, packed images on every rank
+    from sarracen_b200 import parallel
+    g9 = OracleBackend.interpolate_3d_grid(x[lo:hi], y[lo:hi], z[lo:hi], w[lo:hi], h[lo:hi], k, 2, 6, 5, 9,
+                                           0, 1, 0, 1, 0, 1)
+    f9 = OracleBackend.interpolate_3d_grid(x, y, z, w, h, k, 2, 6, 5, 9, 0, 1, 0, 1, 0, 1)
+    parallel.enable(images="all", grids="all")
+    mode = parallel.active()
+    mine = parallel.reduce_along_z(torch.from_numpy(g9.copy()))
+    l9, h9 = slab_range(9, rank, world)
+    whole = parallel.gather_slabs(mine.clone(), 9, mode)
+    imgs = parallel.finish_images([torch.from_numpy(part.copy()), torch.from_numpy(2.0 * part)], mode)
+    full = OracleBackend.interpolate_2d_render(x, y, w, h, k, 2, 24, 18, 0, 1, 0, 1, False)
+    q.put((f"mode{rank}", max(float(np.abs(mine.numpy() - f9[l9:h9]).max() / np.abs(f9).max()),
+                              float(np.abs(whole.numpy() - f9).max() / np.abs(f9).max()),
+                              float(np.abs(imgs[0].numpy() - full).max() / np.abs(full).max()),
+                              float(np.abs(imgs[1].numpy() - 2 * full).max() / np.abs(full).max()))))
+    assert [len(c) for c in parallel.shard_columns([x, y], mode)] == [hi - lo, hi - lo]
+    parallel.disable()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,6 +72,11 @@ def test_shard_ranges_cover_everything():
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
     assert slab_range(512, 3, 8) == (192, 256)
+    for nz in (1, 9, 512, 515):
+        for world in (1, 2, 8):
+            edges = [slab_range(nz, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == nz
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
 
 
 def test_two_rank_combine_matches_single_rank():
@@ -62,10 +86,10 @@ def test_two_rank_combine_matches_single_rank():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=120) for _ in range(3))
+    results = dict(q.get(timeout=120) for _ in range(5))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert set(results) == {"img", "slab0", "slab1"}
+    assert set(results) == {"img", "slab0", "slab1", "mode0", "mode1"}
     for name, err in results.items():
         assert err < 1e-13, (name, err)
