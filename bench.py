@@ -24,9 +24,9 @@ HBM; `e2e` times the reference-facing call `B200Backend.interpolate_3d_projectio
 PAGEABLE host NumPy arrays (what Sarracen's front-end passes), host<->device copies inside the
 timed region.  With N GPUs the SAME particle set is sharded by contiguous index range (strong
 scaling: total work fixed), every rank renders its shard into a full-size partial raster and the
-partial rasters are combined inside the timed region: NCCL reduce to rank 0 (images) or reduce
-along z, slab by slab, overlapped with the render of the following slabs (voxel grids,
-sarracen_b200/parallel.py).  `ms_collective` is the exchange timed on its own, `ms_compute` the
+partial rasters are combined inside the timed region: NCCL reduce to rank 0 (images) or NCCL
+reduce-scatter along z, issued per z-chunk and overlapped with the render of the following chunks
+(voxel grids, sarracen_b200/parallel.py).  `ms_collective` is the exchange timed on its own, `ms_compute` the
 step without it; `collective_hidden` = (ms_compute + ms_collective - ms_per_step) / ms_collective.
 
 `--impl reference` times the reference's own CPU implementation of the headline workload on the
@@ -377,7 +377,7 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
             render_only()
         elif dim3:
             parallel.scatter3d_sharded(devc["x"], devc["y"], devc["z"], devc["h"], [devc["w"]], wf, wl["radius"],
-                                       raster, out=out, slabs=[slab])
+                                       raster, out=out)
         else:
             render_only()
             collective_only()
@@ -532,7 +532,7 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
                    "l2": f"inputs larger than L2 ({n_local * wl['fields'] * itemsize / 1e6:.0f} MB of particle "
                          "columns per GPU per step)", "tile": tile, "pairs": n_pairs, "direct_particles": n_direct,
                    "parallelism": f"particle-sharded x{world} (fixed set, strong scaling)" + (
-                       "" if world == 1 else (", reduce along z slab by slab overlapped with the render" if dim3
+                       "" if world == 1 else (", NCCL reduce-scatter along z in 2 z-chunks overlapped with the render" if dim3
                                               else ", NCCL reduce to rank 0"))},
         "pixel_contributions": contrib, "contributions_per_s": contrib / (ms_step * 1e-3),
         "phases_ms": phases, "ms_step_with_phase_events": ms_phased,
@@ -545,7 +545,8 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
     }
     if world > 1:
         rec.update({"ms_compute": ms_compute, "ms_collective": ms_collective, "collective_hidden": hidden,
-                    "collective": "reduce to the slab owner, one per z-slab, on a second stream" if dim3
+                    "collective": "ncclReduceScatter along z per z-chunk (2 chunks) on NCCL's high-priority stream; "
+                                  "ms_collective times the monolithic reduce-scatter on its own" if dim3
                                   else "ncclReduce to rank 0"})
     if want_cpu:
         rec["cpu_baseline"] = cpu_sample(ctx["cpu"], wl, cols, budget_s=args.cpu_budget,
@@ -564,7 +565,11 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL on a high-priority stream: the reduction of a finished z-slab must get SMs while the
+        # render kernels of the next slabs keep the GPU full (sarracen_b200/parallel.py)
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     ctx = {"dev": dev, "world": world, "rank": rank}
     want_cpu = (not args.no_cpu) and world == 1   # rank 0 at N = 1 only
     if want_cpu:

@@ -425,11 +425,11 @@ class B200Backend:
         if cols is None or cols[0].numel() < _STREAM_MIN:
             c = _to_device([x, y, z, weight, h], dev)
             slab = parallel.scatter3d_sharded(c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r,
-                                              group=mode.group)[0]
+                                              group=mode.group, chunks=mode.chunks)[0]
         else:
             part = streamed_scatter([x, y, z, weight, h], dev, lambda c, out, acc: ops.scatter3d(
                 c[0], c[1], c[2], c[4], [c[3]], wf, kernel_radius, r, out=out, accumulate=acc))[0]
-            slab = parallel.reduce_along_z(part, mode.group)
+            slab = parallel.reduce_along_z(part, mode.group, mode.chunks)
         if mode.grids == "slab":
             return _host(slab)
         return _host(parallel.gather_slabs(slab, int(z_pixels), mode))

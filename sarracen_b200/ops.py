@@ -220,6 +220,9 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
         if staged and split and on_stage is not None:
             for s_done in range(n_stages):
                 on_stage(s_done)
+        if not staged and on_stage is not None and stage_planes is not None:
+            for s_done in range(len(stage_planes)):   # a single stage: the whole call
+                on_stage(s_done)
     last_stats.clear()
     last_stats.update(n_pairs=int(total_pairs), n_direct=int(total_direct), n_tiles=int(stats.n_tiles),
                       tile=(int(stats.tile_x), int(stats.tile_y), int(stats.tile_z)),

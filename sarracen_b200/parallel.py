@@ -8,14 +8,19 @@ a full-size partial raster, then the partial rasters are summed over NVLink / NV
   images        one `reduce` to a root rank (or `all_reduce` when every rank wants the picture);
                 the two components of a `_vec` call, or value + normalisation grid, travel packed
                 in ONE collective;
-  voxel grids   reduce along z: rank k owns z-planes slab_range(nz, k, G).  The render of a voxel
-                grid is issued slab by slab (`ops.scatter3d(..., stage_planes=...)`: the sorted
-                work list is z-major, so slab k is final as soon as stage k has run), and the
-                reduction of slab k onto rank k runs on NCCL's stream while slabs k+1.. are still
-                being rendered (`scatter3d_sharded`).  The monolithic form, one
-                `reduce_scatter_tensor` after the whole render, is `combine_grid_along_z`.
+  voxel grids   reduce-scatter along z, cut into C z-chunks.  The render of a voxel grid is issued
+                chunk by chunk (`ops.scatter3d(..., stage_planes=...)`: the sorted work lists are
+                z-major, so chunk c is final as soon as stage c has run), and the reduce-scatter of
+                chunk c runs on NCCL's stream while chunks c+1.. are still being rendered
+                (`scatter3d_sharded`).  Rank r then owns planes [r b, (r+1) b) of every chunk
+                (`owned_planes`: block-cyclic along z; C = 1 gives contiguous slabs).  The
+                monolithic form, one `reduce_scatter_tensor` after the whole render, is
+                `combine_grid_along_z`.
 
-One process per GPU, `torch.distributed` for the plumbing.  `enable()` switches the nine
+One process per GPU, `torch.distributed` for the plumbing.  Initialise the NCCL group with a
+high-priority stream (`opts = dist.ProcessGroupNCCL.Options(); opts.is_high_priority_stream = True;
+dist.init_process_group("nccl", pg_options=opts)`): the reduction of a finished slab only overlaps the
+render if its few CTAs get onto the SMs ahead of the queued render CTAs.  `enable()` switches the nine
 `B200Backend` methods (and with them `backend='gpu'` of Sarracen's own front-end) to this mode:
 every rank passes the SAME full columns, renders its shard and receives the combined result.
 """
@@ -101,83 +106,121 @@ def combine_grid_along_z(grid: torch.Tensor, slab: torch.Tensor, group=None) -> 
     return slab
 
 
-def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=None, slabs=None,
-                      group=None, overlap: bool = True) -> List[torch.Tensor]:
-    """Voxel grid of THIS rank's particle shard, combined along z: returns, per weight, this rank's
-    slab (planes slab_range(nz, rank, G)) of the sum over all ranks.
+DEFAULT_CHUNKS = 2
 
-    The render is issued in G stages, stage k finishing z-slab k; the reduction of slab k onto
-    its owner starts as soon as stage k is done and overlaps stages k+1.. (NCCL runs on its own
-    stream).  `out` are full-size float64 work grids (allocated if omitted), `slabs` optional
-    destination tensors; without them the returned slabs are views into `out`."""
+
+def z_chunks(nz: int, world: int, chunks: Optional[int] = None) -> int:
+    """Number of z-chunks the reduction along z is cut into: `chunks` (default DEFAULT_CHUNKS)
+    reduced until every chunk splits evenly over the ranks; 0 if not even one chunk does (then
+    the ranks own unequal contiguous slabs, see owned_planes)."""
+    c = DEFAULT_CHUNKS if chunks is None else int(chunks)
+    c = max(1, c)
+    while c > 1 and nz % (c * world):
+        c -= 1
+    return c if nz % (c * world) == 0 else 0
+
+
+def owned_planes(nz: int, rank: int, world: int, chunks: Optional[int] = None) -> List[int]:
+    """z-planes of the summed grid that end up on `rank`, in the order they are returned.
+
+    The reduction along z is a reduce-scatter PER Z-CHUNK (so that it can start as soon as that chunk
+    is rendered): with C = z_chunks(...) chunks of nz / C planes each, rank r receives planes
+    [r b, (r + 1) b) of every chunk, b = nz / (C G) -- a block-cyclic layout.  C = 1 is the plain
+    contiguous slab; when nz does not divide evenly the ranks own the contiguous slab_range()."""
+    c = z_chunks(nz, world, chunks)
+    if c == 0:
+        lo, hi = slab_range(nz, rank, world)
+        return list(range(lo, hi))
+    b = nz // (c * world)
+    return [k * (nz // c) + rank * b + i for k in range(c) for i in range(b)]
+
+
+def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=None, group=None,
+                      chunks: Optional[int] = None, overlap: bool = True) -> List[torch.Tensor]:
+    """Voxel grid of THIS rank's particle shard, summed over the ranks along z: returns, per weight,
+    a (len(owned_planes), ny, nx) tensor holding the planes owned_planes(nz, rank, G, chunks).
+
+    The render is issued in C z-chunk stages (`ops.scatter3d(stage_planes=...)`); as soon as chunk c
+    is final its `reduce_scatter` starts on NCCL's stream and overlaps the render of chunks c+1..;
+    only the last chunk's exchange (1 / C of the volume) is exposed.  Every reduce-scatter uses all
+    links at once, so the total exchange time is that of the monolithic collective.  `out` are
+    full-size float64 work grids (allocated if omitted)."""
     from . import ops
     world, rank = _world(group), _rank(group)
     nz = raster.nz
-    bounds = [slab_range(nz, k, world) for k in range(world)]
-    if world == 1 or not overlap:
+    c = z_chunks(nz, world, chunks)
+    if world == 1:
+        return ops.scatter3d(x, y, z, h, weights, weight_function, radius, raster, out=out)
+    if c == 0:
         out = ops.scatter3d(x, y, z, h, weights, weight_function, radius, raster, out=out)
-        works = []
-        if world > 1:
-            for k, (lo, hi) in enumerate(bounds):
-                for o in out:
-                    works.append(dist.reduce(o[lo:hi], dst=_global(group, k), op=dist.ReduceOp.SUM, group=group,
-                                                 async_op=True))
+        return [reduce_along_z(o, group, chunks) for o in out]
+    per, b = nz // c, nz // (c * world)
+    dev = x.device
+    nw = len(weights)
+    mine = [torch.empty((c * b,) + (raster.ny, raster.nx), dtype=torch.float64, device=dev) for _ in range(nw)]
+    works = []
+    if not overlap or c == 1:
+        out = ops.scatter3d(x, y, z, h, weights, weight_function, radius, raster, out=out)
+        for k in range(c):
+            for o, m in zip(out, mine):
+                works.append(dist.reduce_scatter_tensor(m[k * b:(k + 1) * b], o[k * per:(k + 1) * per],
+                                                        op=dist.ReduceOp.SUM, group=group, async_op=True))
     else:
-        dev = x.device
         main = torch.cuda.current_stream(dev)
-        events = [torch.cuda.Event() for _ in range(world)]
-        works = []
-
-        def after_stage(k):
-            # called by ops.scatter3d right after the kernels of stage k have been enqueued
-            events[k].record(main)
-
-        # The reductions are enqueued from a side stream that waits for stage k only, so the NCCL
-        # stream does not wait for the later stages (it synchronises with the stream current at the
-        # time of the call).
-        side = _side_stream(dev)
-        stage_planes = [hi for (_lo, hi) in bounds]
-        pending = []
+        events = [torch.cuda.Event() for _ in range(c)]
+        done = []
 
         def on_stage(k):
-            after_stage(k)
-            pending.append(k)
+            # called by ops.scatter3d right after the kernels of stage k have been enqueued
+            events[k].record(main)
+            done.append(k)
 
         out = ops.scatter3d(x, y, z, h, weights, weight_function, radius, raster, out=out,
-                            stage_planes=stage_planes, on_stage=on_stage)
-        # NCCL calls are issued after the launches (host side is asynchronous: all stages are in the
-        # stream queue by now and the events fire as the GPU gets there)
+                            stage_planes=[(k + 1) * per for k in range(c)], on_stage=on_stage)
+        # The collectives are enqueued from a side stream that waits for stage k only (NCCL's stream
+        # synchronises with the stream that is current at the time of the call, so from the main stream
+        # it would wait for every stage).  The host is far ahead of the GPU here: all stages are queued.
+        side = _side_stream(dev)
         with torch.cuda.stream(side):
-            for k in pending:
-                lo, hi = bounds[k]
+            for k in sorted(done):
                 side.wait_event(events[k])
-                for o in out:
-                    if hi > lo:
-                        works.append(dist.reduce(o[lo:hi], dst=_global(group, k), op=dist.ReduceOp.SUM, group=group,
-                                                 async_op=True))
+                for o, m in zip(out, mine):
+                    works.append(dist.reduce_scatter_tensor(m[k * b:(k + 1) * b], o[k * per:(k + 1) * per],
+                                                            op=dist.ReduceOp.SUM, group=group, async_op=True))
     for w in works:
         w.wait()   # the current stream waits for the NCCL stream
-    lo, hi = bounds[rank]
-    mine = [o[lo:hi] for o in out]
-    if slabs is not None:
-        for s, m in zip(slabs, mine):
-            s.copy_(m)
-        return list(slabs)
     return mine
 
 
-def reduce_along_z(grid: torch.Tensor, group=None) -> torch.Tensor:
-    """Sum a finished (nz, ny, nx) partial grid along z onto the slab owners (one reduce per slab, in
-    place); returns this rank's slab as a view of `grid`."""
+def reduce_along_z(grid: torch.Tensor, group=None, chunks: Optional[int] = None) -> torch.Tensor:
+    """Sum a FINISHED (nz, ny, nx) partial grid along z; returns the planes
+    owned_planes(nz, rank, G, chunks) of the sum (same layout as scatter3d_sharded, no overlap)."""
     world, rank = _world(group), _rank(group)
-    bounds = [slab_range(grid.shape[0], k, world) for k in range(world)]
-    if world > 1:
-        works = [dist.reduce(grid[lo:hi], dst=_global(group, k), op=dist.ReduceOp.SUM, group=group, async_op=True)
-                 for k, (lo, hi) in enumerate(bounds) if hi > lo]
-        for w in works:
-            w.wait()
-    lo, hi = bounds[rank]
-    return grid[lo:hi]
+    nz = grid.shape[0]
+    if world == 1:
+        return grid
+    c = z_chunks(nz, world, chunks)
+    if c == 0 or not grid.is_cuda:
+        # unequal slabs (or gloo, which has no reduce_scatter): one in-place reduce per owner
+        if c == 0:
+            bounds = [[slab_range(nz, k, world)] for k in range(world)]
+        else:
+            per, b = nz // c, nz // (c * world)
+            bounds = [[(j * per + k * b, j * per + (k + 1) * b) for j in range(c)] for k in range(world)]
+        work = grid if grid.is_cuda else grid.clone()
+        for k in range(world):
+            for lo, hi in bounds[k]:
+                if hi > lo:
+                    dist.reduce(work[lo:hi], dst=_global(group, k), op=dist.ReduceOp.SUM, group=group)
+        return torch.cat([work[lo:hi] for lo, hi in bounds[rank]]) if len(bounds[rank]) > 1 \
+            else work[bounds[rank][0][0]:bounds[rank][0][1]]
+    per, b = nz // c, nz // (c * world)
+    mine = torch.empty((c * b,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
+    works = [dist.reduce_scatter_tensor(mine[k * b:(k + 1) * b], grid[k * per:(k + 1) * per], op=dist.ReduceOp.SUM,
+                                        group=group, async_op=True) for k in range(c)]
+    for w in works:
+        w.wait()
+    return mine
 
 
 _side_streams = {}
@@ -186,36 +229,37 @@ _side_streams = {}
 def _side_stream(dev) -> torch.cuda.Stream:
     s = _side_streams.get(dev.index)
     if s is None:
-        s = _side_streams[dev.index] = torch.cuda.Stream(dev)
+        s = _side_streams[dev.index] = torch.cuda.Stream(dev, priority=-1)
     return s
 
 
 # ---- backend mode -----------------------------------------------------------------------------
 class _Mode:
-    def __init__(self, group, images, grids):
-        self.group, self.images, self.grids = group, images, grids
+    def __init__(self, group, images, grids, chunks):
+        self.group, self.images, self.grids, self.chunks = group, images, grids, chunks
 
 
 _mode: Optional[_Mode] = None
 
 
-def enable(group=None, images: str = "all", grids: str = "all") -> None:
+def enable(group=None, images: str = "all", grids: str = "all", chunks: Optional[int] = None) -> None:
     """Make `B200Backend` multi-GPU: every rank of `group` (default: the world) calls the backend
     (or Sarracen's front-end with backend='gpu') with the same full columns; each renders its
     shard_range() of the particles and the partial rasters are combined as described above.
 
     images: 'all'  -- every rank receives the picture (all_reduce; the drop-in behaviour), or
             'root' -- only rank 0's return value is the sum (reduce), the others get zeros.
-    grids:  'all'  -- every rank receives the whole (nz, ny, nx) grid (overlapped reduce along z,
-                      then all_gather of the slabs), or
-            'slab' -- every rank receives only its slab_range() of z-planes (no gather: the form
-                      `north_star` names; the return shape is (nz_r, ny, nx))."""
+    grids:  'all'  -- every rank receives the whole (nz, ny, nx) grid (overlapped reduce-scatter along
+                      z, then all_gather), or
+            'slab' -- every rank receives only the planes owned_planes(nz, rank, G, chunks) (no
+                      gather: the form `north_star` names; the return shape is (nz / G, ny, nx)).
+    chunks: z-chunks of the overlapped reduce-scatter (default 4; 1 = contiguous slabs)."""
     global _mode
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("torch.distributed is not initialised")
     if images not in ("all", "root") or grids not in ("all", "slab"):
         raise ValueError("images must be 'all' or 'root', grids 'all' or 'slab'")
-    _mode = _Mode(group, images, grids)
+    _mode = _Mode(group, images, grids, chunks)
 
 
 def disable() -> None:
@@ -244,16 +288,22 @@ def finish_images(imgs: Sequence[torch.Tensor], mode: _Mode) -> List[torch.Tenso
     return out
 
 
-def gather_slabs(slab: torch.Tensor, nz: int, mode: _Mode) -> torch.Tensor:
-    """All ranks' slabs -> the whole grid on every rank."""
-    world = _world(mode.group)
-    full = torch.empty((nz,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
-    if nz % world == 0:
-        dist.all_gather_into_tensor(full, slab.contiguous(), group=mode.group)
-    else:
-        parts = [full[slice(*slab_range(nz, k, world))] for k in range(world)]
-        for k, p in enumerate(parts):   # unequal slabs: one broadcast per owner
-            if k == _rank(mode.group):
-                p.copy_(slab)
-            dist.broadcast(p, src=_global(mode.group, k), group=mode.group)
+def gather_slabs(mine: torch.Tensor, nz: int, mode: _Mode) -> torch.Tensor:
+    """Every rank's owned planes -> the whole (nz, ny, nx) grid on every rank."""
+    world, rank = _world(mode.group), _rank(mode.group)
+    c = z_chunks(nz, world, mode.chunks)
+    tail = tuple(mine.shape[1:])
+    if c > 0 and mine.is_cuda:
+        b = nz // (c * world)
+        gathered = torch.empty((world, c, b) + tail, dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(gathered.view((world * c * b,) + tail), mine.contiguous(), group=mode.group)
+        # [rank][chunk][plane] -> z order [chunk][rank][plane]
+        return gathered.permute(1, 0, 2, *range(3, 3 + len(tail))).reshape((nz,) + tail)
+    full = torch.empty((nz,) + tail, dtype=mine.dtype, device=mine.device)
+    for k in range(world):   # unequal slabs / gloo: one broadcast per owner
+        planes = owned_planes(nz, k, world, mode.chunks)
+        piece = mine.contiguous() if k == rank else torch.empty((len(planes),) + tail, dtype=mine.dtype,
+                                                                 device=mine.device)
+        dist.broadcast(piece, src=_global(mode.group, k), group=mode.group)
+        full[planes] = piece
     return full

@@ -19,13 +19,15 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sarracen_b200 as s  # noqa: E402
 from sarracen_b200 import ops, parallel  # noqa: E402
-from sarracen_b200.parallel import (combine_grid_along_z, combine_image, scatter3d_sharded, shard_range,  # noqa: E402
-                                    slab_range)
+from sarracen_b200.parallel import (combine_grid_along_z, combine_image, owned_planes, scatter3d_sharded,  # noqa: E402
+                                    shard_range, slab_range)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+_opts = dist.ProcessGroupNCCL.Options()
+_opts.is_high_priority_stream = True
+dist.init_process_group("nccl", device_id=dev, pg_options=_opts)
 
 rng = np.random.default_rng(42)
 n = 400_003
@@ -57,7 +59,7 @@ zl, zh = slab_range(nz, rank, world)
 errs = []
 for overlap in (True, False):
     slab = scatter3d_sharded(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3, overlap=overlap)[0]
-    errs.append(relmax(slab, full3[zl:zh]))
+    errs.append(relmax(slab, full3[owned_planes(nz, rank, world)]))
 gpart = ops.scatter3d(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3)[0]
 slab2 = torch.empty((zh - zl, 36, 40), dtype=torch.float64, device=dev)
 combine_grid_along_z(gpart, slab2)
@@ -65,9 +67,10 @@ errs.append(relmax(slab2, full3[zl:zh]))
 # a grid whose small particles take the cell path and whose large ones the tile path, 64 planes per rank
 r3b = ops.Raster(64, 64, 0, 1, 0, 1, 64 * world, 0, 1)
 full3b = ops.scatter3d(xd, yd, zd, hd, [wd], c.w, 2.0, r3b)[0]
-zlb, zhb = slab_range(64 * world, rank, world)
-slab3 = scatter3d_sharded(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3b)[0]
-errs.append(relmax(slab3, full3b[zlb:zhb]))
+for ch in (4, 1):      # block-cyclic planes (4 z-chunks, overlapped) and contiguous slabs
+    slab3 = scatter3d_sharded(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3b, chunks=ch)[0]
+    errs.append(relmax(slab3, full3b[owned_planes(64 * world, rank, world, ch)]))
+assert owned_planes(64 * world, rank, world, 1) == list(range(*slab_range(64 * world, rank, world)))
 e = torch.tensor(errs, device=dev, dtype=torch.float64)
 dist.all_reduce(e, op=dist.ReduceOp.MAX)
 
@@ -98,7 +101,11 @@ for name in single:
         api += [np.abs(a[i] - b[i]).max() / np.abs(a[i]).max() for i in range(2)]
     else:
         api.append(np.abs(a - b).max() / np.abs(a).max())
-api.append(np.abs(slab_api - single["grid"][zl:zh]).max() / np.abs(single["grid"]).max())
+api.append(np.abs(slab_api - single["grid"][owned_planes(nz, rank, world)]).max() / np.abs(single["grid"]).max())
+parallel.enable(images="all", grids="all")   # a grid that divides evenly: chunked, block-cyclic, gathered
+g_multi = B.interpolate_3d_grid(x, y, z, w, h, c.w, 2.0, 64, 64, 64 * world, 0, 1, 0, 1, 0, 1)
+parallel.disable()
+api.append(np.abs(g_multi - full3b.cpu().numpy()).max() / float(full3b.abs().max()))
 assert slab_api.shape == (zh - zl, 36, 40)
 ea = torch.tensor(api, device=dev, dtype=torch.float64)
 dist.all_reduce(ea, op=dist.ReduceOp.MAX)
@@ -110,7 +117,7 @@ if rank == 0:
                                                   False)
     eo = float(np.abs(part.cpu().numpy() - ref).max() / np.abs(ref).max())
     print(f"world={world} image: sharded vs single {e2:.2e}, vs oracle {eo:.2e}; grid slabs vs single "
-          f"(overlapped, sequential, reduce-scatter, 64-plane slabs) {[f'{v:.1e}' for v in e.tolist()]}; "
+          f"(unequal slabs overlapped / sequential, reduce-scatter, 4 z-chunks, contiguous) {[f'{v:.1e}' for v in e.tolist()]}; "
           f"backend API in multi-GPU mode vs single {ea.max().item():.2e}")
     assert e2 < 1e-12 and eo < 1e-10 and e.max().item() < 1e-12 and ea.max().item() < 1e-12
     print("multi-GPU check ok")
