@@ -8,9 +8,11 @@
 // with several weight columns) -- the emit kernel writes their packed records in cell order --
 // and rendered here with a LOCAL ACCUMULATOR:
 //
-//   * a warp takes kCellChunk consecutive records of that stream (a coalesced read: the
-//     records of a cell are contiguous), 32 at a time; every lane derives one particle's box,
-//     scales and terms and parks them in the warp's staging slots;
+//   * a warp takes kCellChunk consecutive records of that stream, 32 at a time.  The stream is
+//     contiguous, so a batch is ONE 1-D TMA bulk copy (cp.async.bulk global -> shared, completion
+//     on an mbarrier; SASS UBLKCP) issued by lane 0 a batch ahead: batch k+1 lands while batch k is
+//     evaluated.  Every lane derives one particle's box, scales and terms from the staged record
+//     and parks them in the warp's staging slots;
 //   * the warp owns a private shared-memory accumulator that covers one cell plus the halo a
 //     box can reach beyond it ((cell + halo)^d values per weight).  Particles are walked one at
 //     a time with the lanes laid over the box -- in-plane pixels across lanes (several z-slices
@@ -36,6 +38,66 @@ namespace sphb {
 #endif
 constexpr int kCellMaxWarps = SPHB_CELL_MAXW;
 constexpr int kTinyVolume = 16; // a batch whose largest box holds <= this many pixels reduces directly
+
+// ---- TMA: 1-D bulk copies global -> shared, completion on an mbarrier -------------------------
+// The cell-ordered records of a warp's chunk are one contiguous stream, so the next batch of 32
+// records (1-2 KB) is fetched by ONE cp.async.bulk issued by lane 0 (SASS: UBLKCP) while the warp
+// works on the current batch; the lanes then read their record from shared memory.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\t"
+                 "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// record of lane `i` out of a staged batch in shared memory (same layouts as load_rec)
+__device__ __forceinline__ Rec<double> smem_rec(const double *raw, int stride, int i)
+{
+    Rec<double> r;
+    const double2 *b = reinterpret_cast<const double2 *>(raw + (size_t)i * stride);
+    const double2 a = b[0], c = b[1];
+    r.x = a.x; r.y = a.y; r.h = c.x;
+    if (stride == 4) {
+        r.z = 0.0; r.w[0] = c.y;
+        r.w[1] = r.w[2] = r.w[3] = 0.0;
+    } else {
+        r.z = c.y;
+        const double2 d = b[2], e = b[3];
+        r.w[0] = d.x; r.w[1] = d.y; r.w[2] = e.x; r.w[3] = e.y;
+    }
+    return r;
+}
+__device__ __forceinline__ Rec<float> smem_rec(const float *raw, int stride, int i)
+{
+    Rec<float> r;
+    const float4 *b = reinterpret_cast<const float4 *>(raw + (size_t)i * 8);
+    const float4 a = b[0], c = b[1];
+    r.x = a.x; r.y = a.y; r.h = a.z; r.z = a.w;
+    r.w[0] = c.x; r.w[1] = c.y; r.w[2] = c.z; r.w[3] = c.w;
+    (void)stride;
+    return r;
+}
 
 // Staging slots of one warp: one batch of 32 particles.  Everything a particle's pass needs is
 // derived here once, lane-parallel, so that the pass itself starts with a few broadcast loads.
@@ -167,8 +229,26 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
     if (start >= p_hi) return;
     const int64_t end = min(start + (int64_t)kCellChunk, p_hi);
 
+    // double-buffered raw records + their mbarriers, behind the staging slots
+    const int raw_bytes = 32 * v.rec_stride * (int)sizeof(T);
+    T *const raw0 = reinterpret_cast<T *>(mine + sizeof(CellBatch<R, NW>));
+    const int raw_elems = 32 * v.rec_stride;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(mine + sizeof(CellBatch<R, NW>) + 2 * raw_bytes);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto fetch = [&](int64_t first, int buf) {   // lane 0: records [first, first + 32) of the stream
+        const unsigned bytes = (unsigned)(min((int64_t)32, end - first) * v.rec_stride * (int)sizeof(T));
+        mbar_expect_tx(bar + buf, bytes);
+        bulk_g2s(raw0 + buf * raw_elems, recs + (size_t)first * v.rec_stride, bytes, bar + buf);
+    };
+    if (lane == 0) fetch(start, 0);
+
     CellAcc<R> a;
-    a.acc = reinterpret_cast<R *>(mine + sizeof(CellBatch<R, NW>));
+    a.acc = reinterpret_cast<R *>(mine + sizeof(CellBatch<R, NW>) + 2 * raw_bytes + 16);
     a.s1 = (1 << v.cx_log) + v.halo;
     a.s2 = a.s1 * ((1 << v.cy_log) + v.halo);
     a.plane = plane;
@@ -184,13 +264,17 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
     const R rad2 = (R)(v.radius * v.radius);
     const int cmx = (1 << v.cx_log) - 1, cmy = (1 << v.cy_log) - 1, cmz = (1 << v.cz_log) - 1;
 
-    for (int64_t base = start; base < end; base += 32) {
-        // ---- every lane derives one particle ---------------------------------
+    int batch = 0;
+    for (int64_t base = start; base < end; base += 32, batch++) {
+        // ---- next batch on its way, this one landed; every lane derives one particle ----------
+        const int buf = batch & 1;
+        if (lane == 0 && base + 32 < end) fetch(base + 32, buf ^ 1);
+        mbar_wait(bar + buf, (unsigned)(batch >> 1) & 1u);
         int vol = 0;
         {
             int4 geo = make_int4(0, 0, -1, 0);
             if (base + lane < end) {
-                const Rec<T> pr = load_rec(recs, v.rec_stride, base + lane, NW);
+                const Rec<T> pr = smem_rec(raw0 + buf * raw_elems, v.rec_stride, lane);
                 const double hp = (double)pr.h;
                 const double xp = (double)pr.x, yp = (double)pr.y;
                 const double rad = v.radius * hp;
@@ -352,7 +436,9 @@ static int launch_one(const View &v, const T *recs, const sphb_kernel *k, const 
     const int plane = !acc ? 0 : DIM3 ? s2 * ((1 << v.cz_log) + v.halo) : s2;
     size_t lut_bytes = 0;
     if (KIND == SPHB_COLUMN_LUT) lut_bytes = align_up(sizeof(R2) * (size_t)k->lut_samples, 16);
-    const size_t warp_bytes = align_up(sizeof(CellBatch<R, NW>) + sizeof(R) * (size_t)plane * NW, 16);
+    // staging slots, two raw record batches, two mbarriers, accumulator
+    const size_t warp_bytes = align_up(sizeof(CellBatch<R, NW>) + 2 * 32 * (size_t)v.rec_stride * sizeof(T) + 16 +
+                                           sizeof(R) * (size_t)plane * NW, 16);
     const size_t limit = 227 * 1024;
     if (lut_bytes + warp_bytes > limit) {
         set_error("cell accumulator (%zu bytes) and column table (%zu bytes) do not fit in shared memory",
