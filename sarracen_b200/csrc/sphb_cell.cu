@@ -110,6 +110,7 @@ template <typename R, int NW> struct CellBatch {
     // (0 = nothing to do);  z: cell id;  w: lanes per z-slice (log2) | (65536 / wx + 1) << 8
     int4 geo[32];
     int bx[32], by[32], bz[32]; // box origin (raster pixels)
+    unsigned inv_wxy[32];       // 65536 / (wx wy) + 1
 };
 
 template <typename R> struct CellAcc {
@@ -314,6 +315,7 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                     geo.z = (((z0 >> v.cz_log) * v.ncy) + (y0 >> v.cy_log)) * v.ncx + (x0 >> v.cx_log);
                     const int lpl_log = DIM3 ? min(5, 32 - __clz(wx * wy - 1)) : 5; // ceil(log2(wx wy))
                     geo.w = lpl_log | (int)((65536u / (unsigned)wx + 1u) << 8);
+                    st.inv_wxy[lane] = 65536u / (unsigned)(wx * wy) + 1u;
                 }
             }
             st.geo[lane] = geo;
@@ -331,13 +333,14 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
             const int sub = lane & ((1 << lpp_log) - 1), grp = lane >> lpp_log;
             for (int g = 0; g < 32; g += 32 >> lpp_log) {
                 const int s = g + grp;
-                const int dims = st.geo[s].y;
+                const int4 geo = st.geo[s];
+                const int dims = geo.y;
                 const int wx = dims & 0xff, wy = (dims >> 8) & 0xff, wz = dims >> 16;
                 const int wxy = wx * wy;
                 if (sub < wxy * wz) {
-                    // sub < 16: exact small divisions by multiply-shift
-                    const int iz = (int)(((unsigned)sub * (65536u / (unsigned)wxy + 1u)) >> 16), r = sub - iz * wxy;
-                    const int iy = (int)(((unsigned)r * (65536u / (unsigned)wx + 1u)) >> 16), ix = r - iy * wx;
+                    // sub < 16: exact small divisions by multiply-shift (reciprocals from the staging step)
+                    const int iz = (int)(((unsigned)sub * st.inv_wxy[s]) >> 16), r = sub - iz * wxy;
+                    const int iy = (int)(((unsigned)r * ((unsigned)geo.w >> 8)) >> 16), ix = r - iy * wx;
                     const R dxs = fma((R)ix, st.sx[s], st.ox[s]), dys = fma((R)iy, st.sy[s], st.oy[s]);
                     R q2 = fma(dys, dys, fma(dxs, dxs, st.cq[s]));
                     if (DIM3) {

@@ -106,19 +106,16 @@ __device__ __forceinline__ Rec<float> load_rec(const float *__restrict__ recs, i
     return r;
 }
 
-__device__ __forceinline__ int clamp_to_int(double v, int lo, int hi)
-{
-    // also maps NaN to lo
-    return (int)fmin(fmax(v, (double)lo), (double)hi);
-}
-
-// Pixel box [lo, hi) that holds every pixel centre within rad of c.
+// Pixel box [lo, hi) that holds every pixel centre within rad of c.  The roundings are the
+// converting ones (cvt.rpi / cvt.rmi.s32.f64: they saturate, and map NaN to 0) followed by an
+// integer clamp -- one conversion-pipe instruction per bound instead of a rounding, two double
+// min / max and a conversion.
 __device__ __forceinline__ void pixel_range(double c, double rad, double origin, double inv_pw, int n,
                                             int &lo, int &hi)
 {
     // centre of pixel i sits at origin + (i + 1/2) pw
-    lo = clamp_to_int(ceil((c - rad - origin) * inv_pw - 0.5), 0, n);
-    hi = clamp_to_int(floor((c + rad - origin) * inv_pw - 0.5) + 1.0, 0, n);
+    lo = min(max(__double2int_ru((c - rad - origin) * inv_pw - 0.5), 0), n);
+    hi = min(max(__double2int_rd((c + rad - origin) * inv_pw - 0.5), -1), n - 1) + 1;
 }
 
 // Opt a kernel in to the full 227 KB of dynamic shared memory, once per instantiation and
