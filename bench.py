@@ -388,7 +388,7 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
         torch.cuda.synchronize()
 
     def timed(fn, steps, collect=False):
-        phases = {"ms_bin": 0.0, "ms_sort": 0.0, "ms_render": 0.0, "ms_direct": 0.0}
+        phases = {"ms_bin": 0.0, "ms_count": 0.0, "ms_sort": 0.0, "ms_render": 0.0, "ms_direct": 0.0}
         launches = 0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -501,20 +501,25 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    # the dominant kernel: tile render or small-footprint kernel, whichever took longer; its share of the
-    # per-rank algorithmic bytes is the whole shard (every record read once, every output element written once)
-    dom = "ms_render" if phases["ms_render"] >= phases["ms_direct"] else "ms_direct"
+    # the dominant kernel: the one that took longest -- tile kernel (large footprints), cell kernel (small
+    # footprints) or the emit kernel of the binning (count = ms_count, emit = ms_bin - ms_count); its share
+    # of the per-rank algorithmic bytes is the whole shard (every record read once, every output element
+    # written once)
+    phases["ms_emit"] = max(0.0, phases["ms_bin"] - phases["ms_count"])
+    dom = max(("ms_render", "ms_direct", "ms_emit"), key=lambda k: phases[k])
     ms_dom = phases[dom]
+    dom_kernel = {"ms_render": "render_kernel", "ms_direct": "cell_kernel", "ms_emit": "emit_kernel"}[dom]
     bytes_rank = n_local * wl["fields"] * itemsize + wl["nx"] * wl["ny"] * wl["nz"] * 8
     achieved = bytes_rank / (ms_dom * 1e-3) / 1e9 if ms_dom > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp) and world == 1:
-        traffic = json.load(open(tp)).get(f"{wl['key']}_{args.dtype}")
+        traffic = (json.load(open(tp)).get(f"{wl['key']}_{args.dtype}") or {}).get(dom_kernel)
     whole = alg_bytes(wl, itemsize) / (ms_step * 1e-3) / 1e9 / peak / world
 
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    rate = contrib / world / (ms_dom * 1e-3) if ms_dom > 0 else 0.0   # per GPU
+    ms_eval = max(phases["ms_render"], phases["ms_direct"])   # the kernel that evaluates the contributions
+    rate = contrib / world / (ms_eval * 1e-3) if ms_eval > 0 else 0.0   # per GPU
     if args.dtype == "f64":
         compute = {"bound": "fp64 pipe + issue slots", "contributions_per_s_per_gpu_in_kernel": rate,
                    "peak_fp64_lane_inst_per_s": 148 * 64 * sm_clock * 1e6,
@@ -538,7 +543,7 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
         "phases_ms": phases, "ms_step_with_phase_events": ms_phased,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "render_kernel" if dom == "ms_render" else "small-footprint kernel",
+                     "kernel": dom_kernel,
                      "alg_bytes": bytes_rank, "peak_source": peak_src, "whole_step_frac": whole},
         "compute_bound": compute,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

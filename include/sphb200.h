@@ -105,6 +105,7 @@ typedef struct sphb_stats {
     float ms_render;      /* out: the tile kernel (large footprints) alone */
     float ms_direct;      /* out: the cell kernel (small footprints) alone */
     int32_t launches;     /* out: kernels of this library launched by the call (CUB's not counted) */
+    float ms_count;       /* out: the count kernel + cell scan alone (part of ms_bin) */
 } sphb_stats;
 
 int sphb_version(void);

@@ -43,7 +43,8 @@ class SphbStats(ctypes.Structure):
     _fields_ = [("n_pairs", ctypes.c_int64), ("n_direct", ctypes.c_int64), ("n_tiles", ctypes.c_int64),
                 ("tile_x", ctypes.c_int32), ("tile_y", ctypes.c_int32), ("tile_z", ctypes.c_int32),
                 ("time_phases", ctypes.c_int32), ("ms_bin", ctypes.c_float), ("ms_sort", ctypes.c_float),
-                ("ms_render", ctypes.c_float), ("ms_direct", ctypes.c_float), ("launches", ctypes.c_int32)]
+                ("ms_render", ctypes.c_float), ("ms_direct", ctypes.c_float), ("launches", ctypes.c_int32),
+                ("ms_count", ctypes.c_float)]
 
 
 class SphbError(RuntimeError):

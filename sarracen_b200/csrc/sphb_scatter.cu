@@ -558,18 +558,18 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         for (int i = 0; i < p->n_weights; i++)
             SPHB_CUDA(cudaMemsetAsync(out[i], 0, n_out * sizeof(double), stream));
     const bool timed = stats && stats->time_phases;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (stats) {
         stats->n_pairs = 0;
         stats->n_tiles = n_tiles;
         stats->tile_x = v.tx;
         stats->tile_y = v.ty;
         stats->tile_z = v.tz;
-        stats->ms_bin = stats->ms_sort = stats->ms_render = stats->ms_direct = 0.f;
+        stats->ms_bin = stats->ms_sort = stats->ms_render = stats->ms_direct = stats->ms_count = 0.f;
         stats->n_direct = 0;
         stats->launches = 0;
     }
-    if (timed) SPHB_CUDA(phase_events(ev, 5));
+    if (timed) SPHB_CUDA(phase_events(ev, 6));
     if (ws_needed) *ws_needed = 0;
     auto all_stages_done = [&]() {
         if (stages.fn)
@@ -609,6 +609,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
                                                                                     totals);
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, cell_start, cell_start, n_cells + 1, stream));
+    if (timed) SPHB_CUDA(cudaEventRecord(ev[5], stream));
     unsigned long long *totals_host = nullptr;
     SPHB_CUDA(totals_landing(&totals_host));
     SPHB_CUDA(cudaMemcpyAsync(totals_host, totals, kTotCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -734,6 +735,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         SPHB_CUDA(cudaEventRecord(ev[3], stream));
         SPHB_CUDA(cudaEventSynchronize(ev[3]));
         SPHB_CUDA(cudaEventElapsedTime(&stats->ms_bin, ev[0], ev[1]));
+        SPHB_CUDA(cudaEventElapsedTime(&stats->ms_count, ev[0], ev[5]));
         SPHB_CUDA(cudaEventElapsedTime(&stats->ms_sort, ev[1], ev[2]));
         SPHB_CUDA(cudaEventElapsedTime(&stats->ms_render, ev[2], ev[4]));
         SPHB_CUDA(cudaEventElapsedTime(&stats->ms_direct, ev[4], ev[3]));

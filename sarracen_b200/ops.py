@@ -158,7 +158,7 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
     stats.time_phases = 1 if time_phases else 0
     total_pairs = 0
     total_direct = 0
-    ms = [0.0, 0.0, 0.0, 0.0]
+    ms = [0.0, 0.0, 0.0, 0.0, 0.0]
     launches = 0
     # z-slab stages (voxel grids only): the library calls back right after the kernels of stage s have
     # been enqueued, and `on_stage(s)` runs there, on this thread, so that an event recorded by it sits
@@ -216,7 +216,8 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
             total_pairs += stats.n_pairs
             total_direct += stats.n_direct
             launches += stats.launches
-            ms = [ms[0] + stats.ms_bin, ms[1] + stats.ms_sort, ms[2] + stats.ms_render, ms[3] + stats.ms_direct]
+            ms = [ms[0] + stats.ms_bin, ms[1] + stats.ms_sort, ms[2] + stats.ms_render, ms[3] + stats.ms_direct,
+                  ms[4] + stats.ms_count]
         if staged and split and on_stage is not None:
             for s_done in range(n_stages):
                 on_stage(s_done)
@@ -226,7 +227,8 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
     last_stats.clear()
     last_stats.update(n_pairs=int(total_pairs), n_direct=int(total_direct), n_tiles=int(stats.n_tiles),
                       tile=(int(stats.tile_x), int(stats.tile_y), int(stats.tile_z)),
-                      ms_bin=ms[0], ms_sort=ms[1], ms_render=ms[2], ms_direct=ms[3], launches=launches)
+                      ms_bin=ms[0], ms_sort=ms[1], ms_render=ms[2], ms_direct=ms[3], ms_count=ms[4],
+                      launches=launches)
     return out
 
 
