@@ -13,10 +13,15 @@
  * reference's own tests/kernels/test_kernels.py.
  *
  * Each routine cites the reference file:line whose arithmetic it restates
- * (paths relative to the reference root, sarracen/...).  It is a restatement
- * from the mathematical definition in plain C (double precision, OpenMP
- * threads with private images like the reference's prange blocks), not a
- * translation of the numba source.
+ * (paths relative to the reference root, sarracen/...): plain C, double
+ * precision, OpenMP threads with private images like the reference's prange
+ * blocks.  The sampled scatter, the line cuts and the kernels are restated
+ * from their definition; the exact-integral functions (full_integral_3d,
+ * get_i_terms, line_int3d, surface_int and the 2-D f1 / f2 / f3 family) FOLLOW
+ * THE REFERENCE LINE BY LINE, keeping its variable names
+ * (kernels/cubic_spline_exact.py:7-483) -- the closed forms of Petkova et al.
+ * (2018) have to be evaluated in the same order for the oracle to agree with
+ * the reference to rounding.  Being a checker, that is what it is for.
  */
 #include <math.h>
 #include <stdint.h>
