@@ -248,6 +248,9 @@ def streamed_scatter(arrays, dev, render):
             ready[b] = torch.cuda.Event()
             ready[b].record(copy_stream)
 
+    # the buffers come from the main stream's caching allocator: whatever used their blocks last (the
+    # previous call's kernels, other work of the caller) was ordered on the main stream, so the copies wait
+    copy_stream.wait_stream(main)
     upload(0)
     out = None
     for k, (lo, hi) in enumerate(bounds):

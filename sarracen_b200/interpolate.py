@@ -168,6 +168,12 @@ class _Device:
 
     def weight(self, target, dens_weight: bool) -> torch.Tensor:
         """interpolate.py:448-472; `target` is a column label, a device tensor or None (unity)."""
+        key = ("w", target if (target is None or isinstance(target, str)) else id(target), bool(dens_weight))
+        if key not in self.cache:
+            self.cache[key] = self._weight(target, dens_weight)
+        return self.cache[key]
+
+    def _weight(self, target, dens_weight: bool) -> torch.Tensor:
         if target is None:
             tdata = None
         elif isinstance(target, str):
@@ -388,7 +394,7 @@ def interpolate_3d_line(data, target, x=None, y=None, z=None, kernel: Optional[B
 def interpolate_3d_proj(data, target, x=None, y=None, kernel: Optional[BaseKernel] = None, integral_samples=1000,
                         corotation=None, rotation=None, rot_origin=None, x_pixels=None, y_pixels=None, xlim=None,
                         ylim=None, exact=False, backend=None, dens_weight=None, normalize=True,
-                        hmin=False) -> np.ndarray:
+                        hmin=False, _dv=None) -> np.ndarray:
     """Column-integrated view of 3-D data (interpolate.py:946-1083)."""
     _check_dimension(data, 3)
     x, y, z = _default_xyz(data, x, y, None)
@@ -399,7 +405,8 @@ def interpolate_3d_proj(data, target, x=None, y=None, kernel: Optional[BaseKerne
         if len(flags) != 1:
             raise ValueError("pass dens_weight explicitly when 'rho' is rendered together with other targets")
         dens_weight = flags.pop()
-    dv = _Device(data, [data.xcol, data.ycol, data.zcol, x, y, data.hcol, data.mcol, data.rhocol, target])
+    dv = _dv if _dv is not None else _Device(data, [data.xcol, data.ycol, data.zcol, x, y, data.hcol, data.mcol,
+                                                    data.rhocol, target])
     weights, many = _target_weights(dv, target, dens_weight, normalize)
     if corotation is not None:
         rotation, rot_origin = _corotate(corotation, rotation)
@@ -452,7 +459,13 @@ def interpolate_3d_cross(data, target, x=None, y=None, z=None, z_slice=None, ker
                          corotation=None, rotation=None, rot_origin=None, x_pixels=None, y_pixels=None,
                          xlim=None, ylim=None, backend=None, dens_weight=False, normalize=True,
                          hmin=False) -> np.ndarray:
-    """Cross-section of 3-D data at `z_slice` (interpolate.py:1229-1361)."""
+    """Cross-section of 3-D data at `z_slice` (interpolate.py:1229-1361).
+
+    Extension: `z_slice` may be a sequence of K depths; the result is then a
+    (K, ny, nx) stack.  Evenly spaced depths are rendered in ONE pass -- one upload, one bin, one
+    walk over the particles -- as the K planes of a voxel grid (the reference's grid *is* the loop of
+    cross-sections, cpu_backend.py:213-218); other sequences share the upload, the rotation and the
+    weights and make one pass per depth."""
     _check_dimension(data, 3)
     x, y, z = _default_xyz(data, x, y, z)
     _verify_columns(data, x, y)
@@ -460,6 +473,11 @@ def interpolate_3d_cross(data, target, x=None, y=None, z=None, z_slice=None, ker
     dv = _Device(data, [data.xcol, data.ycol, data.zcol, x, y, z, data.hcol, data.mcol, data.rhocol, target])
     if z_slice is None:
         z_slice = float(dv.col(z).to(torch.float64).mean().item())  # of the unrotated column (:1327-1328)
+    depths = None
+    if isinstance(z_slice, (list, tuple, np.ndarray)):
+        depths = [float(v) for v in np.asarray(z_slice, dtype=np.float64).ravel()]
+        if not depths:
+            raise ValueError("`z_slice` is empty")
     weights, many = _target_weights(dv, target, dens_weight, normalize)
     kernel = kernel if kernel is not None else data.kernel
     if corotation is not None:
@@ -470,9 +488,48 @@ def interpolate_3d_cross(data, target, x=None, y=None, z=None, z_slice=None, ker
     _check_boundaries(x_pixels, y_pixels, xlim, ylim)
     pix = max((xlim[1] - xlim[0]) / x_pixels, (ylim[1] - ylim[0]) / y_pixels)
     r = ops.Raster(x_pixels, y_pixels, xlim[0], xlim[1], ylim[0], ylim[1])
-    out = ops.scatter2d(x_t, y_t, dv.smoothing(hmin, pix), weights, kernel.w, kernel.get_radius(), 3, r, z=z_t,
-                        z_slice=float(z_slice))
-    return _finish_targets(out, normalize, many)
+    h_t = dv.smoothing(hmin, pix)
+    if depths is None:
+        out = ops.scatter2d(x_t, y_t, h_t, weights, kernel.w, kernel.get_radius(), 3, r, z=z_t, z_slice=float(z_slice))
+        return _finish_targets(out, normalize, many)
+    k = len(depths)
+    step = (depths[-1] - depths[0]) / (k - 1) if k > 1 else 0.0
+    even = k > 1 and step > 0 and all(abs(depths[i] - (depths[0] + i * step)) <= 1e-12 * max(1.0, abs(depths[i]))
+                                      for i in range(k))
+    if even:
+        # plane i of the grid has its centre at z_min + (i + 1/2) step = depths[i]
+        r3 = ops.Raster(x_pixels, y_pixels, xlim[0], xlim[1], ylim[0], ylim[1], k, depths[0] - 0.5 * step,
+                        depths[-1] + 0.5 * step)
+        out = ops.scatter3d(x_t, y_t, z_t, h_t, weights, kernel.w, kernel.get_radius(), r3)
+        return _finish_targets(out, normalize, many)
+    stacks = None
+    for i, d in enumerate(depths):
+        out = ops.scatter2d(x_t, y_t, h_t, weights, kernel.w, kernel.get_radius(), 3, r, z=z_t, z_slice=d)
+        res = _finish_targets(out, normalize, many)
+        res = res if many else [res]
+        if stacks is None:
+            stacks = [np.empty((k,) + g.shape) for g in res]
+        for s_, g in zip(stacks, res):
+            s_[i] = g
+    return stacks if many else stacks[0]
+
+
+def interpolate_3d_proj_views(data, target, rotations, **kwargs) -> np.ndarray:
+    """Extension: the column-integrated view of `target` for each rotation of
+    `rotations` (the `render()` call pattern of a turntable, render.py:401-422), as a (K, ny, x) stack.
+    The columns are uploaded, and the weights m / rho A built, ONCE; each view rotates, bins and renders on
+    the device.  Give `xlim` / `ylim` (or the pixel counts) if all views are to share one raster; every
+    other keyword is that of `interpolate_3d_proj`."""
+    if "rotation" in kwargs:
+        raise TypeError("pass `rotations`, not `rotation`")
+    x, y, _ = _default_xyz(data, kwargs.get("x"), kwargs.get("y"), None)
+    dv = _Device(data, [data.xcol, data.ycol, data.zcol, x, y, data.hcol, data.mcol, data.rhocol, target])
+    views = [interpolate_3d_proj(data, target, rotation=rot, _dv=dv, **kwargs) for rot in rotations]
+    if isinstance(views[0], list):
+        return [np.stack([v[i] for v in views]) for i in range(len(views[0]))]
+    if len({v.shape for v in views}) != 1:
+        raise ValueError("the views have different rasters: give xlim / ylim and the pixel counts")
+    return np.stack(views)
 
 
 def interpolate_3d_cross_vec(data, target_x, target_y, target_z, z_slice=None, x=None, y=None, z=None,
