@@ -6,7 +6,7 @@ A from-scratch implementation of the one data-parallel hot path of Sarracen
 backend interface (`B200Backend`).  See DESIGN.md and INTEGRATION.md.
 """
 from .backend import B200Backend, install, resolve_weight_function  # noqa: F401
-from .frame import ParticleFrame  # noqa: F401
+from .frame import DeviceFrame, ParticleFrame  # noqa: F401
 from .kernels import (BaseKernel, CubicSplineKernel, QuarticSplineKernel,  # noqa: F401
                       QuinticSplineKernel, WeightFunction)
 

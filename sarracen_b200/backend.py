@@ -171,10 +171,14 @@ def release_host_buffers() -> None:
 
 
 def _stage_column(j, src, dst, copy_stream):
-    """Worker: pageable `src` (host) -> `dst` (device) through worker j's page-locked slots."""
-    ring = _stage_rings.get(j)
+    """Worker: pageable `src` (host) -> `dst` (device) through the calling worker thread's own
+    page-locked slots (`j` is only a label: the ring belongs to the thread, so any number of
+    columns can be in flight on the pool)."""
+    import threading
+    key = threading.get_ident()
+    ring = _stage_rings.get(key)
     if ring is None:
-        ring = _stage_rings[j] = _StageRing()
+        ring = _stage_rings[key] = _StageRing()
     n = src.numel()
     with torch.cuda.stream(copy_stream):
         for off in range(0, n, _STAGE_ELEMS):

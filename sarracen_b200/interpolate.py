@@ -136,7 +136,10 @@ class _Device:
         flat = []
         for c in columns:  # a target may be a list of labels
             flat.extend(c if isinstance(c, (list, tuple)) else [c])
-        dtypes = [np.asarray(data[c]).dtype for c in flat if isinstance(c, str) and c in data.columns]
+        if hasattr(data, "column_dtype"):   # DeviceFrame: no host copies
+            dtypes = [data.column_dtype(c) for c in flat if isinstance(c, str) and c in data.columns]
+        else:
+            dtypes = [np.asarray(data[c]).dtype for c in flat if isinstance(c, str) and c in data.columns]
         self.dtype = torch.float32 if dtypes and all(dt == np.float32 for dt in dtypes) else torch.float64
         self.cache = {}
         self.n = len(data)
