@@ -178,6 +178,23 @@ int sphb_exact3d_proj(const sphb_particles *p, const sphb_raster *r, int accumul
 int sphb_count_contributions(const sphb_particles *p, double radius, const sphb_raster *r, int use_z,
                              double z_slice, unsigned long long *out, sphb_stream stream);
 
+/* SURVEY 8(f)-4 -- radial binning behind Sarracen's disc analysis (sarracen/disc/utils.py:25-86:
+ * pandas.cut of the particle radii).  index[i] = ring of particle i, i.e. the i such that
+ * edges[i] < r <= edges[i + 1] (right-closed, like pandas.cut), -1 outside (edges[0], edges[bins]];
+ * r = |(x, y) - origin| or, with `spherical`, |(x, y, z) - origin|; counts[ring] = its population.
+ * `edges`: device float64[bins + 1], ascending; `origin`: HOST double[3]; index: device int32[n];
+ * counts: device uint64[bins] (overwritten).  1 <= bins <= 6000. */
+int sphb_radial_index(int dtype, const void *x, const void *y, const void *z, int64_t n, const double *origin,
+                      int spherical, const double *edges, int bins, int *index, unsigned long long *counts,
+                      sphb_stream stream);
+
+/* Sums of `n_values` (1..4) value columns per ring (the groupby(...).sum() of
+ * sarracen/disc/surface_density.py:148-151, :188-201): out[k][ring] = sum of values[k][i] over
+ * the particles with index[i] == ring.  values: HOST array of device pointers of `dtype`;
+ * out: HOST array of device float64[bins] (overwritten). */
+int sphb_bin_sums(int dtype, const int *index, int n_values, const void *const *values, int64_t n, int bins,
+                  double *const *out, sphb_stream stream);
+
 /* N5 -- out = nan_to_num(num / den) elementwise on the device
  * (interpolate.py:594): 0/0 -> 0, +-inf -> +-DBL_MAX. */
 int sphb_normalize(double *num, const double *den, int64_t n, sphb_stream stream);

@@ -17,7 +17,7 @@ SPHB_OK, SPHB_ERR_ARGUMENT, SPHB_ERR_WORKSPACE, SPHB_ERR_CUDA, SPHB_ERR_TOO_MANY
 EXPORTS = ["sphb_version", "sphb_last_error", "sphb_column_kernel", "sphb_scatter2d", "sphb_scatter3d",
            "sphb_scatter3d_staged",
            "sphb_line2d", "sphb_line3d", "sphb_exact2d", "sphb_exact3d_proj", "sphb_normalize",
-           "sphb_count_contributions"]
+           "sphb_count_contributions", "sphb_radial_index", "sphb_bin_sums"]
 
 
 class SphbParticles(ctypes.Structure):
@@ -88,6 +88,9 @@ def load():
     lib.sphb_line3d.argtypes = [P, K, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_int, outs, c_vp]
     lib.sphb_exact2d.argtypes = [P, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), c_vp]
     lib.sphb_exact3d_proj.argtypes = [P, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), c_vp]
+    lib.sphb_radial_index.argtypes = [c_int, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_dbl), c_int, c_vp, c_int,
+                                      c_vp, c_vp, c_vp]
+    lib.sphb_bin_sums.argtypes = [c_int, c_vp, c_int, outs, ctypes.c_int64, c_int, outs, c_vp]
     lib.sphb_normalize.argtypes = [c_vp, c_vp, ctypes.c_int64, c_vp]
     lib.sphb_count_contributions.argtypes = [P, c_dbl, R, c_int, c_dbl, c_vp, c_vp]
     for name in EXPORTS:

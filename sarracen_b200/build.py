@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 BUILD_DIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(OUT_DIR, "libsphb200.so")
-SOURCES = ["sphb_scatter.cu", "sphb_render.cu", "sphb_cell.cu", "sphb_misc.cu", "sphb_exact.cu"]
+SOURCES = ["sphb_scatter.cu", "sphb_render.cu", "sphb_cell.cu", "sphb_misc.cu", "sphb_exact.cu", "sphb_bins.cu"]
 HEADERS = [os.path.join(CSRC, "sphb_common.cuh"), os.path.join(CSRC, "sphb_scatter.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "sphb200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -156,6 +156,21 @@ class _Device:
             self.cache[name] = torch.from_numpy(arr).to(self.dev).to(self.dtype).contiguous()
         return self.cache[name]
 
+    def raw(self, name: str) -> torch.Tensor:
+        """A column on the device in ITS OWN dtype (analysis helpers that do their arithmetic in
+        double whatever the column precision)."""
+        key = ("raw", name)
+        if key not in self.cache:
+            resident = getattr(self.data, "_device_cache", None)
+            if resident and name in resident and resident[name].device == self.dev:
+                self.cache[key] = resident[name].contiguous()
+            else:
+                arr = np.ascontiguousarray(self.data[name].to_numpy())
+                if not arr.flags.writeable:
+                    arr = arr.copy()
+                self.cache[key] = torch.from_numpy(arr).to(self.dev).contiguous()
+        return self.cache[key]
+
     def mass(self):
         """interpolate.py:431-435."""
         if self.data.mcol is None:
