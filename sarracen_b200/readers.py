@@ -174,7 +174,7 @@ def _device_columns(buf, index: Dict[str, list], device, columns=None):
             lo = 0
             for off, _d, n in pieces:
                 # the bytes as they are in the file, viewed in the native kind (swapped on the device below)
-                src = torch.from_numpy(np.frombuffer(buf, native, n, off))
+                src = backend._from_numpy(np.frombuffer(buf, native, n, off))   # read-only view of the map
                 jobs.append(backend._stage_pool.submit(backend._stage_column, j % 8, src, dst[lo:lo + n],
                                                        copy_stream))
                 lo += n
