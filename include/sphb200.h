@@ -156,6 +156,40 @@ int sphb_scatter3d_staged(const sphb_particles *p, const sphb_kernel *k, const s
                           int n_stages, const int *stage_planes, sphb_stage_fn on_stage, void *user,
                           sphb_stream stream);
 
+/* Plan / execute form of the sampled scatter: NO hidden synchronisation.
+ *
+ * sphb_scatter2d / 3d read four bin totals back to size their lists, which costs one stream
+ * synchronisation per call.  A caller that wants a fully stream-asynchronous (CUDA-graph
+ * capturable) call splits it:
+ *   1. sphb_scatter_plan     count pass only; the totals are copied to `plan` (host memory,
+ *                            page-locked for a truly asynchronous copy) with cudaMemcpyAsync.  The
+ *                            caller synchronises whenever it likes -- or keeps the plan of an earlier
+ *                            call on inputs of the same statistics.
+ *   2. sphb_scatter_planned  the whole pipeline (count, emit, sort, render) with every list sized
+ *                            from `plan`; it enqueues work and returns.  ws_needed reports the exact
+ *                            workspace for that plan (call with ws = NULL to query).  If the particle
+ *                            set holds MORE than the plan says, the excess is dropped and a flag is
+ *                            raised in the workspace: sphb_scatter_overflowed() reads it (that call
+ *                            synchronises).  With the plan of the same inputs the result is that of
+ *                            sphb_scatter2d / 3d.
+ * dim3 != 0: voxel grid (use_z ignored). */
+typedef struct sphb_plan {
+    unsigned long long n_small;        /* particles of the cell path */
+    unsigned long long n_pairs;        /* (tile, particle) pairs of the tile path */
+    unsigned long long max_small_edge; /* largest box edge among the cell-path particles */
+    unsigned long long reserved0;
+    unsigned long long n_large;        /* particles of the tile path */
+    unsigned long long reserved[3];
+} sphb_plan;
+
+int sphb_scatter_plan(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int dim3, int use_z,
+                      double z_slice, void *ws, size_t ws_bytes, size_t *ws_needed, sphb_plan *plan,
+                      sphb_stream stream);
+int sphb_scatter_planned(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int dim3, int use_z,
+                         double z_slice, int accumulate, double *const *out, void *ws, size_t ws_bytes,
+                         size_t *ws_needed, const sphb_plan *plan, sphb_stream stream);
+int sphb_scatter_overflowed(const void *ws, int *flag, sphb_stream stream);
+
 /* B4 -- exact pixel-area integral of the 2-D cubic spline, replaces
  * CPUBackend._exact_2d_render (cpu_backend.py:317-447) with the integrals of
  * sarracen/kernels/cubic_spline_exact.py:7-217.  Always computes in float64.

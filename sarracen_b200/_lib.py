@@ -15,7 +15,7 @@ SPHB_CUBIC, SPHB_QUARTIC, SPHB_QUINTIC, SPHB_COLUMN_LUT = 0, 1, 2, 3
 SPHB_OK, SPHB_ERR_ARGUMENT, SPHB_ERR_WORKSPACE, SPHB_ERR_CUDA, SPHB_ERR_TOO_MANY = 0, -1, -2, -3, -4
 
 EXPORTS = ["sphb_version", "sphb_last_error", "sphb_column_kernel", "sphb_scatter2d", "sphb_scatter3d",
-           "sphb_scatter3d_staged",
+           "sphb_scatter3d_staged", "sphb_scatter_plan", "sphb_scatter_planned", "sphb_scatter_overflowed",
            "sphb_line2d", "sphb_line3d", "sphb_exact2d", "sphb_exact3d_proj", "sphb_normalize",
            "sphb_count_contributions", "sphb_radial_index", "sphb_bin_sums"]
 
@@ -45,6 +45,11 @@ class SphbStats(ctypes.Structure):
                 ("time_phases", ctypes.c_int32), ("ms_bin", ctypes.c_float), ("ms_sort", ctypes.c_float),
                 ("ms_render", ctypes.c_float), ("ms_direct", ctypes.c_float), ("launches", ctypes.c_int32),
                 ("ms_count", ctypes.c_float)]
+
+
+class SphbPlan(ctypes.Structure):
+    _fields_ = [("n_small", ctypes.c_uint64), ("n_pairs", ctypes.c_uint64), ("max_small_edge", ctypes.c_uint64),
+                ("reserved0", ctypes.c_uint64), ("n_large", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 3)]
 
 
 class SphbError(RuntimeError):
@@ -84,6 +89,11 @@ def load():
     lib.sphb_scatter3d.argtypes = [P, K, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), S, c_vp]
     lib.sphb_scatter3d_staged.argtypes = [P, K, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), S, c_int,
                                           ctypes.POINTER(c_int), STAGE_FN, c_vp, c_vp]
+    PL = ctypes.POINTER(SphbPlan)
+    lib.sphb_scatter_plan.argtypes = [P, K, R, c_int, c_int, c_dbl, c_vp, c_sz, ctypes.POINTER(c_sz), c_vp, c_vp]
+    lib.sphb_scatter_planned.argtypes = [P, K, R, c_int, c_int, c_dbl, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz),
+                                         PL, c_vp]
+    lib.sphb_scatter_overflowed.argtypes = [c_vp, ctypes.POINTER(c_int), c_vp]
     lib.sphb_line2d.argtypes = [P, K, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_int, outs, c_vp]
     lib.sphb_line3d.argtypes = [P, K, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_int, outs, c_vp]
     lib.sphb_exact2d.argtypes = [P, R, c_int, outs, c_vp, c_sz, ctypes.POINTER(c_sz), c_vp]

@@ -307,8 +307,8 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                 st.by[lane] = y0;
                 st.bz[lane] = z0;
                 const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
-                if (wx > 0 && wy > 0 && wz > 0) {
-                    SPHB_ASSERT(wx <= v.halo + 1 && wy <= v.halo + 1 && wz <= v.halo + 1);
+                // a box wider than the halo can only come with a stale plan (sphb_scatter_planned): dropped
+                if (wx > 0 && wy > 0 && wz > 0 && max(max(wx, wy), wz) <= v.halo + 1) {
                     vol = wx * wy * wz;
                     geo.x = (x0 & cmx) | ((y0 & cmy) << 8) | ((z0 & cmz) << 16);
                     geo.y = wx | (wy << 8) | (wz << 16);

@@ -147,7 +147,8 @@ render_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut
 
     while (pos < chunk_hi) {
         const uint32_t tile = keys[pos];
-        SPHB_ASSERT(tile < (uint32_t)(v.ntx * v.nty * v.ntz) && (int64_t)tile_end[tile] > pos);
+        if (tile >= (uint32_t)(v.ntx * v.nty * v.ntz)) break; // 0xffffffff padding of a planned call: nothing follows
+        SPHB_ASSERT((int64_t)tile_end[tile] > pos);
         const int64_t seg_hi = min((int64_t)tile_end[tile], chunk_hi);
         const int ttx = tile % v.ntx, tty = (tile / v.ntx) % v.nty, ttz = tile / (v.ntx * v.nty);
         const int ox = ttx * TX, oy = tty * TY, oz = ttz * TZ; // tile origin in pixels

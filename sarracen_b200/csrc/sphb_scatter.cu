@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "sphb_scatter.cuh"
@@ -98,8 +99,8 @@ __device__ __forceinline__ uint32_t tile_count(const TileBox &t)
 }
 
 // totals[0] small particles, [1] (tile, particle) pairs, [2] largest small box edge,
-// [3] cursor of the pair list (emit), [4] large particles
-enum { kTotSmall = 0, kTotPairs = 1, kTotEdge = 2, kTotCursor = 3, kTotLarge = 4, kTotCount = 8 };
+// [3] cursor of the pair list (emit), [4] large particles, [5] set when a planned call met more than its plan
+enum { kTotSmall = 0, kTotPairs = 1, kTotEdge = 2, kTotCursor = 3, kTotLarge = 4, kTotOverflow = 5, kTotCount = 8 };
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -241,7 +242,10 @@ emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0,
             int64_t pos = (int64_t)start[k] + slot[k] + __popc(peers[k] & ((1u << lane) - 1u));
             if (dbg_mode == 1) pos = (int64_t)(((uint64_t)(base + 256 * k) * 2654435761ull) % (uint64_t)n_small);
             if (dbg_mode == 3) pos = (base + 256 * k) % n_small;
-            SPHB_ASSERT(pos < n_small);
+            if (pos >= n_small) {   // only with a stale plan: drop and report
+                totals[kTotOverflow] = 1;
+                continue;
+            }
             if (dbg_mode != 2)
             write_rec<T>(v, recs_small + (size_t)pos * v.rec_stride, xs[k], ys[k], zs[k], hs[k], w0, w1, w2, w3, nw,
                          base + 256 * k);
@@ -272,7 +276,11 @@ emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0,
         if (lane == 31) first = atomicAdd(totals + kTotCursor, incl);
         first = __shfl_sync(0xffffffffu, first, 31);
         const uint64_t o0 = first + incl - c;
-        if (large && c <= kOwnPairs) {
+        if (large && o0 + c > (uint64_t)n_pairs) {   // only with a stale plan: drop and report
+            totals[kTotOverflow] = 1;
+            c = 0;
+        }
+        if (large && c > 0 && c <= kOwnPairs) {
             uint64_t o = o0;
             for (int tz = t.z0; tz <= t.z1; tz++)
                 for (int ty = t.y0; ty <= t.y1; ty++)
@@ -305,10 +313,11 @@ emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0,
     }
 }
 
-__global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t *tile_end)
+// keys >= n_tiles are the 0xffffffff padding of a planned call whose list is shorter than planned
+__global__ void tile_end_kernel(const uint32_t *keys, int64_t n_pairs, uint32_t n_tiles, uint32_t *tile_end)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pairs) return;
+    if (i >= n_pairs || keys[i] >= n_tiles) return;
     if (i == n_pairs - 1 || keys[i] != keys[i + 1]) tile_end[keys[i]] = (uint32_t)(i + 1);
 }
 
@@ -499,14 +508,11 @@ struct Stages {
     void *user;
 };
 
-template <typename T>
-static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
-                        int use_z, double z_slice, int accumulate, double *const *out, void *ws,
-                        size_t ws_bytes, size_t *ws_needed, sphb_stats *stats, const Stages &stages,
-                        cudaStream_t stream)
+// Geometry of a call: tiles, cells, record stride.
+static int build_view(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3, int use_z,
+                      double z_slice, View &v, int64_t &n_tiles, int64_t &n_cells, int &end_bit)
 {
     const bool f32 = p->dtype == SPHB_F32;
-    View v;
     v.nx = r->nx;
     v.ny = r->ny;
     v.nz = dim3 ? r->nz : 1;
@@ -544,22 +550,40 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     v.ncy = div_up(v.ny, 1 << v.cy_log);
     v.ncz = dim3 ? div_up(v.nz, 1 << v.cz_log) : 1;
     v.halo = v.small_edge > 0 ? v.small_edge - 1 : 0; // tightened below to the largest box seen
-    const int64_t n_tiles = (int64_t)v.ntx * v.nty * v.ntz;
-    const int64_t n_cells = (int64_t)v.ncx * v.ncy * v.ncz;
+    n_tiles = (int64_t)v.ntx * v.nty * v.ntz;
+    n_cells = (int64_t)v.ncx * v.ncy * v.ncz;
     if (n_tiles > 0x3fffffffLL || n_cells > 0x3fffffffLL) {
         set_error("raster has too many tiles");
         return SPHB_ERR_ARGUMENT;
     }
-    int end_bit = 1;
+    end_bit = 1;
     while ((1LL << end_bit) < n_tiles) end_bit++;
-    const int64_t n = p->n;
-    const size_t n_out = (size_t)v.nx * v.ny * v.nz;
-    v.n_out = n_out;
+    v.n_out = (size_t)v.nx * v.ny * v.nz;
 
-    if (!accumulate)
+    return SPHB_OK;
+}
+
+template <typename T>
+static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, bool dim3,
+                        int use_z, double z_slice, int accumulate, double *const *out, void *ws,
+                        size_t ws_bytes, size_t *ws_needed, sphb_stats *stats, const Stages &stages,
+                        const sphb_plan *plan, sphb_plan *plan_out, cudaStream_t stream)
+{
+    const bool f32 = p->dtype == SPHB_F32;
+    View v;
+    int64_t n_tiles = 0, n_cells = 0;
+    int end_bit = 1;
+    {
+        const int rc = build_view(p, k, r, dim3, use_z, z_slice, v, n_tiles, n_cells, end_bit);
+        if (rc) return rc;
+    }
+    const int64_t n = p->n;
+    const size_t n_out = (size_t)v.n_out;
+
+    if (!accumulate && !plan_out)
         for (int i = 0; i < p->n_weights; i++)
             SPHB_CUDA(cudaMemsetAsync(out[i], 0, n_out * sizeof(double), stream));
-    const bool timed = stats && stats->time_phases;
+    const bool timed = stats && stats->time_phases && !plan && !plan_out;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (stats) {
         stats->n_pairs = 0;
@@ -578,6 +602,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
             for (int s = 0; s < stages.n; s++) stages.fn(stages.user, s);
     };
     if (n == 0) {
+        if (plan_out) memset(plan_out, 0, sizeof(*plan_out));
         all_stages_done();
         return SPHB_OK;
     }
@@ -596,7 +621,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     unsigned char *scan_ws = a.take<unsigned char>(scan_tmp);
     const size_t need_a = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_a;
-    if (!ws || ws_bytes < need_a) {
+    if (!plan && (!ws || ws_bytes < need_a)) {
         set_error("workspace of %zu bytes needed for binning, %zu given", need_a, ws_bytes);
         return SPHB_ERR_WORKSPACE;
     }
@@ -605,18 +630,42 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     const int blocks = div_up(n, 256);
     int sms = 0;
     SPHB_CUDA(sm_count(&sms));
-    if (timed) SPHB_CUDA(cudaEventRecord(ev[0], stream));
-    SPHB_CUDA(cudaMemsetAsync(zero_block, 0, zero_words * sizeof(uint32_t), stream));
-    count_kernel<T><<<std::min<int64_t>(blocks, (int64_t)sms * 16), 256, 0, stream>>>(v, x, y, z, h, n, cell_start,
-                                                                                    totals);
-    SPHB_LAUNCH_CHECK();
-    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, cell_start, cell_start, n_cells + 1, stream));
-    if (timed) SPHB_CUDA(cudaEventRecord(ev[5], stream));
-    unsigned long long *totals_host = nullptr;
-    SPHB_CUDA(totals_landing(&totals_host));
-    SPHB_CUDA(cudaMemcpyAsync(totals_host, totals, kTotCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                              stream));
-    SPHB_CUDA(cudaStreamSynchronize(stream));
+    auto run_count = [&]() -> int {
+        if (timed) SPHB_CUDA(cudaEventRecord(ev[0], stream));
+        SPHB_CUDA(cudaMemsetAsync(zero_block, 0, zero_words * sizeof(uint32_t), stream));
+        count_kernel<T><<<std::min<int64_t>(blocks, (int64_t)sms * 16), 256, 0, stream>>>(v, x, y, z, h, n,
+                                                                                        cell_start, totals);
+        SPHB_LAUNCH_CHECK();
+        SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, cell_start, cell_start, n_cells + 1, stream));
+        if (timed) SPHB_CUDA(cudaEventRecord(ev[5], stream));
+        return SPHB_OK;
+    };
+    if (!plan) {   // a planned call counts after its whole workspace has been checked (below)
+        const int rc = run_count();
+        if (rc) return rc;
+    }
+    if (plan_out) {
+        // plan call: the totals travel to the caller's (page-locked) plan, asynchronously; nothing else
+        static_assert(sizeof(sphb_plan) == kTotCount * sizeof(unsigned long long), "plan mirrors the totals");
+        SPHB_CUDA(cudaMemcpyAsync(plan_out, totals, sizeof(sphb_plan), cudaMemcpyDeviceToHost, stream));
+        return SPHB_OK;
+    }
+    unsigned long long plan_tot[kTotCount] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long *totals_host = plan_tot;
+    if (plan) {
+        // planned call: list sizes and the accumulator halo come from the caller; no read-back, no sync
+        plan_tot[kTotSmall] = plan->n_small;
+        plan_tot[kTotPairs] = plan->n_pairs;
+        plan_tot[kTotEdge] = plan->max_small_edge;
+        plan_tot[kTotLarge] = plan->n_large;
+    } else {
+        unsigned long long *landing = nullptr;
+        SPHB_CUDA(totals_landing(&landing));
+        SPHB_CUDA(cudaMemcpyAsync(landing, totals, kTotCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  stream));
+        SPHB_CUDA(cudaStreamSynchronize(stream));
+        totals_host = landing;
+    }
     const int64_t n_small = (int64_t)totals_host[kTotSmall];
     const int64_t n_large = (int64_t)totals_host[kTotLarge];
     const uint64_t total_pairs = totals_host[kTotPairs];
@@ -641,8 +690,8 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     size_t sort_tmp = 0;
     if (n_pairs > 0)
         SPHB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                                  (uint32_t *)nullptr, (uint32_t *)nullptr, n_pairs, 0, end_bit,
-                                                  stream));
+                                                  (uint32_t *)nullptr, (uint32_t *)nullptr, n_pairs, 0,
+                                                  plan ? 32 : end_bit, stream));
     uint32_t *keys_a = a.take<uint32_t>(n_pairs);
     uint32_t *vals_a = a.take<uint32_t>(n_pairs);
     uint32_t *keys_b = a.take<uint32_t>(n_pairs);
@@ -657,11 +706,17 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     unsigned char *sort_ws = a.take<unsigned char>(sort_tmp);
     const size_t need_b = align_up(a.used, 256);
     if (ws_needed) *ws_needed = need_b;
-    if (ws_bytes < need_b) {
+    if (!ws || ws_bytes < need_b) {
         set_error("workspace of %zu bytes needed for %lld pairs and %lld cell-path particles, %zu given", need_b,
                   (long long)n_pairs, (long long)n_small, ws_bytes);
         return SPHB_ERR_WORKSPACE;
     }
+    if (plan) {
+        const int rc = run_count();
+        if (rc) return rc;
+    }
+    if (plan && n_pairs > 0)   // entries the emit kernel does not fill sort behind every tile
+        SPHB_CUDA(cudaMemsetAsync(keys_a, 0xff, (size_t)n_pairs * sizeof(uint32_t), stream));
     emit_kernel<T><<<div_up(n, 256 * kEmitPer), 256, 0, stream>>>(
         v, x, y, z, h, static_cast<const T *>(p->w[0]), static_cast<const T *>(p->w[1]),
         static_cast<const T *>(p->w[2]), static_cast<const T *>(p->w[3]), p->n_weights, n, cell_start, cell_cursor,
@@ -671,8 +726,8 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
     if (timed) SPHB_CUDA(cudaEventRecord(ev[1], stream));
     if (n_pairs > 0) {
         SPHB_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sort_tmp, keys_a, keys_b, vals_a, vals_b, n_pairs, 0,
-                                                  end_bit, stream));
-        tile_end_kernel<<<div_up(n_pairs, 256), 256, 0, stream>>>(keys_b, n_pairs, tile_end);
+                                                  plan ? 32 : end_bit, stream));
+        tile_end_kernel<<<div_up(n_pairs, 256), 256, 0, stream>>>(keys_b, n_pairs, (uint32_t)n_tiles, tile_end);
         SPHB_LAUNCH_CHECK();
     }
     if (big_lut) {
@@ -759,9 +814,65 @@ extern "C" int sphb_scatter2d(const sphb_particles *p, const sphb_kernel *k, con
     const Stages one = {1, nullptr, nullptr, nullptr};
     if (p->dtype == SPHB_F32)
         return scatter_impl<float>(p, k, r, false, use_z, z_slice, accumulate, out, ws, ws_bytes, ws_needed,
-                                   stats, one, s);
+                                   stats, one, nullptr, nullptr, s);
     return scatter_impl<double>(p, k, r, false, use_z, z_slice, accumulate, out, ws, ws_bytes, ws_needed,
-                                stats, one, s);
+                                stats, one, nullptr, nullptr, s);
+}
+
+extern "C" int sphb_scatter_plan(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int dim3,
+                                 int use_z, double z_slice, void *ws, size_t ws_bytes, size_t *ws_needed,
+                                 sphb_plan *plan, sphb_stream stream)
+{
+    double *dummy[SPHB_MAX_WEIGHTS] = {reinterpret_cast<double *>(8), reinterpret_cast<double *>(8),
+                                       reinterpret_cast<double *>(8), reinterpret_cast<double *>(8)};
+    int rc = validate(p, k, r, dim3 != 0, dim3 ? 0 : use_z, dummy);
+    if (rc) return rc;
+    if (!plan) {
+        set_error("null plan");
+        return SPHB_ERR_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Stages one = {1, nullptr, nullptr, nullptr};
+    if (p->dtype == SPHB_F32)
+        return scatter_impl<float>(p, k, r, dim3 != 0, dim3 ? 0 : use_z, z_slice, 1, dummy, ws, ws_bytes, ws_needed,
+                                   nullptr, one, nullptr, plan, s);
+    return scatter_impl<double>(p, k, r, dim3 != 0, dim3 ? 0 : use_z, z_slice, 1, dummy, ws, ws_bytes, ws_needed,
+                                nullptr, one, nullptr, plan, s);
+}
+
+extern "C" int sphb_scatter_planned(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int dim3,
+                                    int use_z, double z_slice, int accumulate, double *const *out, void *ws,
+                                    size_t ws_bytes, size_t *ws_needed, const sphb_plan *plan, sphb_stream stream)
+{
+    int rc = validate(p, k, r, dim3 != 0, dim3 ? 0 : use_z, out);
+    if (rc) return rc;
+    if (!plan || plan->n_pairs > 0x7fffffffULL) {
+        set_error(plan ? "plan holds more than 2^31-1 pairs: split the particle set" : "null plan");
+        return plan ? SPHB_ERR_TOO_MANY : SPHB_ERR_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Stages one = {1, nullptr, nullptr, nullptr};
+    if (p->dtype == SPHB_F32)
+        return scatter_impl<float>(p, k, r, dim3 != 0, dim3 ? 0 : use_z, z_slice, accumulate, out, ws, ws_bytes,
+                                   ws_needed, nullptr, one, plan, nullptr, s);
+    return scatter_impl<double>(p, k, r, dim3 != 0, dim3 ? 0 : use_z, z_slice, accumulate, out, ws, ws_bytes,
+                                ws_needed, nullptr, one, plan, nullptr, s);
+}
+
+extern "C" int sphb_scatter_overflowed(const void *ws, int *flag, sphb_stream stream)
+{
+    if (!ws || !flag) {
+        set_error("null argument");
+        return SPHB_ERR_ARGUMENT;
+    }
+    // the totals block opens the workspace (see scatter_impl)
+    unsigned long long v = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SPHB_CUDA(cudaMemcpyAsync(&v, static_cast<const unsigned long long *>(ws) + kTotOverflow, sizeof(v),
+                              cudaMemcpyDeviceToHost, s));
+    SPHB_CUDA(cudaStreamSynchronize(s));
+    *flag = v != 0;
+    return SPHB_OK;
 }
 
 extern "C" int sphb_scatter3d_staged(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r,
@@ -783,8 +894,10 @@ extern "C" int sphb_scatter3d_staged(const sphb_particles *p, const sphb_kernel 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Stages st = {n_stages, stage_planes, on_stage, user};
     if (p->dtype == SPHB_F32)
-        return scatter_impl<float>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, st, s);
-    return scatter_impl<double>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, st, s);
+        return scatter_impl<float>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, st, nullptr,
+                                   nullptr, s);
+    return scatter_impl<double>(p, k, r, true, 0, 0.0, accumulate, out, ws, ws_bytes, ws_needed, stats, st, nullptr,
+                                nullptr, s);
 }
 
 extern "C" int sphb_scatter3d(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r,

@@ -232,6 +232,104 @@ def _scatter(dim3: bool, x, y, z, h, weights, weight_function, radius, ndim, ras
     return out
 
 
+class Plan:
+    """Bin totals of one particle set on one raster (`sphb_plan`), in page-locked host memory."""
+
+    def __init__(self):
+        self.buf = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.c = _lib.SphbPlan.from_address(self.buf.data_ptr())
+
+    def __repr__(self):
+        return (f"Plan(n_small={self.c.n_small}, n_pairs={self.c.n_pairs}, n_large={self.c.n_large}, "
+                f"max_small_edge={self.c.max_small_edge})")
+
+
+def _plan_args(dim3, x, y, z, h, weights, weight_function, radius, ndim, raster, z_slice):
+    device = x.device
+    use_z = (not dim3) and z is not None and z_slice is not None
+    kern, keep = _kernel(weight_function, radius, 3 if dim3 else ndim, device)
+    part = _particles(x, y, z if (dim3 or use_z) else None, h, weights)
+    return device, use_z, kern, keep, part, raster.c()
+
+
+def scatter_plan(x, y, h, weights, weight_function, radius, ndim, raster: Raster, z=None, z_slice=None,
+                 plan: Optional[Plan] = None) -> Plan:
+    """Phase 1 of the plan / execute form (`sphb_scatter_plan`): the count pass, asynchronous; the totals
+    land in `plan` once the stream has got there (synchronise before reading or using it).  A voxel
+    raster (raster.nz > 1) plans the grid scatter."""
+    dim3 = raster.nz > 1
+    device, use_z, kern, _keep, part, rast = _plan_args(dim3, x, y, z, h, weights, weight_function, radius, ndim,
+                                                        raster, z_slice)
+    plan = plan or Plan()
+    lib = _lib.load()
+    need = ctypes.c_size_t(0)
+    with torch.cuda.device(device):
+        for _attempt in range(2):
+            ws = _workspaces.get(str(device))
+            rc = lib.sphb_scatter_plan(ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast), 1 if dim3 else 0,
+                                       1 if use_z else 0, float(z_slice or 0.0),
+                                       ctypes.c_void_p(ws.data_ptr()) if ws is not None else None,
+                                       ws.numel() if ws is not None else 0, ctypes.byref(need),
+                                       ctypes.c_void_p(plan.buf.data_ptr()), _stream(device))
+            if rc != _lib.SPHB_ERR_WORKSPACE:
+                break
+            ws = None
+            _workspace(device, need.value)
+        _lib.check(rc)
+    return plan
+
+
+def scatter_planned(plan: Plan, x, y, h, weights, weight_function, radius, ndim, raster: Raster, out, z=None,
+                    z_slice=None, accumulate=False) -> List[torch.Tensor]:
+    """Phase 2 (`sphb_scatter_planned`): the whole pipeline with every list sized from `plan` -- enqueues
+    kernels and returns, no synchronisation, CUDA-graph capturable once the workspace is large enough
+    (`scatter_planned_workspace` grows it outside the capture).  `out`: float64 rasters to fill."""
+    dim3 = raster.nz > 1
+    device, use_z, kern, _keep, part, rast = _plan_args(dim3, x, y, z, h, weights, weight_function, radius, ndim,
+                                                        raster, z_slice)
+    ws = _workspaces.get(str(device))
+    need = ctypes.c_size_t(0)
+    with torch.cuda.device(device):
+        rc = _lib.load().sphb_scatter_planned(
+            ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast), 1 if dim3 else 0, 1 if use_z else 0,
+            float(z_slice or 0.0), 1 if accumulate else 0, _out_ptrs(out),
+            ctypes.c_void_p(ws.data_ptr()) if ws is not None else None, ws.numel() if ws is not None else 0,
+            ctypes.byref(need), ctypes.byref(plan.c), _stream(device))
+    if rc == _lib.SPHB_ERR_WORKSPACE:
+        raise _lib.SphbError(rc, f"workspace of {need.value} bytes needed: call scatter_planned_workspace first")
+    _lib.check(rc)
+    return out
+
+
+def scatter_planned_workspace(plan: Plan, x, y, h, weights, weight_function, radius, ndim, raster: Raster, z=None,
+                              z_slice=None) -> int:
+    """Grow the device workspace to what `scatter_planned` needs for `plan`; returns the byte count."""
+    dim3 = raster.nz > 1
+    device, use_z, kern, _keep, part, rast = _plan_args(dim3, x, y, z, h, weights, weight_function, radius, ndim,
+                                                        raster, z_slice)
+    need = ctypes.c_size_t(0)
+    dummy = (ctypes.c_void_p * len(weights))(*[8] * len(weights))
+    with torch.cuda.device(device):
+        rc = _lib.load().sphb_scatter_planned(ctypes.byref(part), ctypes.byref(kern), ctypes.byref(rast),
+                                              1 if dim3 else 0, 1 if use_z else 0, float(z_slice or 0.0), 1, dummy,
+                                              None, 0, ctypes.byref(need), ctypes.byref(plan.c), _stream(device))
+    if rc not in (_lib.SPHB_ERR_WORKSPACE, _lib.SPHB_OK):
+        _lib.check(rc)
+    _workspace(device, need.value)
+    return int(need.value)
+
+
+def scatter_overflowed(device=None) -> bool:
+    """True if the last planned call on `device` met more particles / pairs than its plan (synchronises)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws = _workspaces[str(device)]
+    flag = ctypes.c_int(0)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().sphb_scatter_overflowed(ctypes.c_void_p(ws.data_ptr()), ctypes.byref(flag),
+                                                       _stream(device)))
+    return bool(flag.value)
+
+
 def scatter2d(x, y, h, weights, weight_function, radius, ndim, raster: Raster, z=None, z_slice=None,
               out=None, accumulate=False) -> List[torch.Tensor]:
     """B3: sampled scatter onto an image (cpu_backend.py:226-313).
