@@ -102,15 +102,19 @@ __device__ __forceinline__ Rec<float> smem_rec(const float *raw, int stride, int
 // Staging slots of one warp: one batch of 32 particles.  Everything a particle's pass needs is
 // derived here once, lane-parallel, so that the pass itself starts with a few broadcast loads.
 template <typename R, int NW> struct CellBatch {
-    R sx[32], sy[32], sz[32]; // pixel -> q along each axis (pixel width / h)
-    R ox[32], oy[32], oz[32]; // q-space offset of the box origin: -(centre - origin) * s
-    R cq[32];                 // dz^2 / h^2 of a cross-section + sqrt guard
-    R term[NW][32];           // norm * w / h^ndim
+    using R2 = typename Real2<R>::type;
+    // pairs, so that a particle's pass starts with a few 16-byte broadcast loads:
+    R2 xs[32], ys[32], zs[32]; // (s, o) per axis: pixel -> q scale (pixel width / h) and the q-space offset of
+                               // the box origin, -(centre - origin) * s
+    R2 ct[32];                 // (dz^2 / h^2 of a cross-section + sqrt guard, term[0])
+    R term[NW][32];            // norm * w / h^ndim (all weights; term[0] also in ct)
     // x: box origin inside its cell, lx | ly << 8 | lz << 16;  y: box size wx | wy << 8 | wz << 16
     // (0 = nothing to do);  z: cell id;  w: lanes per z-slice (log2) | (65536 / wx + 1) << 8
     int4 geo[32];
+    // ready-made for the accumulator pass.  x: element offset of the box origin in the accumulator;
+    // y: wx wy | z-passes << 8;  z: 65536 / (wx wy) + 1 (tiny path);  w: unused
+    int4 use[32];
     int bx[32], by[32], bz[32]; // box origin (raster pixels)
-    unsigned inv_wxy[32];       // 65536 / (wx wy) + 1
 };
 
 template <typename R> struct CellAcc {
@@ -284,25 +288,31 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                 pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, x0, x1);
                 pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, y0, y1);
                 const double sx = v.pwx * hinv, sy = v.pwy * hinv;
-                st.sx[lane] = (R)sx;
-                st.sy[lane] = (R)sy;
-                st.ox[lane] = (R)(-((xp - v.x_min) * v.inv_pwx - 0.5 - x0) * sx);
-                st.oy[lane] = (R)(-((yp - v.y_min) * v.inv_pwy - 0.5 - y0) * sy);
+                R2 pair;
+                pair.x = (R)sx;
+                pair.y = (R)(-((xp - v.x_min) * v.inv_pwx - 0.5 - x0) * sx);
+                st.xs[lane] = pair;
+                pair.x = (R)sy;
+                pair.y = (R)(-((yp - v.y_min) * v.inv_pwy - 0.5 - y0) * sy);
+                st.ys[lane] = pair;
                 double cc = 0.0;
                 if (DIM3) {
                     const double zp = (double)pr.z;
                     pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, z0, z1);
                     const double sz = v.pwz * hinv;
-                    st.sz[lane] = (R)sz;
-                    st.oz[lane] = (R)(-((zp - v.z_min) * v.inv_pwz - 0.5 - z0) * sz);
+                    pair.x = (R)sz;
+                    pair.y = (R)(-((zp - v.z_min) * v.inv_pwz - 0.5 - z0) * sz);
+                    st.zs[lane] = pair;
                 } else if (v.use_z) {
                     const double dz = v.z_slice - (double)pr.z;
                     cc = dz * dz * hinv2;
                 }
-                st.cq[lane] = (R)cc + sqrt_guard(R(0));
                 const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
 #pragma unroll
                 for (int k = 0; k < NW; k++) st.term[k][lane] = (R)((double)pr.w[k] * scale);
+                pair.x = (R)cc + sqrt_guard(R(0));
+                pair.y = (R)((double)pr.w[0] * scale);
+                st.ct[lane] = pair;
                 st.bx[lane] = x0;
                 st.by[lane] = y0;
                 st.bz[lane] = z0;
@@ -315,7 +325,10 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                     geo.z = (((z0 >> v.cz_log) * v.ncy) + (y0 >> v.cy_log)) * v.ncx + (x0 >> v.cx_log);
                     const int lpl_log = DIM3 ? min(5, 32 - __clz(wx * wy - 1)) : 5; // ceil(log2(wx wy))
                     geo.w = lpl_log | (int)((65536u / (unsigned)wx + 1u) << 8);
-                    st.inv_wxy[lane] = 65536u / (unsigned)(wx * wy) + 1u;
+                    const int s1 = (1 << v.cx_log) + v.halo, s2 = s1 * ((1 << v.cy_log) + v.halo);
+                    const int nit = (wz + (32 >> lpl_log) - 1) >> (5 - lpl_log); // z-passes of a lane
+                    st.use[lane] = make_int4((z0 & cmz) * s2 + (y0 & cmy) * s1 + (x0 & cmx), (wx * wy) | (nit << 8),
+                                             (int)(65536u / (unsigned)(wx * wy) + 1u), 0);
                 }
             }
             st.geo[lane] = geo;
@@ -339,12 +352,14 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                 const int wxy = wx * wy;
                 if (sub < wxy * wz) {
                     // sub < 16: exact small divisions by multiply-shift (reciprocals from the staging step)
-                    const int iz = (int)(((unsigned)sub * st.inv_wxy[s]) >> 16), r = sub - iz * wxy;
+                    const int iz = (int)(((unsigned)sub * (unsigned)st.use[s].z) >> 16), r = sub - iz * wxy;
                     const int iy = (int)(((unsigned)r * ((unsigned)geo.w >> 8)) >> 16), ix = r - iy * wx;
-                    const R dxs = fma((R)ix, st.sx[s], st.ox[s]), dys = fma((R)iy, st.sy[s], st.oy[s]);
-                    R q2 = fma(dys, dys, fma(dxs, dxs, st.cq[s]));
+                    const R2 xs = st.xs[s], ys = st.ys[s];
+                    const R dxs = fma((R)ix, xs.x, xs.y), dys = fma((R)iy, ys.x, ys.y);
+                    R q2 = fma(dys, dys, fma(dxs, dxs, st.ct[s].x));
                     if (DIM3) {
-                        const R dzs = fma((R)iz, st.sz[s], st.oz[s]);
+                        const R2 zz = st.zs[s];
+                        const R dzs = fma((R)iz, zz.x, zz.y);
                         q2 = fma(dzs, dzs, q2);
                     }
                     if (q2 < rad2) {
@@ -374,28 +389,30 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                 a.cz0 = st.bz[s] - (geo.x >> 16);
             }
             a.dirty = true;
-            const int wx = geo.y & 0xff, wy = (geo.y >> 8) & 0xff, wz = geo.y >> 16;
-            const int lx0 = geo.x & 0xff, ly0 = (geo.x >> 8) & 0xff, lz0 = geo.x >> 16;
-            SPHB_ASSERT(lx0 + wx <= a.s1 && (ly0 + wy) * a.s1 <= a.s2 && (lz0 + wz) * a.s2 <= a.plane);
-            const R sx = st.sx[s], sy = st.sy[s], ox = st.ox[s], oy = st.oy[s], cq = st.cq[s];
+            const int4 use = st.use[s];
+            const int wx = geo.y & 0xff, wz = geo.y >> 16;
+            const int wxy = use.y & 0xff, nit = use.y >> 8;
+            SPHB_ASSERT((geo.x & 0xff) + wx <= a.s1 && ((geo.x >> 16) + wz) * a.s2 <= a.plane);
+            const R2 xs = st.xs[s], ys = st.ys[s], ct = st.ct[s];
+            const R sx = xs.x, ox = xs.y, sy = ys.x, oy = ys.y, cq = ct.x;
             R term[NW];
+            term[0] = ct.y;
 #pragma unroll
-            for (int k = 0; k < NW; k++) term[k] = st.term[k][s];
-            const int wxy = wx * wy;
+            for (int k = 1; k < NW; k++) term[k] = st.term[k][s];
             const unsigned inv_wx = (unsigned)geo.w >> 8;
             if (DIM3) {
                 // lanes: in-plane pixel lane % lpl, z-slice lane / lpl (lpl = power of two >= wx wy, at
                 // most 32; a wider plane is covered in several rounds)
-                const R sz = st.sz[s], oz = st.oz[s];
+                const R2 zz = st.zs[s];
+                const R sz = zz.x, oz = zz.y;
                 const int lpl_log = geo.w & 0xff, lpl = 1 << lpl_log, sp = 32 >> lpl_log, zs = lane >> lpl_log;
-                const int nit = (wz + sp - 1) >> (5 - lpl_log);
                 const R dz0 = fma((R)zs, sz, oz), step = (R)sp * sz;
                 const int zstride = sp * a.s2;
                 for (int a0 = lane & (lpl - 1); a0 < wxy; a0 += lpl) {
                     const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
                     const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
                     const R qxy = fma(dys, dys, fma(dxs, dxs, cq)); // cq carries sqrt_guard()
-                    R *ap = a.acc + ((lz0 + zs) * a.s2 + (ly0 + iy) * a.s1 + lx0 + ix);
+                    R *ap = a.acc + (use.x + zs * a.s2 + iy * a.s1 + ix);
                     switch (nit) {
                     case 1: cell_column<R, KIND, NW, 1>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
                     case 2: cell_column<R, KIND, NW, 2>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
@@ -414,7 +431,7 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                     const R qxy = fma(dys, dys, fma(dxs, dxs, cq));
                     if (qxy < rad2) {
                         const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
-                        R *ap = a.acc + ((ly0 + iy) * a.s1 + lx0 + ix);
+                        R *ap = a.acc + (use.x + iy * a.s1 + ix);
 #pragma unroll
                         for (int k = 0; k < NW; k++) ap[k * plane] = fma(term[k], wv, ap[k * plane]);
                     }

@@ -79,67 +79,70 @@ __device__ __forceinline__ Angle angle_from_cos(double c)
     return a;
 }
 
-// cubic_spline_exact.py:124-155 -- region 0 < q <= 1
-__device__ __forceinline__ double f1_2d(const Angle &a, double q0)
-{
-    const double ic2 = 1.0 / (a.c * a.c);
-    const double i2 = a.tn;
-    const double i4 = (1.0 / 3.0) * a.tn * (2.0 + ic2);
-    const double s3 = a.s * (20.0 - 12.0 * a.s * a.s); // 11 sin + 3 sin 3phi
-    const double i5 = (1.0 / 16.0) * (0.5 * s3 * ic2 * ic2 + 6.0 * a.logs);
-    const double q02 = q0 * q0;
-    return 5.0 / 7.0 * q02 / kPi * (i2 - 0.75 * q02 * i4 + 0.3 * q02 * q0 * i5);
-}
+// The three closed forms of a half-segment, cubic_spline_exact.py:124-155 (region 0 < q <= 1),
+// :158-196 (1 < q <= 2) and :199-217 (q > 2), evaluated TOGETHER: they are polynomials in q0 of
+// the same few integrals I_0 = phi, I_2 = tan, I_3, I_4, I_5, all algebraic in the Angle, so the
+// three values cost little more than one and the caller selects without branching.
+struct F123 {
+    double f1, f2, f3;
+};
 
-// cubic_spline_exact.py:158-196 -- region 1 < q <= 2
-__device__ __forceinline__ double f2_2d(const Angle &a, double q0)
+__device__ __forceinline__ F123 f123_2d(const Angle &a, double q0)
 {
     const double ic = 1.0 / a.c, ic2 = ic * ic;
     const double q02 = q0 * q0, q03 = q02 * q0;
     const double i0 = a.phi, i2 = a.tn;
     const double i3 = 0.5 * (a.tn * ic + a.logs);
     const double i4 = (1.0 / 3.0) * a.tn * (2.0 + ic2);
-    const double s3 = a.s * (20.0 - 12.0 * a.s * a.s);
+    const double s3 = a.s * (20.0 - 12.0 * a.s * a.s); // 11 sin + 3 sin 3phi
     const double i5 = (1.0 / 16.0) * (0.5 * s3 * ic2 * ic2 + 6.0 * a.logs);
-    return 5.0 / 7.0 * q02 / kPi *
-           (2.0 * i2 - 2.0 * q0 * i3 + 0.75 * q02 * i4 - 0.1 * q03 * i5 - 0.1 / q02 * i0);
+    const double k = 5.0 / 7.0 * q02 / kPi;
+    F123 f;
+    f.f1 = k * (i2 - 0.75 * q02 * i4 + 0.3 * q03 * i5);
+    f.f2 = k * (2.0 * i2 - 2.0 * q0 * i3 + 0.75 * q02 * i4 - 0.1 * q03 * i5 - 0.1 / q02 * i0);
+    f.f3 = 0.5 / kPi * a.phi;
+    return f;
 }
 
-// cubic_spline_exact.py:199-217 -- region q > 2
-__device__ __forceinline__ double f3_2d(double phi) { return 0.5 / kPi * phi; }
-
-// cubic_spline_exact.py:58-121; `t` is tan(phi) of the segment end point.  Not inlined: eight call sites per
-// pixel would otherwise blow the kernel past the instruction cache (ncu: 14.6 'no instruction' stalls per
-// issue with everything inlined).
-__device__ __noinline__ double full_2d_mod(double t, double q0)
-{
-    const Angle e = angle_from_tan(t);
-    const double q = q0 / e.c;
-    if (q0 <= 1.0) {
-        if (q <= 1.0) return f1_2d(e, q0);
-        const Angle pa = angle_from_cos(q0);
-        if (q <= 2.0) return f2_2d(e, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
-        const Angle pb = angle_from_cos(0.5 * q0);
-        return f3_2d(e.phi) - f3_2d(pb.phi) + f2_2d(pb, q0) - f2_2d(pa, q0) + f1_2d(pa, q0);
-    }
-    if (q0 <= 2.0) {
-        if (q <= 2.0) return f2_2d(e, q0);
-        const Angle pb = angle_from_cos(0.5 * q0);
-        return f3_2d(e.phi) - f3_2d(pb.phi) + f2_2d(pb, q0);
-    }
-    return f3_2d(e.phi);
-}
-
-// cubic_spline_exact.py:7-55
-__device__ double line_int(double r0, double d1, double d2, double h)
+// cubic_spline_exact.py:7-55 with :58-121 (`_full_2d_mod`) regrouped.  The reference walks a
+// half-segment from the foot of the perpendicular (q = q0) to its end point (q = q0 / cos phi) and
+// switches closed form where the segment crosses q = 1 (at phi_a = acos q0) and q = 2
+// (phi_b = acos q0/2):
+//     q0 <= 1:  F = f1(e)                                            q <= 1
+//               F = f2(e) - f2(pa) + f1(pa)                          q <= 2
+//               F = f3(e) - f3(pb) + f2(pb) - f2(pa) + f1(pa)        q >  2     (and likewise for q0 > 1)
+// The crossing terms c1 = f1(pa) - f2(pa) and c2 = f2(pb) - f3(pb) depend on q0 only -- one value per
+// edge, shared by its two half-segments, and (the lanes of a warp walk a column of edges) nearly
+// warp-uniform -- so they are worked out once per edge under q0 tests, and each half-segment is
+//     F = q <= 1 ? f1(e) : q <= 2 ? f2(e) + c1 : f3(e) + c2 + c1
+// (c1 = 0 for q0 > 1, c2 = 0 for q0 > 2): no data-dependent branch on the end point's region, which
+// is what made the lanes of a warp diverge (ncu r1: 17.8 of 32 threads active).  Same terms as the
+// reference, summed in a different order.
+__device__ __noinline__ double line_int(double r0, double d1, double d2, double h)
 {
     if (r0 == 0.0) return 0.0;
     const double sign = r0 > 0.0 ? 1.0 : -1.0, ar0 = fabs(r0);
     const double q0 = ar0 / h;
-    const double fa = full_2d_mod(fabs(d1) / ar0, q0), fb = full_2d_mod(fabs(d2) / ar0, q0);
-    if (d1 * d2 >= 0.0) return sign * (fa + fb);
-    if (fabs(d1) < fabs(d2)) return sign * (fb - fa);
-    return sign * (fa - fb);
+    double c1 = 0.0, c2 = 0.0;
+    if (q0 <= 1.0) {
+        const F123 fa = f123_2d(angle_from_cos(q0), q0);
+        c1 = fa.f1 - fa.f2;
+    }
+    if (q0 <= 2.0) {
+        const F123 fb = f123_2d(angle_from_cos(0.5 * q0), q0);
+        c2 = fb.f2 - fb.f3;
+    }
+    double half[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const Angle e = angle_from_tan(fabs(k == 0 ? d1 : d2) / ar0);
+        const F123 f = f123_2d(e, q0);
+        const double q = q0 / e.c;
+        half[k] = (q <= 1.0 && q0 <= 1.0) ? f.f1 : (q <= 2.0 && q0 <= 2.0) ? f.f2 + c1 : f.f3 + c2 + c1;
+    }
+    if (d1 * d2 >= 0.0) return sign * (half[0] + half[1]);
+    if (fabs(d1) < fabs(d2)) return sign * (half[1] - half[0]);
+    return sign * (half[0] - half[1]);
 }
 
 // cubic_spline_exact.py:457-483
@@ -246,16 +249,27 @@ __device__ __forceinline__ double edge_integral(double d, const Edge3 &s)
     const double cphi = 1.0 / sec;
     const double r_ = s.r1 * sec;
     const double r2 = s.r0 * s.r0 + r_ * r_;
-    if (!(r2 <= 4.0 * s.h2)) // beyond the support: I_0 and I_1 only
+    const bool outside = !(r2 <= 4.0 * s.h2);
+    if (__all_sync(__activemask(), outside)) // the whole warp is beyond the support: I_0 and I_1 only
         return s.r0h3 / kPi * (-0.25 * s.r0h_3 * get_i1(cphi, s.a2, s.a) + s.b3 / s.r03 * phi + s.d3);
+    // One evaluation of the I terms serves the three regions: they differ in the coefficients of the same
+    // integrals, selected per lane, instead of in code the lanes of a warp would run one after the other
+    // (the end points of a column of faces straddle r = h and r = 2h).
     const ITerms t = get_i_terms(cphi, phi, tcl, s.a2, s.a);
-    if (r2 <= s.h2)
-        return s.r0h3 / kPi *
-               (1.0 / 6.0 * t.i2 - 3.0 / 40.0 * s.r0h2 * t.i4 + 1.0 / 40.0 * s.r0h3 * t.i5 + s.b1 / s.r03 * t.i0);
-    return s.r0h3 / kPi *
-           (0.25 * (4.0 / 3.0 * t.i2 - s.r0h * t.i3 + 0.3 * s.r0h2 * t.i4 - 1.0 / 30.0 * s.r0h3 * t.i5 +
-                    1.0 / 15.0 * s.r0h_3 * t.i1) +
-            s.b2 / s.r03 * t.i0 + s.d2);
+    const bool inner = r2 <= s.h2;
+    double c0, c1, c2, c3, c4, c5, add;
+    if (outside) {
+        c0 = s.b3 / s.r03; c1 = -0.25 * s.r0h_3; c2 = c3 = c4 = c5 = 0.0; add = s.d3;
+    } else if (inner) {
+        c0 = s.b1 / s.r03; c1 = 0.0; c2 = 1.0 / 6.0; c3 = 0.0; c4 = -3.0 / 40.0 * s.r0h2; c5 = 1.0 / 40.0 * s.r0h3;
+        add = 0.0;
+    } else {
+        c0 = s.b2 / s.r03; c1 = 0.25 / 15.0 * s.r0h_3; c2 = 1.0 / 3.0; c3 = -0.25 * s.r0h; c4 = 0.075 * s.r0h2;
+        c5 = -0.25 / 30.0 * s.r0h3; add = s.d2;
+    }
+    // outside the support I_2 .. I_5 are not needed (and may be huge): the zero coefficients must not meet them
+    const double hi = outside ? 0.0 : c2 * t.i2 + c3 * t.i3 + c4 * t.i4 + c5 * t.i5;
+    return s.r0h3 / kPi * (hi + c1 * t.i1 + c0 * t.i0 + add);
 }
 
 // cubic_spline_exact.py:284-350 (its diagnostic prints are dropped).  Not inlined: one copy serves the
@@ -272,8 +286,10 @@ __device__ __noinline__ double line_int3d(double r0, double r1, double d1, doubl
     }
     Edge3 s;
     edge_setup(ar0, ar1, h, s);
+    // a segment centred on the foot of the perpendicular (the along-z edges of a column's side faces:
+    // the column is centred on the particle) has two equal halves
     double int1 = edge_integral(d1, s);
-    double int2 = edge_integral(d2, s);
+    double int2 = d2 == d1 ? int1 : edge_integral(d2, s);
     if (int1 < 0.0) int1 = 0.0;
     if (int2 < 0.0) int2 = 0.0;
     if (d1 * d2 >= 0.0) return sign * (int1 + int2);
@@ -281,16 +297,28 @@ __device__ __noinline__ double line_int3d(double r0, double r1, double d1, doubl
     return sign * (int1 - int2);
 }
 
-// cubic_spline_exact.py:220-281
-__device__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx, double wy,
-                              double h)
+// cubic_spline_exact.py:220-281.  A face whose centre has the particle's x (dx = 0) or y (dy = 0) -- the
+// side faces of a pixel column, which is centred on the particle along the line of sight -- has two
+// coincident edge integrals (the reference evaluates both): they are evaluated once.
+__device__ __forceinline__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx,
+                                              double wy, double h)
 {
     const double dx = x2 - x1, dy = y2 - y1;
     double res = 0.0;
-    res += line_int3d(r0, 0.5 * wy + dy, 0.5 * wx - dx, 0.5 * wx + dx, h);
-    res += line_int3d(r0, 0.5 * wy - dy, 0.5 * wx + dx, 0.5 * wx - dx, h);
-    res += line_int3d(r0, 0.5 * wx + dx, 0.5 * wy + dy, 0.5 * wy - dy, h);
-    res += line_int3d(r0, 0.5 * wx - dx, 0.5 * wy - dy, 0.5 * wy + dy, h);
+    if (dx == 0.0) {
+        res += line_int3d(r0, 0.5 * wy + dy, 0.5 * wx, 0.5 * wx, h);
+        res += line_int3d(r0, 0.5 * wy - dy, 0.5 * wx, 0.5 * wx, h);
+        res += 2.0 * line_int3d(r0, 0.5 * wx, 0.5 * wy + dy, 0.5 * wy - dy, h);
+    } else if (dy == 0.0) {
+        res += 2.0 * line_int3d(r0, 0.5 * wy, 0.5 * wx - dx, 0.5 * wx + dx, h);
+        res += line_int3d(r0, 0.5 * wx + dx, 0.5 * wy, 0.5 * wy, h);
+        res += line_int3d(r0, 0.5 * wx - dx, 0.5 * wy, 0.5 * wy, h);
+    } else {
+        res += line_int3d(r0, 0.5 * wy + dy, 0.5 * wx - dx, 0.5 * wx + dx, h);
+        res += line_int3d(r0, 0.5 * wy - dy, 0.5 * wx + dx, 0.5 * wx - dx, h);
+        res += line_int3d(r0, 0.5 * wx + dx, 0.5 * wy + dy, 0.5 * wy - dy, h);
+        res += line_int3d(r0, 0.5 * wx - dx, 0.5 * wy - dy, 0.5 * wy + dy, h);
+    }
     return res;
 }
 
