@@ -167,7 +167,7 @@ __device__ __forceinline__ void cell_flush(CellAcc<R> &a, const View &v, int lan
 // One lane's column of a particle's box: U z-slices (iz = zs, zs + sp, ...) evaluated without
 // branches, so that the U dependent chains (q^2 -> square root -> polynomial / table) overlap; a
 // slice outside the support evaluates to W = 0 and is not stored.
-template <typename R, int KIND, int NW, int U>
+template <typename R, int KIND, int NW, int U, bool CHECKZ>
 __device__ __forceinline__ void cell_column(R qxy, R dz0, R step, int zs, int sp, int wz, R rad2, const R *term,
                                             R *ap, int zstride, int plane, const LutView<R> &lv)
 {
@@ -188,7 +188,8 @@ __device__ __forceinline__ void cell_column(R qxy, R dz0, R step, int zs, int sp
     for (int u = 0; u < U; u++) wv[u] = kernel_eval_unguarded<KIND, R>(q2[u], rad2, lv);
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        if (zs + u * sp < wz && q2[u] < rad2) {
+        // CHECKZ = false: one z-slice per pass (sp = 1), the U passes are exactly the wz slices
+        if ((!CHECKZ || zs + u * sp < wz) && q2[u] < rad2) {
             R *p = ap + u * zstride;
 #pragma unroll
             for (int k = 0; k < NW; k++) p[k * plane] = fma(term[k], wv[u], p[k * plane]);
@@ -413,16 +414,28 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                     const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
                     const R qxy = fma(dys, dys, fma(dxs, dxs, cq)); // cq carries sqrt_guard()
                     R *ap = a.acc + (use.x + zs * a.s2 + iy * a.s1 + ix);
-                    switch (nit) {
-                    case 1: cell_column<R, KIND, NW, 1>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
-                    case 2: cell_column<R, KIND, NW, 2>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
-                    case 3: cell_column<R, KIND, NW, 3>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
-                    case 4: cell_column<R, KIND, NW, 4>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
-                    case 5: cell_column<R, KIND, NW, 5>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
-                    case 6: cell_column<R, KIND, NW, 6>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
-                    case 7: cell_column<R, KIND, NW, 7>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
-                    default: cell_column<R, KIND, NW, 8>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv); break;
+#define SPHB_COLUMN(U, CZ) \
+    cell_column<R, KIND, NW, U, CZ>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv)
+                    if (sp == 1) {
+                        switch (nit) {
+                        case 1: SPHB_COLUMN(1, false); break;
+                        case 2: SPHB_COLUMN(2, false); break;
+                        case 3: SPHB_COLUMN(3, false); break;
+                        case 4: SPHB_COLUMN(4, false); break;
+                        case 5: SPHB_COLUMN(5, false); break;
+                        case 6: SPHB_COLUMN(6, false); break;
+                        case 7: SPHB_COLUMN(7, false); break;
+                        default: SPHB_COLUMN(8, false); break;
+                        }
+                    } else {
+                        switch (nit) {   // at least two slices per pass: at most four passes
+                        case 1: SPHB_COLUMN(1, true); break;
+                        case 2: SPHB_COLUMN(2, true); break;
+                        case 3: SPHB_COLUMN(3, true); break;
+                        default: SPHB_COLUMN(4, true); break;
+                        }
                     }
+#undef SPHB_COLUMN
                 }
             } else {
                 for (int a0 = lane; a0 < wxy; a0 += 32) {

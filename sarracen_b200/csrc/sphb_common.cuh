@@ -156,9 +156,10 @@ __device__ __forceinline__ float sqrt_pos(float a)
 template <int KIND, typename R> __device__ __forceinline__ R kernel_shape(R q)
 {
     if (KIND == SPHB_CUBIC) {
-        R a = R(2) - q;
-        R w = R(0.25) * a * a * a;
-        R w1 = fma(q * q, fma(R(0.75), q, R(-1.5)), R(1));
+        // (2 - q)^3 / 4 as (c (2 - q))^3 with c = 4^(-1/3): one multiply less
+        const R a = fma(q, R(-0.62996052494743658), R(1.25992104989487316));
+        const R w = a * a * a;
+        const R w1 = fma(q * q, fma(R(0.75), q, R(-1.5)), R(1));
         return q < R(1) ? w1 : w;
     } else if (KIND == SPHB_QUARTIC) {
         R a = R(2.5) - q, b = R(1.5) - q, c = R(0.5) - q;
