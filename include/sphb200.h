@@ -193,15 +193,16 @@ int sphb_scatter_overflowed(const void *ws, int *flag, sphb_stream stream);
 /* B4 -- exact pixel-area integral of the 2-D cubic spline, replaces
  * CPUBackend._exact_2d_render (cpu_backend.py:317-447) with the integrals of
  * sarracen/kernels/cubic_spline_exact.py:7-217.  Always computes in float64.
- * Workspace: 8 (n + 1) bytes + scan scratch (size reported through ws_needed);
- * fully asynchronous. */
+ * Workspace: 16 (n + 1) bytes + scan scratch + 16 bytes per lattice line of the particles' pixel
+ * boxes (reported through ws_needed in up to two rounds); synchronises the stream once (the line
+ * count sizes the table of per-line terms). */
 int sphb_exact2d(const sphb_particles *p, const sphb_raster *r, int accumulate, double *const *out,
                  void *ws, size_t ws_bytes, size_t *ws_needed, sphb_stream stream);
 
 /* B5 -- exact column integral of the 3-D cubic spline, replaces
  * CPUBackend._exact_3d_project (cpu_backend.py:611-720) with the integrals of
- * sarracen/kernels/cubic_spline_exact.py:220-483.  Always computes in float64;
- * workspace as for sphb_exact2d. */
+ * sarracen/kernels/cubic_spline_exact.py:220-483.  Always computes in float64.
+ * Workspace: 8 (n + 1) bytes + scan scratch (size reported through ws_needed); fully asynchronous. */
 int sphb_exact3d_proj(const sphb_particles *p, const sphb_raster *r, int accumulate,
                       double *const *out, void *ws, size_t ws_bytes, size_t *ws_needed, sphb_stream stream);
 

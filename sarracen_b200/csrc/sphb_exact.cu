@@ -27,6 +27,8 @@
 //    (:370, :387) and its out-of-bounds row write (:353) are not reproduced.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+
 #include "sphb_common.cuh"
 
 namespace sphb {
@@ -118,11 +120,9 @@ __device__ __forceinline__ F123 f123_2d(const Angle &a, double q0)
 // (c1 = 0 for q0 > 1, c2 = 0 for q0 > 2): no data-dependent branch on the end point's region, which
 // is what made the lanes of a warp diverge (ncu r1: 17.8 of 32 threads active).  Same terms as the
 // reference, summed in a different order.
-__device__ __noinline__ double line_int(double r0, double d1, double d2, double h)
+// crossing terms of a lattice line at normalised distance q0 (see above): (c1, c2)
+__device__ __noinline__ double2 line_crossings(double q0)
 {
-    if (r0 == 0.0) return 0.0;
-    const double sign = r0 > 0.0 ? 1.0 : -1.0, ar0 = fabs(r0);
-    const double q0 = ar0 / h;
     double c1 = 0.0, c2 = 0.0;
     if (q0 <= 1.0) {
         const F123 fa = f123_2d(angle_from_cos(q0), q0);
@@ -132,17 +132,36 @@ __device__ __noinline__ double line_int(double r0, double d1, double d2, double 
         const F123 fb = f123_2d(angle_from_cos(0.5 * q0), q0);
         c2 = fb.f2 - fb.f3;
     }
-    double half[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const Angle e = angle_from_tan(fabs(k == 0 ? d1 : d2) / ar0);
-        const F123 f = f123_2d(e, q0);
-        const double q = q0 / e.c;
-        half[k] = (q <= 1.0 && q0 <= 1.0) ? f.f1 : (q <= 2.0 && q0 <= 2.0) ? f.f2 + c1 : f.f3 + c2 + c1;
-    }
-    if (d1 * d2 >= 0.0) return sign * (half[0] + half[1]);
-    if (fabs(d1) < fabs(d2)) return sign * (half[1] - half[0]);
-    return sign * (half[0] - half[1]);
+    return make_double2(c1, c2);
+}
+
+// value of the half-segment from the foot of the perpendicular to an end point at tangent t = |d| / |r0|
+__device__ __noinline__ double half_segment(double t, double q0, double c1, double c2)
+{
+    const Angle e = angle_from_tan(t);
+    const F123 f = f123_2d(e, q0);
+    const double q = q0 / e.c;
+    return (q <= 1.0 && q0 <= 1.0) ? f.f1 : (q <= 2.0 && q0 <= 2.0) ? f.f2 + c1 : f.f3 + c2 + c1;
+}
+
+// the two half-segments of an edge combined (cubic_spline_exact.py:43-53): `ga`, `gb` are their
+// values, `da`, `db` the signed offsets of the end points from the foot of the perpendicular
+// measured along the line in ONE direction (the foot lies between them iff da db <= 0)
+__device__ __forceinline__ double combine_halves(double ga, double gb, double da, double db)
+{
+    if (da * db <= 0.0) return ga + gb;
+    return fabs(da) < fabs(db) ? gb - ga : ga - gb;
+}
+
+__device__ __noinline__ double line_int(double r0, double d1, double d2, double h)
+{
+    if (r0 == 0.0) return 0.0;
+    const double sign = r0 > 0.0 ? 1.0 : -1.0, ar0 = fabs(r0);
+    const double q0 = ar0 / h;
+    const double2 c = line_crossings(q0);
+    const double ga = half_segment(fabs(d1) / ar0, q0, c.x, c.y), gb = half_segment(fabs(d2) / ar0, q0, c.x, c.y);
+    // d1 and d2 are measured in opposite directions (cubic_spline_exact.py:7-55): d1 d2 >= 0 <=> foot inside
+    return sign * combine_halves(ga, gb, -d1, d2);
 }
 
 // cubic_spline_exact.py:457-483
@@ -520,6 +539,163 @@ exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, cons
     }
 }
 
+// ---------------------------------------------------------------------------
+// Exact 2-D render, lattice form.
+//
+// The pixel edges of a particle's box lie on the lines of a lattice: bw + 1 vertical lines with bh + 1 end
+// points each, bh + 1 horizontal lines with bw + 1 end points each.  Everything an edge integral needs
+// factors over that lattice:
+//   * the crossing terms (c1, c2) -- two inverse cosines, two logarithms, two sets of closed forms --
+//     depend on the LINE only (its distance from the particle): `exact2_lines_kernel` works them out once
+//     per line, one warp per particle with the lanes over its lines;
+//   * the half-segment value G -- one arctangent, one logarithm, one set of closed forms -- belongs to an
+//     END POINT and serves the two edges that meet there: `exact2_edges_kernel` lays its lanes over
+//     consecutive end points of a line and forms the edge between a lane and its neighbour from the two
+//     values (one shuffle).  Work units are 32 end points = 31 edges; consecutive units overlap by one
+//     end point.
+// Per edge that is one closed-form evaluation instead of four (round 1: two end points + two crossing
+// angles per edge, with the three regions as divergent branches).
+struct Exact2Box {
+    double sx, sy, sh;
+    int i0, j0, bw, bh;
+};
+
+__device__ __forceinline__ int units_of(int endpoints) { return endpoints > 1 ? (endpoints - 2) / 31 + 1 : 0; }
+
+template <typename T>
+__global__ void exact2_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
+                                    unsigned long long *units, unsigned long long *lines)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n) return;
+    unsigned long long u = 0, l = 0; // entry n stays 0: the exclusive scans leave the totals there
+    double xp, yp, hp;
+    int i0, i1, j0, j1;
+    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
+        const int bw = i1 - i0, bh = j1 - j0;
+        // end points are enumerated line by line; a unit's 31 edges may straddle lines (such edges are skipped)
+        u = (unsigned long long)(2 * units_of((bw + 1) * (bh + 1)));
+        l = (unsigned long long)(bw + bh + 2);
+    }
+    units[p] = u;
+    lines[p] = l;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+exact2_lines_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
+                    int64_t n, const unsigned long long *__restrict__ line_off, double2 *__restrict__ cross)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n; p += warps) {
+        double sx, sy, sh;
+        int i0, i1, j0, j1;
+        if (!exact_box(v, x, y, h, p, sx, sy, sh, i0, i1, j0, j1)) continue;
+        const int nv = i1 - i0 + 1, nl = nv + (j1 - j0 + 1);
+        double2 *dst = cross + line_off[p];
+        for (int t = lane; t < nl; t += 32) {
+            const double r0 = t < nv ? sx - (v.x_min + (i0 + t) * v.pwx) : sy - (v.y_min + (j0 + t - nv) * v.pwy);
+            dst[t] = ex::line_crossings(fabs(r0) / sh);
+        }
+    }
+}
+
+template <typename T, int NW>
+__global__ void __launch_bounds__(kExactWarps * 32, 8)
+exact2_edges_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
+                    const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
+                    const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets,
+                    const unsigned long long *__restrict__ line_off, const double2 *__restrict__ cross, double *o0,
+                    double *o1, double *o2, double *o3)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T *wsrc[4] = {w0, w1, w2, w3};
+    double *outs[4] = {o0, o1, o2, o3};
+    const unsigned long long total = offsets[n];
+    const unsigned long long stride = (unsigned long long)gridDim.x * kExactWarps;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * kExactWarps + warp; u < total; u += stride) {
+        // largest p with offsets[p] <= u: a 33-way search, the lanes probe 32 positions at once
+        int64_t lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const int64_t step = (hi - lo + 32) / 33;
+            const int64_t probe = lo + (int64_t)(lane + 1) * step;
+            const bool le = probe < hi && __ldg(offsets + probe) <= u;
+            const int k = __popc(__ballot_sync(0xffffffffu, le));
+            hi = min(hi, lo + (int64_t)(k + 1) * step);
+            lo = lo + (int64_t)k * step;
+        }
+        const int64_t p = lo;
+        double sx, sy, sh;
+        int i0, i1, j0, j1;
+        if (!exact_box(v, x, y, h, p, sx, sy, sh, i0, i1, j0, j1)) continue;
+        const int bw = i1 - i0, bh = j1 - j0;
+        const int half = units_of((bw + 1) * (bh + 1));
+        int ul = (int)(u - offsets[p]);
+        const bool vertical = ul < half;     // first the vertical lines, then the horizontal ones
+        if (!vertical) ul -= half;
+        // a line has `len` edges and len + 1 end points; lines are enumerated one after the other
+        const int len = vertical ? bh : bw, nlines = vertical ? bw + 1 : bh + 1;
+        const int e = ul * 31 + lane;
+        const int line = e / (len + 1), k = e - line * (len + 1);
+        const bool live = line < nlines;
+        double g = 0.0, d = 0.0, r0 = 0.0;
+        if (live) {
+            // r0: signed distance particle -> line; d: offset of the end point from the foot of the perpendicular
+            r0 = vertical ? sx - (v.x_min + (i0 + line) * v.pwx) : sy - (v.y_min + (j0 + line) * v.pwy);
+            d = vertical ? (v.y_min + (j0 + k) * v.pwy) - sy : (v.x_min + (i0 + k) * v.pwx) - sx;
+            if (r0 != 0.0) {
+                const double2 c = __ldg(cross + line_off[p] + (vertical ? line : bw + 1 + line));
+                const double ar0 = fabs(r0);
+                g = ex::half_segment(fabs(d) / ar0, ar0 / sh, c.x, c.y);
+            }
+        }
+        // the edge from this lane's end point to the next one of the same line
+        const double g_next = __shfl_down_sync(0xffffffffu, g, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
+        if (!live || lane == 31 || k >= len || r0 == 0.0) continue;
+        double val = (r0 > 0.0 ? 1.0 : -1.0) * ex::combine_halves(g, g_next, d, d_next);
+        // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (cpu_backend.py:333, :365)
+        val *= (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
+        if (val == 0.0) continue;
+        // the pixel after the line gains the integral, the pixel before it loses it (cpu_backend.py:404-440)
+        const int ia = vertical ? i0 + line : i0 + k, ja = vertical ? j0 + k : j0 + line;
+        const int ib = vertical ? ia - 1 : ia, jb = vertical ? ja : ja - 1;
+        const bool has_a = line < nlines - 1, has_b = line > 0;
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            const double wv = (double)__ldg(wsrc[q] + p) * val;
+            if (has_a) {
+                SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
+                red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
+            }
+            if (has_b) {
+                SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
+                red_add(outs[q] + (size_t)jb * v.nx + ib, -wv);
+            }
+        }
+    }
+}
+
+template <typename T, int NW>
+static int launch_exact2(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
+                         const unsigned long long *line_off, const double2 *cross, double *const *out,
+                         cudaStream_t stream)
+{
+    int sms = 0;
+    SPHB_CUDA(sm_count(&sms));
+    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NW; i++) {
+        w[i] = static_cast<const T *>(p->w[i]);
+        o[i] = out[i];
+    }
+    exact2_edges_kernel<T, NW><<<sms * 32, kExactWarps * 32, 0, stream>>>(
+        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), w[0], w[1], w[2],
+        w[3], p->n, offsets, line_off, cross, o[0], o[1], o[2], o[3]);
+    SPHB_LAUNCH_CHECK();
+    return SPHB_OK;
+}
+
 template <typename T, int NW, bool PROJ3D>
 static int launch_exact(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
                         double *const *out, cudaStream_t stream)
@@ -552,6 +728,22 @@ static int exact_nw(const ExactView &v, const sphb_particles *p, const unsigned 
     }
 }
 
+// Page-locked landing zone of the 2-D line total, one per host thread and device.
+static cudaError_t exact_landing(unsigned long long **out)
+{
+    static thread_local unsigned long long *cache[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidValue;
+    if (!cache[dev]) {
+        e = cudaHostAlloc(reinterpret_cast<void **>(&cache[dev]), sizeof(unsigned long long), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+    }
+    *out = cache[dev];
+    return cudaSuccess;
+}
+
 template <typename T>
 static int exact_typed(const ExactView &v, const sphb_particles *p, bool proj3d, double *const *out, void *ws,
                        size_t ws_bytes, size_t *ws_needed, cudaStream_t stream)
@@ -561,20 +753,54 @@ static int exact_typed(const ExactView &v, const sphb_particles *p, bool proj3d,
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned long long *)nullptr,
                                             (unsigned long long *)nullptr, n + 1, stream));
     const size_t off_bytes = align_up(sizeof(unsigned long long) * (size_t)(n + 1), 256);
-    const size_t need = off_bytes + align_up(scan_tmp, 256);
+    // 3-D projection: unit offsets + scan scratch.  2-D render: also the per-particle line offsets, and
+    // (sized after the count, below) the crossing terms of every lattice line.
+    const size_t need = (proj3d ? 1 : 2) * off_bytes + align_up(scan_tmp, 256);
     if (ws_needed) *ws_needed = need;
     if (!ws || ws_bytes < need) {
         set_error("workspace of %zu bytes needed, %zu given", need, ws_bytes);
         return SPHB_ERR_WORKSPACE;
     }
     unsigned long long *offsets = static_cast<unsigned long long *>(ws);
-    void *scan_ws = static_cast<unsigned char *>(ws) + off_bytes;
-    exact_units_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(
-        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), n, !proj3d,
-        offsets);
+    const T *x = static_cast<const T *>(p->x), *y = static_cast<const T *>(p->y), *h = static_cast<const T *>(p->h);
+    if (proj3d) {
+        void *scan_ws = static_cast<unsigned char *>(ws) + off_bytes;
+        exact_units_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, false, offsets);
+        SPHB_LAUNCH_CHECK();
+        SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
+        return exact_nw<T, true>(v, p, offsets, out, stream);
+    }
+    unsigned long long *line_off = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + off_bytes);
+    void *scan_ws = static_cast<unsigned char *>(ws) + 2 * off_bytes;
+    exact2_count_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, offsets, line_off);
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
-    return proj3d ? exact_nw<T, true>(v, p, offsets, out, stream) : exact_nw<T, false>(v, p, offsets, out, stream);
+    SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, line_off, line_off, n + 1, stream));
+    // the one synchronisation of the call: the number of lattice lines sizes the table of crossing terms
+    unsigned long long *total_lines = nullptr;
+    SPHB_CUDA(exact_landing(&total_lines));
+    SPHB_CUDA(cudaMemcpyAsync(total_lines, line_off + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    SPHB_CUDA(cudaStreamSynchronize(stream));
+    const size_t cross_off = align_up(need, 256);
+    const size_t need2 = cross_off + align_up(sizeof(double2) * (size_t)*total_lines, 256);
+    if (ws_needed) *ws_needed = need2;
+    if (ws_bytes < need2) {
+        set_error("workspace of %zu bytes needed for %llu lattice lines, %zu given", need2, *total_lines, ws_bytes);
+        return SPHB_ERR_WORKSPACE;
+    }
+    if (*total_lines == 0) return SPHB_OK;
+    double2 *cross = reinterpret_cast<double2 *>(static_cast<unsigned char *>(ws) + cross_off);
+    int sms = 0;
+    SPHB_CUDA(sm_count(&sms));
+    exact2_lines_kernel<T><<<(int)std::min<int64_t>(div_up(n, 4), (int64_t)sms * 16), 128, 0, stream>>>(v, x, y, h, n,
+                                                                                                     line_off, cross);
+    SPHB_LAUNCH_CHECK();
+    switch (p->n_weights) {
+    case 1: return launch_exact2<T, 1>(v, p, offsets, line_off, cross, out, stream);
+    case 2: return launch_exact2<T, 2>(v, p, offsets, line_off, cross, out, stream);
+    case 3: return launch_exact2<T, 3>(v, p, offsets, line_off, cross, out, stream);
+    default: return launch_exact2<T, 4>(v, p, offsets, line_off, cross, out, stream);
+    }
 }
 
 static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d, int accumulate,

@@ -389,7 +389,7 @@ def _exact(fn_name, x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
         fn = getattr(_lib.load(), fn_name)
         need = ctypes.c_size_t(0)
         ws = _workspaces.get(str(device))
-        for _attempt in range(2):
+        for _attempt in range(3):   # exact2d sizes its table of line terms after a first count
             rc = fn(ctypes.byref(part), ctypes.byref(rast), 0, _out_ptrs(out),
                     ctypes.c_void_p(ws.data_ptr()) if ws is not None else None,
                     ws.numel() if ws is not None else 0, ctypes.byref(need), _stream(device))
