@@ -316,6 +316,16 @@ __device__ __noinline__ double line_int3d(double r0, double r1, double d1, doubl
     return sign * (int1 - int2);
 }
 
+// One clamped half-segment integral of the line at distances (|r0|, r1 > 0): the end-point part of
+// line_int3d, for callers that combine the two halves of an edge themselves (lattice form below).
+__device__ __noinline__ double half_segment3d(double ar0, double r1, double d, double h)
+{
+    Edge3 s;
+    edge_setup(ar0, r1, h, s);
+    const double v = edge_integral(d, s);
+    return v < 0.0 ? 0.0 : v;
+}
+
 // cubic_spline_exact.py:220-281.  A face whose centre has the particle's x (dx = 0) or y (dy = 0) -- the
 // side faces of a pixel column, which is centred on the particle along the line of sight -- has two
 // coincident edge integrals (the reference evaluates both): they are evaluated once.
@@ -696,6 +706,159 @@ static int launch_exact2(const ExactView &v, const sphb_particles *p, const unsi
     return SPHB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Exact 3-D projection, lattice form for the side faces.
+//
+// The column of a pixel has a top and a bottom face (equal integrals) and four side faces, each shared
+// with the neighbouring column.  Take a lattice line (x = const, say) at signed distance r0 from the
+// particle and its slot between the lattice vertices k and k + 1 (offsets d_k, d_{k+1} along the line).
+// Two things live on that slot, and both feed the pixel after the line with + and the pixel before it
+// with -:
+//   the side face in the plane of the line (surface_int with the face centred on the particle along the
+//   line of sight):   S = Z(d_{k+1}) - Z(d_k) + 2 sign(r0) combine(E_k, E_{k+1})
+//       Z(d) = line_int3d(r0, r1 = d, 2h, 2h)   the edge along the line of sight through the vertex
+//       E_k  = clamped half-segment of the face's top edge: line (|r0|, r1 = 2h), end point d_k
+//   the edge of the top (= bottom) faces on the line:   2 sign(r0) combine(T_k, T_{k+1})
+//       T_k  = clamped half-segment of the line (2h, r1 = |r0|), end point d_k
+// so, as in the 2-D render, everything belongs to lattice VERTICES and serves the two slots that meet
+// there: the lanes take consecutive vertices of a line, a slot is formed from a lane and its neighbour
+// (four shuffles).  Per pixel that is 2 full edge set-ups and 6 half-segments instead of 10 and 16 (and
+// round 1's 12 and 24); vertices whose slots feed no pixel inside the reference's cull are skipped.
+template <typename T, int NW>
+__global__ void __launch_bounds__(kExactWarps * 32, 8)
+exact3_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
+              const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
+              const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets, double *o0,
+              double *o1, double *o2, double *o3)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T *wsrc[4] = {w0, w1, w2, w3};
+    double *outs[4] = {o0, o1, o2, o3};
+    const unsigned long long total = offsets[n];
+    const unsigned long long stride = (unsigned long long)gridDim.x * kExactWarps;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * kExactWarps + warp; u < total; u += stride) {
+        int64_t lo = 0, hi = n; // largest p with offsets[p] <= u (33-way search)
+        while (hi - lo > 1) {
+            const int64_t step = (hi - lo + 32) / 33;
+            const int64_t probe = lo + (int64_t)(lane + 1) * step;
+            const bool le = probe < hi && __ldg(offsets + probe) <= u;
+            const int k = __popc(__ballot_sync(0xffffffffu, le));
+            hi = min(hi, lo + (int64_t)(k + 1) * step);
+            lo = lo + (int64_t)k * step;
+        }
+        const int64_t p = lo;
+        double sx, sy, sh;
+        int i0, i1, j0, j1;
+        if (!exact_box(v, x, y, h, p, sx, sy, sh, i0, i1, j0, j1)) continue;
+        const int bw = i1 - i0, bh = j1 - j0;
+        const double pwz = 4.0 * sh, hinv2 = 1.0 / (sh * sh);
+        // the reference's cull on the pixel centre, q^2 < 4 + 3 pwx pwy / h^2 (cpu_backend.py:675)
+        const double cull = 4.0 + 3.0 * v.pwx * v.pwy * hinv2;
+        auto passes = [&](int i, int j) {
+            const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
+            return (dx * dx + dy * dy) * hinv2 < cull;
+        };
+        // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (cpu_backend.py:628-629)
+        const double h3 = sh * sh * sh;
+        const double scale = (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
+        int ul = (int)(u - offsets[p]);
+        const int half = units_of((bw + 1) * (bh + 1));
+        const bool vertical = ul < half; // lattice lines x = const first, then y = const
+        if (!vertical) ul -= half;
+        const int len = vertical ? bh : bw, nlines = vertical ? bw + 1 : bh + 1;
+        const int e = ul * 31 + lane;
+        const int line = e / (len + 1), k = e - line * (len + 1);
+        const bool live = line < nlines;
+        // slot kk of this line: the edge from vertex kk to kk + 1; pixel a lies after the line, b before it
+        auto slot_pixels = [&](int kk, int &pa_i, int &pa_j, int &pb_i, int &pb_j) {
+            pa_i = vertical ? i0 + line : i0 + kk;
+            pa_j = vertical ? j0 + kk : j0 + line;
+            pb_i = vertical ? pa_i - 1 : pa_i;
+            pb_j = vertical ? pa_j : pa_j - 1;
+        };
+        auto slot_live = [&](int kk, bool &a_ok, bool &b_ok) {
+            a_ok = b_ok = false;
+            if (kk < 0 || kk >= len) return false;
+            int ai, aj, bi, bj;
+            slot_pixels(kk, ai, aj, bi, bj);
+            a_ok = line < nlines - 1 && passes(ai, aj);
+            b_ok = line > 0 && passes(bi, bj);
+            return a_ok || b_ok;
+        };
+        bool has_a = false, has_b = false, dummy_a, dummy_b;
+        const bool mine = live && slot_live(k, has_a, has_b);
+        // a vertex is evaluated only if one of the two slots that meet there feeds a pixel inside the cull
+        const bool needed = live && (mine || slot_live(k - 1, dummy_a, dummy_b));
+        double zk = 0.0, ek = 0.0, tk = 0.0, d = 0.0, r0 = 0.0;
+        if (needed) {
+            r0 = vertical ? sx - (v.x_min + (i0 + line) * v.pwx) : sy - (v.y_min + (j0 + line) * v.pwy);
+            d = vertical ? (v.y_min + (j0 + k) * v.pwy) - sy : (v.x_min + (i0 + k) * v.pwx) - sx;
+            if (r0 != 0.0) {
+                zk = ex::line_int3d(r0, d, 0.5 * pwz, 0.5 * pwz, sh);          // side face: edge along the line of sight
+                ek = ex::half_segment3d(fabs(r0), 0.5 * pwz, d, sh);           // side face: its top edge
+                tk = ex::half_segment3d(0.5 * pwz, fabs(r0), d, sh);           // top face: the edge on this line
+            }
+        }
+        const double z_next = __shfl_down_sync(0xffffffffu, zk, 1), e_next = __shfl_down_sync(0xffffffffu, ek, 1);
+        const double t_next = __shfl_down_sync(0xffffffffu, tk, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
+        if (!mine || lane == 31 || r0 == 0.0) continue;
+        int ia, ja, ib, jb;
+        slot_pixels(k, ia, ja, ib, jb);
+        // side face + top and bottom face edges on this slot (same two pixels, same signs)
+        const double s_val = z_next - zk + 2.0 * (r0 > 0.0 ? 1.0 : -1.0) * (ex::combine_halves(ek, e_next, d, d_next) +
+                                                                          ex::combine_halves(tk, t_next, d, d_next));
+        const double val = s_val * scale;
+        if (val == 0.0) continue;
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            const double wv = (double)__ldg(wsrc[q] + p) * val;
+            if (has_a) {
+                SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
+                red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
+            }
+            if (has_b) {
+                SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
+                red_add(outs[q] + (size_t)jb * v.nx + ib, -wv);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void exact3_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
+                                    unsigned long long *units)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n) return;
+    unsigned long long u = 0;
+    double xp, yp, hp;
+    int i0, i1, j0, j1;
+    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
+        const int bw = i1 - i0, bh = j1 - j0;
+        u = (unsigned long long)(2 * units_of((bw + 1) * (bh + 1)));
+    }
+    units[p] = u;
+}
+
+template <typename T, int NW>
+static int launch_exact3(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
+                         double *const *out, cudaStream_t stream)
+{
+    int sms = 0;
+    SPHB_CUDA(sm_count(&sms));
+    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < NW; i++) {
+        w[i] = static_cast<const T *>(p->w[i]);
+        o[i] = out[i];
+    }
+    exact3_kernel<T, NW><<<sms * 32, kExactWarps * 32, 0, stream>>>(
+        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), w[0], w[1], w[2],
+        w[3], p->n, offsets, o[0], o[1], o[2], o[3]);
+    SPHB_LAUNCH_CHECK();
+    return SPHB_OK;
+}
+
 template <typename T, int NW, bool PROJ3D>
 static int launch_exact(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
                         double *const *out, cudaStream_t stream)
@@ -765,10 +928,15 @@ static int exact_typed(const ExactView &v, const sphb_particles *p, bool proj3d,
     const T *x = static_cast<const T *>(p->x), *y = static_cast<const T *>(p->y), *h = static_cast<const T *>(p->h);
     if (proj3d) {
         void *scan_ws = static_cast<unsigned char *>(ws) + off_bytes;
-        exact_units_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, false, offsets);
+        exact3_count_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, offsets);
         SPHB_LAUNCH_CHECK();
         SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
-        return exact_nw<T, true>(v, p, offsets, out, stream);
+        switch (p->n_weights) {
+        case 1: return launch_exact3<T, 1>(v, p, offsets, out, stream);
+        case 2: return launch_exact3<T, 2>(v, p, offsets, out, stream);
+        case 3: return launch_exact3<T, 3>(v, p, offsets, out, stream);
+        default: return launch_exact3<T, 4>(v, p, offsets, out, stream);
+        }
     }
     unsigned long long *line_off = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + off_bytes);
     void *scan_ws = static_cast<unsigned char *>(ws) + 2 * off_bytes;
