@@ -8,20 +8,27 @@
 // is a difference of edge/face terms that cancel to many digits.
 //
 // Decomposition: these paths cost 10^3 - 10^4 double-precision operations per
-// (particle, pixel), so accumulation is not the bottleneck but load balance is
-// (boxes range from 1 to thousands of pixels).  The work is flattened into
-// units of 32 consecutive pixels of one particle's box (count -> exclusive
-// scan); warps take units grid-stride, find the particle by binary search in
-// the scanned offsets, every lane evaluates its item and adds it to the image
-// with red.global.add.f64.
+// (particle, pixel), so accumulation is not the bottleneck; load balance (boxes
+// range from 1 to thousands of pixels) and redundant transcendental work are.
 //
-//  - 2-D: the work items are the pixel EDGES of the box, not its pixels: an
-//    interior edge's flux integral is added to the pixel on one side and
-//    subtracted from the pixel on the other (line_int is odd in r0 and symmetric
-//    in d1, d2), as the reference does (:404-440) -- two integrals per pixel
-//    instead of four.  3-D projection likewise: one item per pixel for the top /
-//    bottom faces, one per side face between neighbouring columns -- three
-//    surface integrals per pixel instead of five.
+//  - LATTICE FORM.  The pixel edges (2-D) / column faces (3-D) of a particle's
+//    box lie on the lines of a lattice, and every term of the closed forms
+//    belongs either to a lattice LINE (its distance from the particle) or to a
+//    lattice VERTEX (an end point on a line), shared by the two edges / faces
+//    that meet there.  The lanes of a warp take consecutive vertices of a line,
+//    evaluate the vertex terms once, and form each edge / face from a lane and its
+//    neighbour with shuffles; an edge / face value is added to the pixel on one
+//    side of the line and subtracted from the pixel on the other (the integrals
+//    are odd in the signed distance), as the reference does for its shared 2-D
+//    edges (:404-440).  2-D: one closed-form evaluation per edge instead of the
+//    reference's four per pixel edge pair; 3-D: 2 edge set-ups and 6 half-segments
+//    per pixel instead of the reference's ~40 `_full_integral_3d` calls.
+//  - WORK UNITS of 32 vertices (31 edges; consecutive units overlap by one
+//    vertex) are counted per particle and scanned; warps take units grid-stride
+//    and find the unit's particle by a 33-way search in the scanned offsets.
+//  - The region structure of the closed forms (q <= 1, <= 2, > 2) is evaluated
+//    without data-dependent branches: all three forms share their integrals and
+//    the result is selected (see line_crossings / half_segment).
 //  - A particle whose clamped pixel range is empty contributes nothing; the
 //    reference's lone top-row / left-column edge terms for such a particle
 //    (:370, :387) and its out-of-bounds row write (:353) are not reproduced.
@@ -151,17 +158,6 @@ __device__ __forceinline__ double combine_halves(double ga, double gb, double da
 {
     if (da * db <= 0.0) return ga + gb;
     return fabs(da) < fabs(db) ? gb - ga : ga - gb;
-}
-
-__device__ __noinline__ double line_int(double r0, double d1, double d2, double h)
-{
-    if (r0 == 0.0) return 0.0;
-    const double sign = r0 > 0.0 ? 1.0 : -1.0, ar0 = fabs(r0);
-    const double q0 = ar0 / h;
-    const double2 c = line_crossings(q0);
-    const double ga = half_segment(fabs(d1) / ar0, q0, c.x, c.y), gb = half_segment(fabs(d2) / ar0, q0, c.x, c.y);
-    // d1 and d2 are measured in opposite directions (cubic_spline_exact.py:7-55): d1 d2 >= 0 <=> foot inside
-    return sign * combine_halves(ga, gb, -d1, d2);
 }
 
 // cubic_spline_exact.py:457-483
@@ -326,31 +322,6 @@ __device__ __noinline__ double half_segment3d(double ar0, double r1, double d, d
     return v < 0.0 ? 0.0 : v;
 }
 
-// cubic_spline_exact.py:220-281.  A face whose centre has the particle's x (dx = 0) or y (dy = 0) -- the
-// side faces of a pixel column, which is centred on the particle along the line of sight -- has two
-// coincident edge integrals (the reference evaluates both): they are evaluated once.
-__device__ __forceinline__ double surface_int(double r0, double x1, double y1, double x2, double y2, double wx,
-                                              double wy, double h)
-{
-    const double dx = x2 - x1, dy = y2 - y1;
-    double res = 0.0;
-    if (dx == 0.0) {
-        res += line_int3d(r0, 0.5 * wy + dy, 0.5 * wx, 0.5 * wx, h);
-        res += line_int3d(r0, 0.5 * wy - dy, 0.5 * wx, 0.5 * wx, h);
-        res += 2.0 * line_int3d(r0, 0.5 * wx, 0.5 * wy + dy, 0.5 * wy - dy, h);
-    } else if (dy == 0.0) {
-        res += 2.0 * line_int3d(r0, 0.5 * wy, 0.5 * wx - dx, 0.5 * wx + dx, h);
-        res += line_int3d(r0, 0.5 * wx + dx, 0.5 * wy, 0.5 * wy, h);
-        res += line_int3d(r0, 0.5 * wx - dx, 0.5 * wy, 0.5 * wy, h);
-    } else {
-        res += line_int3d(r0, 0.5 * wy + dy, 0.5 * wx - dx, 0.5 * wx + dx, h);
-        res += line_int3d(r0, 0.5 * wy - dy, 0.5 * wx + dx, 0.5 * wx - dx, h);
-        res += line_int3d(r0, 0.5 * wx + dx, 0.5 * wy + dy, 0.5 * wy - dy, h);
-        res += line_int3d(r0, 0.5 * wx - dx, 0.5 * wy - dy, 0.5 * wy + dy, h);
-    }
-    return res;
-}
-
 } // namespace ex
 
 struct ExactView {
@@ -378,175 +349,6 @@ __device__ __forceinline__ bool exact_box(const ExactView &v, const T *x, const 
     j0 = (int)fmax(b0, 0.0);
     j1 = (int)fmin(b1, (double)v.ny);
     return i1 > i0 && j1 > j0;
-}
-
-// Work units: 32 consecutive pixels of one particle's box.  units[p] = number
-// of units of particle p (units[n] = 0 so the exclusive scan leaves the total
-// in units[n]).
-template <typename T>
-__global__ void exact_units_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n, bool edges,
-                                   unsigned long long *units)
-{
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > n) return;
-    unsigned long long c = 0;
-    double xp, yp, hp;
-    int i0, i1, j0, j1;
-    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
-        const int64_t bw = i1 - i0, bh = j1 - j0;
-        // work items: the pixel EDGES of the box (2-D render); its pixels (top / bottom faces) and the
-        // side faces between them (3-D projection)
-        const int64_t shared = (bw + 1) * bh + bw * (bh + 1);
-        const int64_t items = edges ? shared : bw * bh + shared;
-        c = (unsigned long long)((items + 31) / 32);
-    }
-    units[p] = c;
-}
-
-// One warp per work unit (grid-stride): the unit's particle is found by binary
-// search in the scanned unit offsets; the lanes take the unit's 32 pixels.
-template <typename T, int NW, bool PROJ3D>
-// 8 CTAs (32 warps) per SM at 64 registers: the kernel waits on instruction fetch (ncu: 2.9
-// 'no instruction' stalls per issue, 2 500+ SASS instructions of inlined log / atan / acos) and on
-// dependent FP64 chains, so resident warps are worth more than the ~200 bytes of spills
-// (profiles/r1_exact2d_v1.txt; 5 CTAs at 88 registers: 28.4 / 95.5 ms, 8 CTAs: 26.7 / 92.3 ms).
-__global__ void __launch_bounds__(kExactWarps * 32, 8)
-exact_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
-             const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
-             const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets, double *o0,
-             double *o1, double *o2, double *o3)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const T *wsrc[4] = {w0, w1, w2, w3};
-    double *outs[4] = {o0, o1, o2, o3};
-    const unsigned long long total = offsets[n];
-    const unsigned long long stride = (unsigned long long)gridDim.x * kExactWarps;
-    for (unsigned long long u = (unsigned long long)blockIdx.x * kExactWarps + warp; u < total; u += stride) {
-        // largest p with offsets[p] <= u: a 33-way search, the lanes probe 32 positions at once
-        // (5 dependent rounds of loads for 2^23 particles instead of 23)
-        int64_t lo = 0, hi = n; // offsets[lo] <= u < offsets[hi]
-        while (hi - lo > 1) {
-            const int64_t step = (hi - lo + 32) / 33;
-            const int64_t probe = lo + (int64_t)(lane + 1) * step;
-            const bool le = probe < hi && __ldg(offsets + probe) <= u;
-            const int k = __popc(__ballot_sync(0xffffffffu, le)); // offsets are non-decreasing
-            hi = min(hi, lo + (int64_t)(k + 1) * step);
-            lo = lo + (int64_t)k * step;
-        }
-        const int64_t p = lo;
-        double sx, sy, sh;
-        int si0, si1, sj0, sj1;
-        if (!exact_box(v, x, y, h, p, sx, sy, sh, si0, si1, sj0, sj1)) continue;
-        const int bw = si1 - si0, bh = sj1 - sj0;
-        const int e = (int)(u - offsets[p]) * 32 + lane;
-        if (!PROJ3D) {
-            // 2-D render (cpu_backend.py:365-440): a pixel's integral is the sum of the flux
-            // integrals over its four edges, and an interior edge serves the two pixels it
-            // separates with opposite signs (line_int is odd in r0 and symmetric in d1, d2) -- the
-            // reference shares them the same way (:404-440).  So the lanes take EDGES, not pixels:
-            // (bw + 1) bh vertical and bw (bh + 1) horizontal ones, half the integrals of four per
-            // pixel; each adds to the pixel after it and subtracts from the pixel before it.
-            const int nv = (bw + 1) * bh;
-            if (e >= nv + bw * (bh + 1)) continue;
-            double val;
-            int ia, ja, ib, jb; // pixel that gains the integral, pixel that loses it
-            bool has_a, has_b;
-            if (e < nv) {
-                // column-major: the lanes of a warp share the edge's x, hence r0 and the q0 region
-                // of the closed forms (the horizontal edges below share y the same way)
-                const int ii = e / bh, jj = e - ii * bh;
-                const int i = si0 + ii, j = sj0 + jj;
-                const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
-                val = ex::line_int(0.5 * v.pwx - dx, 0.5 * v.pwy - dy, 0.5 * v.pwy + dy, sh); // left edge of (i, j)
-                ia = i; ja = j; ib = i - 1; jb = j;
-                has_a = ii < bw; has_b = ii > 0;
-            } else {
-                const int f = e - nv;
-                const int jj = f / bw, ii = f - jj * bw;
-                const int i = si0 + ii, j = sj0 + jj;
-                const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
-                val = ex::line_int(0.5 * v.pwy - dy, 0.5 * v.pwx + dx, 0.5 * v.pwx - dx, sh); // top edge of (i, j)
-                ia = i; ja = j; ib = i; jb = j - 1;
-                has_a = jj < bh; has_b = jj > 0;
-            }
-            // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (:333, :365)
-            val *= (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
-            if (val != 0.0) {
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const double wv = (double)__ldg(wsrc[k] + p) * val;
-                    if (has_a) {
-                        SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
-                        red_add(outs[k] + (size_t)ja * v.nx + ia, wv);
-                    }
-                    if (has_b) {
-                        SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
-                        red_add(outs[k] + (size_t)jb * v.nx + ib, -wv);
-                    }
-                }
-            }
-            continue;
-        }
-        // 3-D projection (cpu_backend.py:673-713): the column of a pixel has six faces.  Top and
-        // bottom give the same integral (one item per pixel, counted twice); a side face is shared
-        // by the two columns it separates with opposite signs (surface_int is odd in r0), so the
-        // side faces are items of their own: 3 surface integrals per pixel instead of 5.  A pixel
-        // takes part only if its centre passes the reference's cull q^2 < 4 + 3 pwx pwy / h^2 (:675).
-        const int nt = bw * bh, nv = (bw + 1) * bh;
-        if (e >= nt + nv + bw * (bh + 1)) continue;
-        const double pwz = 4.0 * sh, hinv2 = 1.0 / (sh * sh);
-        const double cull = 4.0 + 3.0 * v.pwx * v.pwy * hinv2;
-        auto passes = [&](int i, int j) {
-            const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
-            return (dx * dx + dy * dy) * hinv2 < cull;
-        };
-        double s;
-        int ia, ja, ib = 0, jb = 0;
-        bool has_a, has_b = false;
-        if (e < nt) {
-            const int jj = e / bw, ii = e - jj * bw;
-            ia = si0 + ii; ja = sj0 + jj;
-            has_a = passes(ia, ja);
-            if (!has_a) continue;
-            const double xpix = v.x_min + (ia + 0.5) * v.pwx, ypix = v.y_min + (ja + 0.5) * v.pwy;
-            s = 2.0 * ex::surface_int(0.5 * pwz, sx, sy, xpix, ypix, v.pwx, v.pwy, sh);
-        } else if (e < nt + nv) {
-            const int f = e - nt;
-            const int ii = f / bh, jj = f - ii * bh; // column-major: one r0 per warp (see the 2-D path)
-            ia = si0 + ii; ja = sj0 + jj; ib = ia - 1; jb = ja;
-            has_a = ii < bw && passes(ia, ja);
-            has_b = ii > 0 && passes(ib, jb);
-            if (!has_a && !has_b) continue;
-            const double xpix = v.x_min + (ia + 0.5) * v.pwx, ypix = v.y_min + (ja + 0.5) * v.pwy;
-            s = ex::surface_int(sx - xpix + 0.5 * v.pwx, 0.0, sy, 0.0, ypix, pwz, v.pwy, sh); // -x face of (ia, ja)
-        } else {
-            const int f = e - nt - nv;
-            const int jj = f / bw, ii = f - jj * bw;
-            ia = si0 + ii; ja = sj0 + jj; ib = ia; jb = ja - 1;
-            has_a = jj < bh && passes(ia, ja);
-            has_b = jj > 0 && passes(ib, jb);
-            if (!has_a && !has_b) continue;
-            const double xpix = v.x_min + (ia + 0.5) * v.pwx, ypix = v.y_min + (ja + 0.5) * v.pwy;
-            s = ex::surface_int(sy - ypix + 0.5 * v.pwy, sx, 0.0, xpix, 0.0, v.pwx, pwz, sh); // -y face of (ia, ja)
-        }
-        // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (:628-629)
-        const double h3 = sh * sh * sh;
-        const double val = s * (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
-        if (val != 0.0) {
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                const double wv = (double)__ldg(wsrc[k] + p) * val;
-                if (has_a) {
-                    SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
-                    red_add(outs[k] + (size_t)ja * v.nx + ia, wv);
-                }
-                if (has_b) {
-                    SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
-                    red_add(outs[k] + (size_t)jb * v.nx + ib, -wv);
-                }
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -857,38 +659,6 @@ static int launch_exact3(const ExactView &v, const sphb_particles *p, const unsi
         w[3], p->n, offsets, o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
-}
-
-template <typename T, int NW, bool PROJ3D>
-static int launch_exact(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
-                        double *const *out, cudaStream_t stream)
-{
-    int sms = 0;
-    SPHB_CUDA(sm_count(&sms));
-    const int grid = sms * 32; // grid-stride over the work units
-    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
-    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < NW; i++) {
-        w[i] = static_cast<const T *>(p->w[i]);
-        o[i] = out[i];
-    }
-    exact_kernel<T, NW, PROJ3D><<<grid, kExactWarps * 32, 0, stream>>>(
-        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), w[0],
-        w[1], w[2], w[3], p->n, offsets, o[0], o[1], o[2], o[3]);
-    SPHB_LAUNCH_CHECK();
-    return SPHB_OK;
-}
-
-template <typename T, bool PROJ3D>
-static int exact_nw(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
-                    double *const *out, cudaStream_t stream)
-{
-    switch (p->n_weights) {
-    case 1: return launch_exact<T, 1, PROJ3D>(v, p, offsets, out, stream);
-    case 2: return launch_exact<T, 2, PROJ3D>(v, p, offsets, out, stream);
-    case 3: return launch_exact<T, 3, PROJ3D>(v, p, offsets, out, stream);
-    default: return launch_exact<T, 4, PROJ3D>(v, p, offsets, out, stream);
-    }
 }
 
 // Page-locked landing zone of the 2-D line total, one per host thread and device.
