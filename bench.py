@@ -13,10 +13,12 @@ A "step" is one pass of the hot path over one FIXED synthetic particle set:
              cubic kernel, h = 1.2 N^-1/3 (2h / voxel = 2.44).
   grid_hmin  the HBM-bound variant of configs[3]: same particles, h = 0.3 voxel
              with hmin=True, i.e. clamped to 0.5 voxel.
+  exact2d, exact3d   BASELINE configs[4] (sub-records only): interpolate_2d / interpolate_3d_proj with
+             exact=True, 2^23 particles, h log-uniform in [pw/20, 20 pw], 1024 x 1024.
 
 The JSON line's top level is the headline workload (default `proj`); `workloads` holds one full
 sub-record (ms_per_step, value, phases_ms, roofline incl. traffic, e2e, cpu_baseline) for every
-other workload of `--sub` (default: grid and grid_hmin), so the whole metric -- both functions,
+other workload of `--sub` (default: grid, grid_hmin, exact2d, exact3d), so the whole metric -- both functions,
 and the HBM-bound variant -- is in the one line the driver reads.
 
 `value` times the device pipeline (bin + sort + render [+ collective]) with inputs resident in
@@ -72,6 +74,17 @@ def _plummer_block(n, seed, n_total, a=1.0, rmax=10.0):
     return dict(x=r * st * np.cos(ph), y=r * st * np.sin(ph), h=h, w=w)
 
 
+def _exact_block(n, seed, n_total):
+    """centres strictly inside the image, h log-uniform in [pw/20, 20 pw]."""
+    rng = np.random.default_rng(seed)
+    pw = 1.0 / 1024
+    x = rng.uniform(0.0, 1.0, n)
+    y = rng.uniform(0.0, 1.0, n)
+    A = rng.uniform(0.0, 1.0, n)
+    h = np.exp(rng.uniform(np.log(pw / 20), np.log(20 * pw), n))
+    return dict(x=x, y=y, h=h, w=A * (1.0 / n_total))
+
+
 def _cube_block(n, seed, n_total):
     """SURVEY 8(d) config 4 (h is filled in by the workload: constant)."""
     rng = np.random.default_rng(seed)
@@ -88,6 +101,11 @@ def grid_side(n_total):
 
 def describe(name, n_total, dtype):
     """Static description of a workload (no arrays)."""
+    if name in ("exact2d", "exact3d"):
+        fn = "interpolate_2d(exact=True)" if name == "exact2d" else "interpolate_3d_proj(exact=True)"
+        return dict(key=name, name=fn, kind="cubic", lut=name == "exact3d", radius=2.0, ndim=2, fields=4,
+                    nx=1024, ny=1024, nz=1, lim=(0.0, 1.0, 0.0, 1.0), n=n_total, seed=1005,
+                    desc=f"{fn}: {n_total} uniform particles, h log-uniform in [pw/20, 20 pw], cubic, 1024x1024, f64")
     if name == "proj":
         return dict(key="proj", name="interpolate_3d_proj", kind="quintic", lut=True, radius=3.0, ndim=2, fields=4,
                     nx=2048, ny=2048, nz=1, lim=(-2.0, 2.0, -2.0, 2.0), n=n_total, seed=1002,
@@ -113,10 +131,10 @@ def generate(wl, rank, world, dtype, share=None):
     else:
         parts = []
         for b, (lo, hi) in enumerate(mine, start=len(blocks) * rank // world):
-            gen = _plummer_block if wl["key"] == "proj" else _cube_block
+            gen = {"proj": _plummer_block, "exact2d": _exact_block, "exact3d": _exact_block}.get(wl["key"], _cube_block)
             parts.append(gen(hi - lo, [wl["seed"], b], wl["n"]))
         cols = {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts]).astype(np_dtype)) for k in parts[0]}
-    if wl["key"] != "proj":
+    if wl["key"] in ("grid", "grid_hmin"):
         cols["h"] = np.full(cols["x"].shape[0], wl["hval"], dtype=np_dtype)
     return cols
 
@@ -235,9 +253,11 @@ class CpuReference:
         sl = {k: v[:ns] for k, v in cols.items()}
         hh = sl["h"] if h is None else h[:ns]
         t0 = time.perf_counter()
-        if wl["nz"] == 1:
+        if wl["key"] == "exact2d":
+            be.interpolate_2d_render(sl["x"], sl["y"], sl["w"], hh, wf, wl["radius"], wl["nx"], wl["ny"], *wl["lim"], True)
+        elif wl["nz"] == 1:
             be.interpolate_3d_projection(sl["x"], sl["y"], sl["w"], hh, wf, wl["radius"], wl["nx"], wl["ny"],
-                                         *wl["lim"], False)
+                                         *wl["lim"], wl["key"] == "exact3d")
         else:
             be.interpolate_3d_grid(sl["x"], sl["y"], sl["z"], sl["w"], hh, wf, wl["radius"], m, m, m, *wl["lim"])
         return time.perf_counter() - t0
@@ -332,7 +352,7 @@ def run_reference(args):
 
 
 def default_particles(name):
-    return 1 << 24 if name == "proj" else 1 << 27
+    return {"proj": 1 << 24, "exact2d": 1 << 23, "exact3d": 1 << 23}.get(name, 1 << 27)
 
 
 # ------------------------------------------------------------------ our arm
@@ -559,6 +579,94 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
     return rec
 
 
+def measure_exact(wl, cols, args, ctx, want_cpu):
+    """BASELINE configs[4]: the exact=True paths at full size -- device-resident time, end to end through
+    the backend, reference CPU on a sample.  Fewer steps than the scatter workloads (a step is seconds)."""
+    import torch
+    import torch.distributed as dist
+    import sarracen_b200 as s
+    from sarracen_b200 import ops, parallel
+
+    dev, world, rank = ctx["dev"], ctx["world"], ctx["rank"]
+    fn = ops.exact2d if wl["key"] == "exact2d" else ops.exact3d_proj
+    raster = ops.Raster(wl["nx"], wl["ny"], *wl["lim"])
+    devc = {k: torch.from_numpy(v).to(dev) for k, v in cols.items()}
+    steps, warm = max(1, min(args.steps, 3)), 1
+
+    def step_device():
+        out = fn(devc["x"], devc["y"], devc["h"], [devc["w"]], raster)[0]
+        if world > 1:
+            parallel.combine_image(out, dst=0)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step_device()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_device()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    e2e = None
+    if not args.no_e2e and world == 1:
+        kern = s.CubicSplineKernel()
+        wf = kern.get_column_kernel_func(1000) if wl["lut"] else kern.w
+        call = s.B200Backend.interpolate_2d_render if wl["key"] == "exact2d" else s.B200Backend.interpolate_3d_projection
+        call(cols["x"], cols["y"], cols["w"], cols["h"], wf, 2.0, wl["nx"], wl["ny"], *wl["lim"], True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call(cols["x"], cols["y"], cols["w"], cols["h"], wf, 2.0, wl["nx"], wl["ny"], *wl["lim"], True)
+        t_e2e = (time.perf_counter() - t0) / steps
+        e2e = {"value": wl["n"] / t_e2e, "unit": "particles/s", "h2d_bytes_per_step": sum(v.nbytes for v in cols.values()),
+               "d2h_bytes_per_step": wl["nx"] * wl["ny"] * 8, "ms_per_step": t_e2e * 1e3, "steps": steps,
+               "host_memory": "pageable NumPy arrays in; result in a new NumPy array"}
+    # pixel integrals: every pixel of each particle's box (2-D); pixels passing the reference's cull (3-D) are fewer
+    h = devc["h"]
+    pw = 1.0 / wl["nx"]
+    boxes = float((((4.0 * h / pw).ceil() + 1.0) ** 2).sum().item())
+    del devc
+    ops.release_workspaces()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+    ab = alg_bytes(wl, 8)
+    rec = {"metric": "particles/sec", "value": wl["n"] / (ms_step * 1e-3), "unit": "particles/s", "n_gpus": world,
+           "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl["desc"], "particles_total": wl["n"],
+                      "bbox_pixels_upper_bound": boxes * world if world > 1 else boxes},
+           "roofline": {"bound": "hbm", "achieved": ab / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": ab / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "alg_bytes": ab,
+                        "kernel": "exact2_edges_kernel" if wl["key"] == "exact2d" else "exact3_kernel",
+                        "note": "compute-bound by construction: 10^3-10^4 double-precision operations (closed forms with "
+                                "log / atan / acos) per pixel integral; the HBM fraction is reported for uniformity"},
+           "e2e": e2e, "gpu_launches": steps * (5 if wl["key"] == "exact2d" else 2)}
+    if want_cpu:
+        cpu = ctx["cpu"]
+        ns = 1 << (14 if wl["key"] == "exact2d" else 12)
+        cpu.run(wl, cols, 256)                       # JIT, untimed
+        tt = cpu.run(wl, cols, ns)
+        ns2 = int(min(wl["n"], max(ns, ns * args.cpu_budget / max(tt, 1e-3))))
+        if ns2 > 1.5 * ns:
+            ns, tt = ns2, cpu.run(wl, cols, ns2)
+        rec["cpu_baseline"] = {"value": ns / tt, "unit": "particles/s", "cores": cpu.threads, "kind": cpu.kind,
+                               "seconds": tt, "sample_particles": ns, "sample_fraction": ns / wl["n"],
+                               "sample": f"first {ns} of {wl['n']} particles of the same set, same raster, {tt:.2f} s; {cpu.note}"}
+    return rec
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -589,7 +697,10 @@ def run_gpu(args):
         if name in ("grid", "grid_hmin"):
             shared = cols
         sampler = ClockSampler(local) if (i == 0 and rank == 0 and not os.environ.get("BENCH_NO_CLOCKS")) else None
-        records[name] = measure(wl, cols, args, ctx, want_cpu, sampler)
+        if name in ("exact2d", "exact3d"):
+            records[name] = measure_exact(wl, cols, args, ctx, want_cpu)
+        else:
+            records[name] = measure(wl, cols, args, ctx, want_cpu, sampler)
         del cols
     if rank == 0:
         line = records[names[0]]
@@ -607,7 +718,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="proj", choices=["proj", "grid", "grid_hmin"])
-    ap.add_argument("--sub", default="grid,grid_hmin",
+    ap.add_argument("--sub", default="grid,grid_hmin,exact2d,exact3d",
                     help="comma list of further workloads reported as sub-records under `workloads` ('none')")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--particles", type=int, default=0, help="override the TOTAL particle count of every workload")
