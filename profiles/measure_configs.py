@@ -91,6 +91,22 @@ for dt in (np.float32, np.float64):
     del xd, yd, zd, hd, wd, wx, wy
     torch.cuda.empty_cache()
 
+# ---- huge footprints on the sampled path (missing #7): h >> tile.  2^14 particles whose support
+# spans 200 .. 2000 pixels of a 2048^2 image (up to the whole image: ~1000 tile pairs per particle)
+n = 1 << 14
+rng = np.random.default_rng(1007)
+x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+h = np.exp(rng.uniform(np.log(50 / 2048), np.log(500 / 2048), n))
+w = rng.uniform(0, 1, n) / n
+r = ops.Raster(2048, 2048, 0, 1, 0, 1)
+for dt in (np.float64, np.float32):
+    xd, yd, hd, wd = (dv(a, dt) for a in (x, y, h, w))
+    for kern, wf, nd in (("cubic", k.w, 2), ("cubic column table", k.get_column_kernel_func(1000), 2)):
+        ms = timed(lambda: ops.scatter2d(xd, yd, hd, [wd], wf, 2, nd, r))
+        c = ops.count_contributions(xd, yd, hd, 2.0, r)
+        record(f"huge footprints (box 200-2000 px) 2048^2 {kern} {np.dtype(dt).name}", n, ms, contributions=c,
+               contributions_per_s=c / (ms * 1e-3), stats=dict(ops.last_stats))
+
 # ---- config 5 (BASELINE configs[4]): exact paths, 2^23 particles, h log-uniform [pw/20, 20 pw], 1024^2
 pw = 1.0 / 1024
 for name, n_full, fn in (("exact2d", 1 << 23, ops.exact2d), ("exact3d_proj", 1 << 23, ops.exact3d_proj)):

@@ -442,9 +442,14 @@ class B200Backend:
         return _host(parallel.gather_slabs(slab, int(z_pixels), mode))
 
 
-def install() -> None:
-    """Route Sarracen's backend='gpu' to `B200Backend` (see module docstring)."""
+def install() -> type:
+    """Route Sarracen's backend='gpu' to `B200Backend` (see module docstring).  The class installed is
+    `B200Backend` re-based on Sarracen's own `BaseBackend` (base_backend.py:7), so `isinstance` /
+    `issubclass` checks against the reference interface hold; it is returned."""
     import sarracen.interpolate
     import sarracen.interpolate.interpolate as front
-    front.GPUBackend = B200Backend
-    sarracen.interpolate.GPUBackend = B200Backend
+    from sarracen.interpolate.base_backend import BaseBackend
+    cls = type("B200Backend", (B200Backend, BaseBackend), {"__doc__": B200Backend.__doc__})
+    front.GPUBackend = cls
+    sarracen.interpolate.GPUBackend = cls
+    return cls

@@ -13,8 +13,12 @@ def test_install_routes_backend_gpu():
     sar = ref_shim.load_reference()
     import sarracen_b200
     from sarracen.interpolate import interpolate as front
-    sarracen_b200.install()
-    assert front.get_backend("gpu") is sarracen_b200.B200Backend
+    installed = sarracen_b200.install()
+    from sarracen.interpolate.base_backend import BaseBackend
+    assert front.get_backend("gpu") is installed
+    assert issubclass(installed, sarracen_b200.B200Backend) and issubclass(installed, BaseBackend)
+    for name in (n for n in vars(BaseBackend) if n.startswith("interpolate_")):     # our method, not the stub
+        assert getattr(installed, name) is getattr(sarracen_b200.B200Backend, name)
     assert front.get_backend("cpu") is sar.interpolate.CPUBackend
     with pytest.raises(ValueError):
         front.get_backend("tpu")
