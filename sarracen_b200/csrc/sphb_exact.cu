@@ -59,6 +59,7 @@ namespace ex {
 __device__ __noinline__ double m_log(double a) { return log(a); }
 __device__ __noinline__ double m_atan(double a) { return atan(a); }
 __device__ __noinline__ double m_acos(double a) { return acos(a); }
+__device__ __noinline__ double m_atan2(double a, double b) { return atan2(a, b); }
 
 struct Angle {
     double s, c, tn, logs, phi;
@@ -173,8 +174,8 @@ __device__ __noinline__ ITerms get_i_terms(double cosp, double p, double tn, dou
     const double cosp2 = cosp * cosp;
     const double mu2_1 = 1.0 / (1.0 + cosp2 / a2);
     const double u2 = (1.0 - cosp2) * mu2_1, u = sqrt(u2);
-    const double logs = log((1.0 + u) / (1.0 - u));
-    const double i1 = atan2(u, a);
+    const double logs = m_log((1.0 + u) / (1.0 - u));
+    const double i1 = m_atan2(u, a);
     const double fac = 1.0 / (1.0 - u2);
     const double im1 = 0.5 * a * logs + i1;
     const double im3 = im1 + a * 0.25 * (1.0 + a2) * (2.0 * u * fac + logs);
@@ -188,9 +189,9 @@ __device__ __noinline__ ITerms get_i_terms(double cosp, double p, double tn, dou
     return t;
 }
 
-__device__ __forceinline__ ITerms get_i_terms_cos(double cosp, double a2, double a)
+__device__ __noinline__ ITerms get_i_terms_cos(double cosp, double a2, double a)
 {
-    return get_i_terms(cosp, acos(cosp), sqrt(1.0 - cosp * cosp) / cosp, a2, a);
+    return get_i_terms(cosp, m_acos(cosp), sqrt(1.0 - cosp * cosp) / cosp, a2, a);
 }
 
 // I_1 alone (the only term besides I_0 = phi that the region outside the kernel support needs):
@@ -200,7 +201,7 @@ __device__ __forceinline__ double get_i1(double cosp, double a2, double a)
     const double cosp2 = cosp * cosp;
     const double mu2_1 = 1.0 / (1.0 + cosp2 / a2);
     const double u = sqrt((1.0 - cosp2) * mu2_1);
-    return atan2(u, a);
+    return m_atan2(u, a);
 }
 
 // cubic_spline_exact.py:353-454, split in two.  The reference evaluates `full_integral_3d(d, r0, r1, h)`
@@ -258,7 +259,7 @@ __device__ __forceinline__ double edge_integral(double d, const Edge3 &s)
     // phi = atan(|d| / r1): its cosine and tangent are algebraic in t = |d| / r1
     const double tphi = fabs(d) / s.r1;
     if (s.zero || tphi == 0.0) return 0.0;
-    const double phi = atan(tphi);
+    const double phi = m_atan(tphi);
     const double tcl = fmin(tphi, 1e150);
     const double sec = sqrt(fma(tcl, tcl, 1.0)); // 1 / cos(phi)
     const double cphi = 1.0 / sec;
@@ -287,38 +288,49 @@ __device__ __forceinline__ double edge_integral(double d, const Edge3 &s)
     return s.r0h3 / kPi * (hi + c1 * t.i1 + c0 * t.i0 + add);
 }
 
-// cubic_spline_exact.py:284-350 (its diagnostic prints are dropped).  Not inlined: one copy serves the
-// 20 edges of a pixel column (instruction cache, see full_2d_mod).
-__device__ __noinline__ double line_int3d(double r0, double r1, double d1, double d2, double h)
+// The edge along the line of sight through a lattice vertex: cubic_spline_exact.py:284-350 for a
+// segment centred on the foot of the perpendicular (the column is centred on the particle), whose two
+// half-segments are equal: line_int3d(r0, r1, dhalf, dhalf, h) = sign * 2 * max(I(dhalf), 0).  Not
+// inlined: one copy serves the kernel (instruction cache).
+__device__ __noinline__ double los_edge(double r0, double r1, double dhalf, double h)
 {
     if (fabs(r0) == 0.0) return 0.0;
     double sign = r0 > 0.0 ? 1.0 : -1.0;
-    const double ar0 = fabs(r0);
     double ar1 = r1;
     if (!(r1 > 0.0)) {
         sign = -sign;
         ar1 = -r1;
     }
     Edge3 s;
-    edge_setup(ar0, ar1, h, s);
-    // a segment centred on the foot of the perpendicular (the along-z edges of a column's side faces:
-    // the column is centred on the particle) has two equal halves
-    double int1 = edge_integral(d1, s);
-    double int2 = d2 == d1 ? int1 : edge_integral(d2, s);
-    if (int1 < 0.0) int1 = 0.0;
-    if (int2 < 0.0) int2 = 0.0;
-    if (d1 * d2 >= 0.0) return sign * (int1 + int2);
-    if (fabs(d1) < fabs(d2)) return sign * (int2 - int1);
-    return sign * (int1 - int2);
+    edge_setup(fabs(r0), ar1, h, s);
+    const double v = edge_integral(dhalf, s);
+    return v > 0.0 ? sign * (v + v) : 0.0;
 }
 
-// One clamped half-segment integral of the line at distances (|r0|, r1 > 0): the end-point part of
-// line_int3d, for callers that combine the two halves of an edge themselves (lattice form below).
-__device__ __noinline__ double half_segment3d(double ar0, double r1, double d, double h)
+// One clamped half-segment integral of a line that lies wholly outside the kernel support,
+// r0^2 + r1^2 >= (2h)^2 -- the top edges of the side faces (r1 = 2h) and the edges of the top faces
+// (r0 = 2h) of a column of height 4h.  There D2 = D3 = 0 and only I_0 = phi and I_1 appear
+// (cubic_spline_exact.py:391-397, :438-447): an arctangent and an atan2, no logarithm, no inverse cosine.
+__device__ __noinline__ double half_outside(double ar0, double r1, double d, double h)
 {
-    Edge3 s;
-    edge_setup(ar0, r1, h, s);
-    const double v = edge_integral(d, s);
+    const double r0h = ar0 / h;
+    const double tphi = fabs(d) / r1;
+    if (r0h == 0.0 || r1 / h == 0.0 || tphi == 0.0) return 0.0;
+    const double r03 = ar0 * ar0 * ar0;
+    const double r0h2 = r0h * r0h, r0h3 = r0h2 * r0h;
+    const double r0h_2 = 1.0 / r0h2, r0h_3 = 1.0 / r0h3;
+    double b3;
+    if (ar0 > 2.0 * h)
+        b3 = 0.25 * h * h * h;
+    else if (ar0 > h)
+        b3 = 0.25 * r03 * (-4.0 / 3.0 + r0h - 0.3 * r0h2 + 1.0 / 30.0 * r0h3 - 1.0 / 15.0 * r0h_3 + 8.0 / 5.0 * r0h_2);
+    else
+        b3 = 0.25 * r03 * (-2.0 / 3.0 + 0.3 * r0h2 - 0.1 * r0h3 + 1.4 * r0h_2);
+    const double a = r1 / ar0;
+    const double phi = m_atan(tphi);
+    const double tcl = fmin(tphi, 1e150);
+    const double cphi = 1.0 / sqrt(fma(tcl, tcl, 1.0));
+    const double v = r0h3 / kPi * (-0.25 * r0h_3 * get_i1(cphi, a * a, a) + b3 / r03 * phi + 0.0);
     return v < 0.0 ? 0.0 : v;
 }
 
@@ -518,7 +530,7 @@ static int launch_exact2(const ExactView &v, const sphb_particles *p, const unsi
 // with -:
 //   the side face in the plane of the line (surface_int with the face centred on the particle along the
 //   line of sight):   S = Z(d_{k+1}) - Z(d_k) + 2 sign(r0) combine(E_k, E_{k+1})
-//       Z(d) = line_int3d(r0, r1 = d, 2h, 2h)   the edge along the line of sight through the vertex
+//       Z(d) = line_int3d(r0, r1 = d, 2h, 2h)   the edge along the line of sight through the vertex (los_edge)
 //       E_k  = clamped half-segment of the face's top edge: line (|r0|, r1 = 2h), end point d_k
 //   the edge of the top (= bottom) faces on the line:   2 sign(r0) combine(T_k, T_{k+1})
 //       T_k  = clamped half-segment of the line (2h, r1 = |r0|), end point d_k
@@ -596,9 +608,9 @@ exact3_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, con
             r0 = vertical ? sx - (v.x_min + (i0 + line) * v.pwx) : sy - (v.y_min + (j0 + line) * v.pwy);
             d = vertical ? (v.y_min + (j0 + k) * v.pwy) - sy : (v.x_min + (i0 + k) * v.pwx) - sx;
             if (r0 != 0.0) {
-                zk = ex::line_int3d(r0, d, 0.5 * pwz, 0.5 * pwz, sh);          // side face: edge along the line of sight
-                ek = ex::half_segment3d(fabs(r0), 0.5 * pwz, d, sh);           // side face: its top edge
-                tk = ex::half_segment3d(0.5 * pwz, fabs(r0), d, sh);           // top face: the edge on this line
+                zk = ex::los_edge(r0, d, 0.5 * pwz, sh);                       // side face: edge along the line of sight
+                ek = ex::half_outside(fabs(r0), 0.5 * pwz, d, sh);             // side face: its top edge
+                tk = ex::half_outside(0.5 * pwz, fabs(r0), d, sh);             // top face: the edge on this line
             }
         }
         const double z_next = __shfl_down_sync(0xffffffffu, zk, 1), e_next = __shfl_down_sync(0xffffffffu, ek, 1);
