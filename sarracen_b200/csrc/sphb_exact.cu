@@ -310,27 +310,29 @@ __device__ __noinline__ double los_edge(double r0, double r1, double dhalf, doub
 // One clamped half-segment integral of a line that lies wholly outside the kernel support,
 // r0^2 + r1^2 >= (2h)^2 -- the top edges of the side faces (r1 = 2h) and the edges of the top faces
 // (r0 = 2h) of a column of height 4h.  There D2 = D3 = 0 and only I_0 = phi and I_1 appear
-// (cubic_spline_exact.py:391-397, :438-447): an arctangent and an atan2, no logarithm, no inverse cosine.
+// (cubic_spline_exact.py:391-397, :438-447):
+//     F = (r0/h)^3 / pi * ( -(h/r0)^3 / 4 * I_1 + B3 / r0^3 * phi ) = ( B3 / h^3 * phi - I_1 / 4 ) / pi,
+// with phi = atan(|d| / r1) and, from cubic_spline_exact.py:457-483 with cos(phi) = 1 / sqrt(1 + t^2),
+// t = |d| / r1, a = r1 / r0:   I_1 = atan2(u, a),  u^2 = a^2 t^2 / (a^2 (1 + t^2) + 1), i.e.
+//     I_1 = atan( |d| r0 / (r1 sqrt(r0^2 + r1^2 + d^2)) ).
+// B3 / h^3 is a polynomial in r0 / h (the reference's negative powers of r0/h cancel against r0^3):
+// two arctangents, two divisions and a square root, no logarithm, no inverse cosine.
 __device__ __noinline__ double half_outside(double ar0, double r1, double d, double h)
 {
-    const double r0h = ar0 / h;
-    const double tphi = fabs(d) / r1;
-    if (r0h == 0.0 || r1 / h == 0.0 || tphi == 0.0) return 0.0;
-    const double r03 = ar0 * ar0 * ar0;
-    const double r0h2 = r0h * r0h, r0h3 = r0h2 * r0h;
-    const double r0h_2 = 1.0 / r0h2, r0h_3 = 1.0 / r0h3;
-    double b3;
+    const double ad = fabs(d);
+    if (ar0 == 0.0 || r1 == 0.0 || ad == 0.0) return 0.0;
+    const double q = ar0 / h, q2 = q * q, q3 = q2 * q;
+    double b3; // B3 / h^3
     if (ar0 > 2.0 * h)
-        b3 = 0.25 * h * h * h;
+        b3 = 0.25;
     else if (ar0 > h)
-        b3 = 0.25 * r03 * (-4.0 / 3.0 + r0h - 0.3 * r0h2 + 1.0 / 30.0 * r0h3 - 1.0 / 15.0 * r0h_3 + 8.0 / 5.0 * r0h_2);
+        b3 = 0.25 * (q3 * (-4.0 / 3.0 + q - 0.3 * q2 + 1.0 / 30.0 * q3) - 1.0 / 15.0 + 1.6 * q);
     else
-        b3 = 0.25 * r03 * (-2.0 / 3.0 + 0.3 * r0h2 - 0.1 * r0h3 + 1.4 * r0h_2);
-    const double a = r1 / ar0;
-    const double phi = m_atan(tphi);
-    const double tcl = fmin(tphi, 1e150);
-    const double cphi = 1.0 / sqrt(fma(tcl, tcl, 1.0));
-    const double v = r0h3 / kPi * (-0.25 * r0h_3 * get_i1(cphi, a * a, a) + b3 / r03 * phi + 0.0);
+        b3 = 0.25 * (q3 * (-2.0 / 3.0 + 0.3 * q2 - 0.1 * q3) + 1.4 * q);
+    const double rinv = 1.0 / r1;
+    const double phi = m_atan(ad * rinv);
+    const double i1 = m_atan(ad * rinv * (ar0 * rsqrt(fma(ar0, ar0, fma(r1, r1, ad * ad)))));
+    const double v = (1.0 / kPi) * fma(b3, phi, -0.25 * i1);
     return v < 0.0 ? 0.0 : v;
 }
 
@@ -339,6 +341,7 @@ __device__ __noinline__ double half_outside(double ar0, double r1, double d, dou
 struct ExactView {
     int nx, ny;
     double x_min, y_min, pwx, pwy;
+    double inv_area; // 1 / (pwx pwy)
 };
 
 constexpr int kExactWarps = 4;
@@ -537,9 +540,98 @@ static int launch_exact2(const ExactView &v, const sphb_particles *p, const unsi
 // so, as in the 2-D render, everything belongs to lattice VERTICES and serves the two slots that meet
 // there: the lanes take consecutive vertices of a line, a slot is formed from a lane and its neighbour
 // (four shuffles).  Per pixel that is 2 full edge set-ups and 6 half-segments instead of 10 and 16 (and
-// round 1's 12 and 24); vertices whose slots feed no pixel inside the reference's cull are skipped.
+// round 1's 12 and 24).
+//
+// Which vertices: the reference evaluates a pixel only if its centre passes q^2 < 4 + 3 pwx pwy / h^2
+// (cpu_backend.py:675), a disc inside the box, so ~ 1 - pi/4 of the lattice is never needed.  The lines
+// of each orientation are cut into at most 32 GROUPS of G consecutive lines; a group keeps, of every line,
+// only the vertex range its widest chord of that disc can reach (widened by one pixel, so rounding cannot
+// lose a pixel the cull accepts; the cull itself is still applied per pixel).  Inside a group the
+// (line, vertex) numbering is rectangular, the groups are laid end to end, and that sequence is cut into
+// units of 32 vertices overlapping by one.  A warp takes kExact3Chunk consecutive units of one particle,
+// so the search for the particle, its box and the group table are worked out once per chunk.
+constexpr int kExact3Chunk = 16;
+constexpr int kExact3Groups = 32;
+
+struct Box3 {
+    double sx, sy, sh, r2cull;
+    int i0, j0, bw, bh;
+};
+
+// Lines [g G, g G + nl) of one orientation: the vertex range [klo, klo + cnt) kept of each (cnt = 0: none).
+__device__ __forceinline__ void exact3_group(const ExactView &v, const Box3 &b, bool vertical, int G, int g, int &nl,
+                                             int &klo, int &cnt)
+{
+    const int nlines = (vertical ? b.bw : b.bh) + 1, len = vertical ? b.bh : b.bw;
+    const int l0 = g * G;
+    nl = min(G, nlines - l0);
+    klo = cnt = 0;
+    if (nl <= 0) {
+        nl = 0;
+        return;
+    }
+    // across the lines: the pixel columns beside them, centres a0 .. a1; nearest one to the particle
+    const double pa = vertical ? v.pwx : v.pwy, oa = vertical ? v.x_min + b.i0 * v.pwx : v.y_min + b.j0 * v.pwy;
+    const double sa = vertical ? b.sx : b.sy;
+    const int c0 = max(l0 - 1, 0), c1 = min(l0 + nl - 1, nlines - 2);
+    const double a0 = oa + (c0 + 0.5) * pa, a1 = oa + (c1 + 0.5) * pa;
+    const double dmin = sa < a0 ? a0 - sa : sa > a1 ? sa - a1 : 0.0;
+    const double c = b.r2cull - dmin * dmin;
+    if (!(c > 0.0)) return;
+    // along the lines: pixels whose centre lies within the chord, one more on either side
+    const double half = sqrt(c);
+    const double pl = vertical ? v.pwy : v.pwx, ol = vertical ? v.y_min + b.j0 * v.pwy : v.x_min + b.i0 * v.pwx;
+    const double sl = vertical ? b.sy : b.sx;
+    const double lo = floor((sl - half - ol) / pl - 0.5), hi = ceil((sl + half - ol) / pl - 0.5);
+    const int jlo = (int)fmax(lo, 0.0), jhi = (int)fmin(hi, (double)(len - 1));
+    if (jlo > jhi) return;
+    klo = jlo;
+    cnt = jhi - jlo + 2;
+}
+
+template <typename T>
+__device__ __forceinline__ bool exact3_box(const ExactView &v, const T *x, const T *y, const T *h, int64_t p, Box3 &b)
+{
+    int i1, j1;
+    if (!exact_box(v, x, y, h, p, b.sx, b.sy, b.sh, b.i0, i1, b.j0, j1)) return false;
+    b.bw = i1 - b.i0;
+    b.bh = j1 - b.j0;
+    b.r2cull = 4.0 * b.sh * b.sh + 3.0 * v.pwx * v.pwy;   // (4 + 3 pwx pwy / h^2) h^2
+    return true;
+}
+
+__device__ __forceinline__ int chunks_of(unsigned long long vertices)
+{
+    return vertices > 1 ? (int)((((vertices - 2) / 31 + 1) + kExact3Chunk - 1) / kExact3Chunk) : 0;
+}
+
+template <typename T>
+__global__ void exact3_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
+                                    unsigned long long *chunks)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n) return;
+    unsigned long long total = 0;
+    Box3 b;
+    if (p < n && exact3_box(v, x, y, h, p, b)) {
+        for (int o = 0; o < 2; o++) {
+            const int nlines = (o == 0 ? b.bw : b.bh) + 1, G = (nlines + kExact3Groups - 1) / kExact3Groups;
+            for (int g = 0; g * G < nlines; g++) {
+                int nl, klo, cnt;
+                exact3_group(v, b, o == 0, G, g, nl, klo, cnt);
+                total += (unsigned long long)nl * cnt;
+            }
+        }
+    }
+    chunks[p] = (unsigned long long)chunks_of(total);
+}
+
+#ifndef SPHB_EXACT3_MINB
+#define SPHB_EXACT3_MINB 8
+#endif
+
 template <typename T, int NW>
-__global__ void __launch_bounds__(kExactWarps * 32, 8)
+__global__ void __launch_bounds__(kExactWarps * 32, SPHB_EXACT3_MINB)
 exact3_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
               const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
               const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets, double *o0,
@@ -561,97 +653,100 @@ exact3_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, con
             lo = lo + (int64_t)k * step;
         }
         const int64_t p = lo;
-        double sx, sy, sh;
-        int i0, i1, j0, j1;
-        if (!exact_box(v, x, y, h, p, sx, sy, sh, i0, i1, j0, j1)) continue;
-        const int bw = i1 - i0, bh = j1 - j0;
-        const double pwz = 4.0 * sh, hinv2 = 1.0 / (sh * sh);
-        // the reference's cull on the pixel centre, q^2 < 4 + 3 pwx pwy / h^2 (cpu_backend.py:675)
-        const double cull = 4.0 + 3.0 * v.pwx * v.pwy * hinv2;
-        auto passes = [&](int i, int j) {
-            const double dx = v.x_min + (i + 0.5) * v.pwx - sx, dy = v.y_min + (j + 0.5) * v.pwy - sy;
-            return (dx * dx + dy * dy) * hinv2 < cull;
-        };
-        // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (cpu_backend.py:628-629)
-        const double h3 = sh * sh * sh;
-        const double scale = (h3 / (v.pwx * v.pwy * (1.0 / kPi))) * ((1.0 / kPi) / h3);
-        int ul = (int)(u - offsets[p]);
-        const int half = units_of((bw + 1) * (bh + 1));
-        const bool vertical = ul < half; // lattice lines x = const first, then y = const
-        if (!vertical) ul -= half;
-        const int len = vertical ? bh : bw, nlines = vertical ? bw + 1 : bh + 1;
-        const int e = ul * 31 + lane;
-        const int line = e / (len + 1), k = e - line * (len + 1);
-        const bool live = line < nlines;
-        // slot kk of this line: the edge from vertex kk to kk + 1; pixel a lies after the line, b before it
-        auto slot_pixels = [&](int kk, int &pa_i, int &pa_j, int &pb_i, int &pb_j) {
-            pa_i = vertical ? i0 + line : i0 + kk;
-            pa_j = vertical ? j0 + kk : j0 + line;
-            pb_i = vertical ? pa_i - 1 : pa_i;
-            pb_j = vertical ? pa_j : pa_j - 1;
-        };
-        auto slot_live = [&](int kk, bool &a_ok, bool &b_ok) {
-            a_ok = b_ok = false;
-            if (kk < 0 || kk >= len) return false;
-            int ai, aj, bi, bj;
-            slot_pixels(kk, ai, aj, bi, bj);
-            a_ok = line < nlines - 1 && passes(ai, aj);
-            b_ok = line > 0 && passes(bi, bj);
-            return a_ok || b_ok;
-        };
-        bool has_a = false, has_b = false, dummy_a, dummy_b;
-        const bool mine = live && slot_live(k, has_a, has_b);
-        // a vertex is evaluated only if one of the two slots that meet there feeds a pixel inside the cull
-        const bool needed = live && (mine || slot_live(k - 1, dummy_a, dummy_b));
-        double zk = 0.0, ek = 0.0, tk = 0.0, d = 0.0, r0 = 0.0;
-        if (needed) {
-            r0 = vertical ? sx - (v.x_min + (i0 + line) * v.pwx) : sy - (v.y_min + (j0 + line) * v.pwy);
-            d = vertical ? (v.y_min + (j0 + k) * v.pwy) - sy : (v.x_min + (i0 + k) * v.pwx) - sx;
-            if (r0 != 0.0) {
-                zk = ex::los_edge(r0, d, 0.5 * pwz, sh);                       // side face: edge along the line of sight
-                ek = ex::half_outside(fabs(r0), 0.5 * pwz, d, sh);             // side face: its top edge
-                tk = ex::half_outside(0.5 * pwz, fabs(r0), d, sh);             // top face: the edge on this line
-            }
-        }
-        const double z_next = __shfl_down_sync(0xffffffffu, zk, 1), e_next = __shfl_down_sync(0xffffffffu, ek, 1);
-        const double t_next = __shfl_down_sync(0xffffffffu, tk, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
-        if (!mine || lane == 31 || r0 == 0.0) continue;
-        int ia, ja, ib, jb;
-        slot_pixels(k, ia, ja, ib, jb);
-        // side face + top and bottom face edges on this slot (same two pixels, same signs)
-        const double s_val = z_next - zk + 2.0 * (r0 > 0.0 ? 1.0 : -1.0) * (ex::combine_halves(ek, e_next, d, d_next) +
-                                                                          ex::combine_halves(tk, t_next, d, d_next));
-        const double val = s_val * scale;
-        if (val == 0.0) continue;
+        Box3 b;
+        if (!exact3_box(v, x, y, h, p, b)) continue;
+        // group table: lane g holds group g of either orientation, start = first vertex number of the group
+        const int Gv = (b.bw + kExact3Groups) / kExact3Groups, Gh = (b.bh + kExact3Groups) / kExact3Groups;
+        int nl_v, klo_v, cnt_v, nl_h, klo_h, cnt_h;
+        exact3_group(v, b, true, Gv, lane, nl_v, klo_v, cnt_v);
+        exact3_group(v, b, false, Gh, lane, nl_h, klo_h, cnt_h);
+        int start_v = nl_v * cnt_v, start_h = nl_h * cnt_h;
 #pragma unroll
-        for (int q = 0; q < NW; q++) {
-            const double wv = (double)__ldg(wsrc[q] + p) * val;
-            if (has_a) {
-                SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
-                red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tv = __shfl_up_sync(0xffffffffu, start_v, o), th = __shfl_up_sync(0xffffffffu, start_h, o);
+            if (lane >= o) {
+                start_v += tv;
+                start_h += th;
             }
-            if (has_b) {
-                SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
-                red_add(outs[q] + (size_t)jb * v.nx + ib, -wv);
+        }
+        const int total_v = __shfl_sync(0xffffffffu, start_v, 31);
+        const int total_all = total_v + __shfl_sync(0xffffffffu, start_h, 31);
+        start_v -= nl_v * cnt_v;                       // exclusive
+        start_h += total_v - nl_h * cnt_h;
+
+        // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (cpu_backend.py:628-629)
+        const double scale = v.inv_area;
+        const double two_h = 2.0 * b.sh;
+        const int units = (total_all - 2) / 31 + 1;
+        const int ul0 = (int)(u - offsets[p]) * kExact3Chunk, ul1 = min(ul0 + kExact3Chunk, units);
+        for (int ul = ul0; ul < ul1; ul++) {
+            const int e = ul * 31 + lane;
+            const bool vertical = e < total_v;
+            // the group holding vertex e: the last one whose start is <= e
+            int g = 0;
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+                const int cand = g + st;
+                const int sv = __shfl_sync(0xffffffffu, start_v, cand), sh_ = __shfl_sync(0xffffffffu, start_h, cand);
+                if ((vertical ? sv : sh_) <= e) g = cand;
+            }
+            const int gs_v = __shfl_sync(0xffffffffu, start_v, g), gs_h = __shfl_sync(0xffffffffu, start_h, g);
+            const int gk_v = __shfl_sync(0xffffffffu, klo_v, g), gk_h = __shfl_sync(0xffffffffu, klo_h, g);
+            const int gc_v = __shfl_sync(0xffffffffu, cnt_v, g), gc_h = __shfl_sync(0xffffffffu, cnt_h, g);
+            const int gstart = vertical ? gs_v : gs_h, klo = vertical ? gk_v : gk_h;
+            const int cnt = max(vertical ? gc_v : gc_h, 1);
+            const int f = e - gstart, fl = f / cnt;
+            const int line = g * (vertical ? Gv : Gh) + fl, k = klo + (f - fl * cnt);
+            const bool live = e < total_all;
+            const bool last = k == klo + cnt - 1;               // the line's last kept vertex: no slot after it
+            const int len = vertical ? b.bh : b.bw, nlines = (vertical ? b.bw : b.bh) + 1;
+            // signed distance of the particle from the line, offset of the vertex along it
+            const double r0 = vertical ? b.sx - (v.x_min + (b.i0 + line) * v.pwx) : b.sy - (v.y_min + (b.j0 + line) * v.pwy);
+            const double d = vertical ? (v.y_min + (b.j0 + k) * v.pwy) - b.sy : (v.x_min + (b.i0 + k) * v.pwx) - b.sx;
+            // the four pixels around the vertex: a / b = after / before the line, rows k and k - 1
+            // (centre offsets as functions of the pixel index alone: the two lanes that share a slot must agree)
+            const double pa = vertical ? v.pwx : v.pwy, pl = vertical ? v.pwy : v.pwx;
+            const double oa = vertical ? v.x_min - b.sx : v.y_min - b.sy, ol = vertical ? v.y_min - b.sy : v.x_min - b.sx;
+            const int ca = (vertical ? b.i0 : b.j0) + line, cl = (vertical ? b.j0 : b.i0) + k;
+            const double xa = fma(ca + 0.5, pa, oa), xb = fma(ca - 0.5, pa, oa);
+            const double y1 = fma(cl + 0.5, pl, ol), y0 = fma(cl - 0.5, pl, ol);
+            const double xa2 = xa * xa, xb2 = xb * xb, y12 = y1 * y1, y02 = y0 * y0;
+            const bool col_a = live && line < nlines - 1, col_b = live && line > 0;
+            const bool has_a = col_a && k < len && !last && xa2 + y12 < b.r2cull;
+            const bool has_b = col_b && k < len && !last && xb2 + y12 < b.r2cull;
+            const bool mine = has_a || has_b;
+            // a vertex is evaluated only if one of the two slots that meet there feeds a pixel inside the cull
+            const bool needed = mine || (k > klo && ((col_a && xa2 + y02 < b.r2cull) || (col_b && xb2 + y02 < b.r2cull)));
+            double zk = 0.0, ek = 0.0, tk = 0.0;
+            if (needed && r0 != 0.0) {
+                zk = ex::los_edge(r0, d, two_h, b.sh);                 // side face: edge along the line of sight
+                ek = ex::half_outside(fabs(r0), two_h, d, b.sh);       // side face: its top edge
+                tk = ex::half_outside(two_h, fabs(r0), d, b.sh);       // top face: the edge on this line
+            }
+            const double z_next = __shfl_down_sync(0xffffffffu, zk, 1), e_next = __shfl_down_sync(0xffffffffu, ek, 1);
+            const double t_next = __shfl_down_sync(0xffffffffu, tk, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
+            if (!mine || lane == 31 || r0 == 0.0) continue;
+            // side face + top and bottom face edges on this slot (same two pixels, same signs)
+            const double s_val = z_next - zk + 2.0 * (r0 > 0.0 ? 1.0 : -1.0) * (ex::combine_halves(ek, e_next, d, d_next) +
+                                                                              ex::combine_halves(tk, t_next, d, d_next));
+            const double val = s_val * scale;
+            if (val == 0.0) continue;
+            const int ia = vertical ? b.i0 + line : b.i0 + k, ja = vertical ? b.j0 + k : b.j0 + line;
+            const int ib = vertical ? ia - 1 : ia, jb = vertical ? ja : ja - 1;
+#pragma unroll
+            for (int q = 0; q < NW; q++) {
+                const double wv = (double)__ldg(wsrc[q] + p) * val;
+                if (has_a) {
+                    SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
+                    red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
+                }
+                if (has_b) {
+                    SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
+                    red_add(outs[q] + (size_t)jb * v.nx + ib, -wv);
+                }
             }
         }
     }
-}
-
-template <typename T>
-__global__ void exact3_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
-                                    unsigned long long *units)
-{
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > n) return;
-    unsigned long long u = 0;
-    double xp, yp, hp;
-    int i0, i1, j0, j1;
-    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
-        const int bw = i1 - i0, bh = j1 - j0;
-        u = (unsigned long long)(2 * units_of((bw + 1) * (bh + 1)));
-    }
-    units[p] = u;
 }
 
 template <typename T, int NW>
@@ -789,6 +884,7 @@ static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d
     v.y_min = r->y_min;
     v.pwx = (r->x_max - r->x_min) / r->nx;
     v.pwy = (r->y_max - r->y_min) / r->ny;
+    v.inv_area = 1.0 / (v.pwx * v.pwy);
     if (p->dtype == SPHB_F32) return exact_typed<float>(v, p, proj3d, out, ws, ws_bytes, ws_needed, stream);
     return exact_typed<double>(v, p, proj3d, out, ws, ws_bytes, ws_needed, stream);
 }
