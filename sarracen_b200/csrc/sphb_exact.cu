@@ -389,6 +389,10 @@ struct Exact2Box {
 
 __device__ __forceinline__ int units_of(int endpoints) { return endpoints > 1 ? (endpoints - 2) / 31 + 1 : 0; }
 
+// Units of one particle a warp takes in a row: the search for the particle, its box and its constants are
+// worked out once per chunk (they were two thirds of the instructions when every unit did them).
+constexpr int kExact2Chunk = 16;
+
 template <typename T>
 __global__ void exact2_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
                                     unsigned long long *units, unsigned long long *lines)
@@ -401,7 +405,8 @@ __global__ void exact2_count_kernel(ExactView v, const T *x, const T *y, const T
     if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
         const int bw = i1 - i0, bh = j1 - j0;
         // end points are enumerated line by line; a unit's 31 edges may straddle lines (such edges are skipped)
-        u = (unsigned long long)(2 * units_of((bw + 1) * (bh + 1)));
+        // (a warp takes kExact2Chunk consecutive units of a particle: the count is in chunks)
+        u = (unsigned long long)((2 * units_of((bw + 1) * (bh + 1)) + kExact2Chunk - 1) / kExact2Chunk);
         l = (unsigned long long)(bw + bh + 2);
     }
     units[p] = u;
@@ -458,46 +463,51 @@ exact2_edges_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ 
         if (!exact_box(v, x, y, h, p, sx, sy, sh, i0, i1, j0, j1)) continue;
         const int bw = i1 - i0, bh = j1 - j0;
         const int half = units_of((bw + 1) * (bh + 1));
-        int ul = (int)(u - offsets[p]);
-        const bool vertical = ul < half;     // first the vertical lines, then the horizontal ones
-        if (!vertical) ul -= half;
-        // a line has `len` edges and len + 1 end points; lines are enumerated one after the other
-        const int len = vertical ? bh : bw, nlines = vertical ? bw + 1 : bh + 1;
-        const int e = ul * 31 + lane;
-        const int line = e / (len + 1), k = e - line * (len + 1);
-        const bool live = line < nlines;
-        double g = 0.0, d = 0.0, r0 = 0.0;
-        if (live) {
-            // r0: signed distance particle -> line; d: offset of the end point from the foot of the perpendicular
-            r0 = vertical ? sx - (v.x_min + (i0 + line) * v.pwx) : sy - (v.y_min + (j0 + line) * v.pwy);
-            d = vertical ? (v.y_min + (j0 + k) * v.pwy) - sy : (v.x_min + (i0 + k) * v.pwx) - sx;
-            if (r0 != 0.0) {
-                const double2 c = __ldg(cross + line_off[p] + (vertical ? line : bw + 1 + line));
-                const double ar0 = fabs(r0);
-                g = ex::half_segment(fabs(d) / ar0, ar0 / sh, c.x, c.y);
-            }
-        }
-        // the edge from this lane's end point to the next one of the same line
-        const double g_next = __shfl_down_sync(0xffffffffu, g, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
-        if (!live || lane == 31 || k >= len || r0 == 0.0) continue;
-        double val = (r0 > 0.0 ? 1.0 : -1.0) * ex::combine_halves(g, g_next, d, d_next);
+        const unsigned long long lbase = line_off[p];
         // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (cpu_backend.py:333, :365)
-        val *= (1.0 / fabs(v.pwx * v.pwy) * sh * sh) / (sh * sh);
-        if (val == 0.0) continue;
-        // the pixel after the line gains the integral, the pixel before it loses it (cpu_backend.py:404-440)
-        const int ia = vertical ? i0 + line : i0 + k, ja = vertical ? j0 + k : j0 + line;
-        const int ib = vertical ? ia - 1 : ia, jb = vertical ? ja : ja - 1;
-        const bool has_a = line < nlines - 1, has_b = line > 0;
+        double wp[NW];
 #pragma unroll
-        for (int q = 0; q < NW; q++) {
-            const double wv = (double)__ldg(wsrc[q] + p) * val;
-            if (has_a) {
-                SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
-                red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
+        for (int q = 0; q < NW; q++) wp[q] = (double)__ldg(wsrc[q] + p) * v.inv_area;
+        const int c0 = (int)(u - offsets[p]) * kExact2Chunk, c1 = min(c0 + kExact2Chunk, 2 * half);
+        for (int uc = c0; uc < c1; uc++) {
+            const bool vertical = uc < half;     // first the vertical lines, then the horizontal ones
+            const int ul = vertical ? uc : uc - half;
+            // a line has `len` edges and len + 1 end points; lines are enumerated one after the other
+            const int len = vertical ? bh : bw, nlines = vertical ? bw + 1 : bh + 1;
+            const int e = ul * 31 + lane;
+            const int line = e / (len + 1), k = e - line * (len + 1);
+            const bool live = line < nlines;
+            double g = 0.0, d = 0.0, r0 = 0.0;
+            if (live) {
+                // r0: signed distance particle -> line; d: offset of the end point from the foot of the perpendicular
+                r0 = vertical ? sx - (v.x_min + (i0 + line) * v.pwx) : sy - (v.y_min + (j0 + line) * v.pwy);
+                d = vertical ? (v.y_min + (j0 + k) * v.pwy) - sy : (v.x_min + (i0 + k) * v.pwx) - sx;
+                if (r0 != 0.0) {
+                    const double2 c = __ldg(cross + lbase + (vertical ? line : bw + 1 + line));
+                    const double ar0 = fabs(r0);
+                    g = ex::half_segment(fabs(d) / ar0, ar0 / sh, c.x, c.y); // same q0 as the lines kernel
+                }
             }
-            if (has_b) {
-                SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
-                red_add(outs[q] + (size_t)jb * v.nx + ib, -wv);
+            // the edge from this lane's end point to the next one of the same line
+            const double g_next = __shfl_down_sync(0xffffffffu, g, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
+            if (!live || lane == 31 || k >= len || r0 == 0.0) continue;
+            const double val = (r0 > 0.0 ? 1.0 : -1.0) * ex::combine_halves(g, g_next, d, d_next);
+            if (val == 0.0) continue;
+            // the pixel after the line gains the integral, the pixel before it loses it (cpu_backend.py:404-440)
+            const int ia = vertical ? i0 + line : i0 + k, ja = vertical ? j0 + k : j0 + line;
+            const int ib = vertical ? ia - 1 : ia, jb = vertical ? ja : ja - 1;
+            const bool has_a = line < nlines - 1, has_b = line > 0;
+#pragma unroll
+            for (int q = 0; q < NW; q++) {
+                const double wv = wp[q] * val;
+                if (has_a) {
+                    SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
+                    red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
+                }
+                if (has_b) {
+                    SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
+                    red_add(outs[q] + (size_t)jb * v.nx + ib, -wv);
+                }
             }
         }
     }
@@ -675,7 +685,9 @@ exact3_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, con
         start_h += total_v - nl_h * cnt_h;
 
         // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (cpu_backend.py:628-629)
-        const double scale = v.inv_area;
+        double wp[NW];
+#pragma unroll
+        for (int q = 0; q < NW; q++) wp[q] = (double)__ldg(wsrc[q] + p) * v.inv_area;
         const double two_h = 2.0 * b.sh;
         const int units = (total_all - 2) / 31 + 1;
         const int ul0 = (int)(u - offsets[p]) * kExact3Chunk, ul1 = min(ul0 + kExact3Chunk, units);
@@ -729,13 +741,12 @@ exact3_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, con
             // side face + top and bottom face edges on this slot (same two pixels, same signs)
             const double s_val = z_next - zk + 2.0 * (r0 > 0.0 ? 1.0 : -1.0) * (ex::combine_halves(ek, e_next, d, d_next) +
                                                                               ex::combine_halves(tk, t_next, d, d_next));
-            const double val = s_val * scale;
-            if (val == 0.0) continue;
+            if (s_val == 0.0) continue;
             const int ia = vertical ? b.i0 + line : b.i0 + k, ja = vertical ? b.j0 + k : b.j0 + line;
             const int ib = vertical ? ia - 1 : ia, jb = vertical ? ja : ja - 1;
 #pragma unroll
             for (int q = 0; q < NW; q++) {
-                const double wv = (double)__ldg(wsrc[q] + p) * val;
+                const double wv = wp[q] * s_val;
                 if (has_a) {
                     SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
                     red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
