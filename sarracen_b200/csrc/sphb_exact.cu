@@ -24,8 +24,10 @@
 //    reference's four per pixel edge pair; 3-D: 2 edge set-ups and 6 half-segments
 //    per pixel instead of the reference's ~40 `_full_integral_3d` calls.
 //  - WORK UNITS of 32 vertices (31 edges; consecutive units overlap by one
-//    vertex) are counted per particle and scanned; warps take units grid-stride
-//    and find the unit's particle by a 33-way search in the scanned offsets.
+//    vertex) are counted per particle in chunks of 16 and scanned; warps take
+//    chunks grid-stride, find the chunk's particle by a 33-way search in the
+//    scanned offsets, and run its units one after the other.  The 3-D path trims
+//    the lattice to the reference's cull disc first (see "Lattice form" below).
 //  - The region structure of the closed forms (q <= 1, <= 2, > 2) is evaluated
 //    without data-dependent branches: all three forms share their integrals and
 //    the result is selected (see line_crossings / half_segment).
@@ -367,50 +369,131 @@ __device__ __forceinline__ bool exact_box(const ExactView &v, const T *x, const 
 }
 
 // ---------------------------------------------------------------------------
-// Exact 2-D render, lattice form.
+// Lattice form of both exact paths.
 //
-// The pixel edges of a particle's box lie on the lines of a lattice: bw + 1 vertical lines with bh + 1 end
-// points each, bh + 1 horizontal lines with bw + 1 end points each.  Everything an edge integral needs
-// factors over that lattice:
+// The pixel edges (2-D) / column faces (3-D) of a particle's box lie on the lines of a lattice: bw + 1
+// vertical lines with bh + 1 vertices each, bh + 1 horizontal lines with bw + 1 vertices each.  Everything
+// the closed forms need factors over that lattice.
+//
+// 2-D render (cpu_backend.py:317-447):
 //   * the crossing terms (c1, c2) -- two inverse cosines, two logarithms, two sets of closed forms --
 //     depend on the LINE only (its distance from the particle): `exact2_lines_kernel` works them out once
 //     per line, one warp per particle with the lanes over its lines;
-//   * the half-segment value G -- one arctangent, one logarithm, one set of closed forms -- belongs to an
-//     END POINT and serves the two edges that meet there: `exact2_edges_kernel` lays its lanes over
-//     consecutive end points of a line and forms the edge between a lane and its neighbour from the two
-//     values (one shuffle).  Work units are 32 end points = 31 edges; consecutive units overlap by one
-//     end point.
-// Per edge that is one closed-form evaluation instead of four (round 1: two end points + two crossing
-// angles per edge, with the three regions as divergent branches).
-struct Exact2Box {
-    double sx, sy, sh;
+//   * the half-segment value G -- one arctangent, one logarithm, one set of closed forms -- belongs to a
+//     VERTEX and serves the two edges that meet there; an edge is formed from a lane and its neighbour
+//     (one shuffle).  One closed-form evaluation per edge instead of the reference's four.
+//
+// 3-D projection (cpu_backend.py:611-720): the column of a pixel has a top and a bottom face (equal
+// integrals) and four side faces, each shared with the neighbouring column.  Take a lattice line at signed
+// distance r0 from the particle and its slot between the vertices k and k + 1 (offsets d_k, d_{k+1} along
+// the line).  Two things live on that slot, and both feed the pixel after the line with + and the pixel
+// before it with -:
+//   the side face in the plane of the line (surface_int with the face centred on the particle along the
+//   line of sight):   S = Z(d_{k+1}) - Z(d_k) + 2 sign(r0) combine(E_k, E_{k+1})
+//       Z(d) = line_int3d(r0, r1 = d, 2h, 2h)   the edge along the line of sight through the vertex (los_edge)
+//       E_k  = clamped half-segment of the face's top edge: line (|r0|, r1 = 2h), end point d_k
+//   the edge of the top (= bottom) faces on the line:   2 sign(r0) combine(T_k, T_{k+1})
+//       T_k  = clamped half-segment of the line (2h, r1 = |r0|), end point d_k
+// Per pixel that is 2 full edge set-ups and 6 half-segments instead of the reference's 10 and 16.
+//
+// Which vertices.  2-D: all of them, line by line (vertical lines first, each orientation cut into its own
+// units).  3-D: the reference evaluates a pixel only if its centre passes q^2 < 4 + 3 pwx pwy / h^2
+// (cpu_backend.py:675), a disc inside the box, so ~ 1 - pi/4 of a large box is never needed.  The lines of
+// each orientation are cut into at most 32 GROUPS of G consecutive lines; a group keeps, of every line, only
+// the vertex range the widest chord of that disc beside its lines can reach (widened by one pixel, so
+// rounding cannot lose a pixel the cull accepts; the cull itself is still applied per pixel).  Inside a
+// group the (line, vertex) numbering is rectangular and the groups are laid end to end.  (The same trimming
+// of the 2-D lattice to the pixels that touch the support was measured and costs more than it saves there:
+// 4.0 against 3.8 ms, a vertex is four times cheaper.)
+// Either sequence is cut into UNITS of 32 vertices = 31 slots, consecutive units overlapping by one vertex.
+// A warp takes kExactChunk consecutive units of one particle, so the search for the particle, its box and
+// the group table are worked out once per chunk (they were two thirds of the 2-D kernel's instructions
+// when every unit did them).
+constexpr int kExactChunk = 16;
+constexpr int kExactGroups = 32;
+
+struct LatBox {
+    double sx, sy, sh, r2cull;
     int i0, j0, bw, bh;
 };
 
-__device__ __forceinline__ int units_of(int endpoints) { return endpoints > 1 ? (endpoints - 2) / 31 + 1 : 0; }
+template <typename T, bool PROJ3>
+__device__ __forceinline__ bool lat_box(const ExactView &v, const T *x, const T *y, const T *h, int64_t p, LatBox &b)
+{
+    int i1, j1;
+    if (!exact_box(v, x, y, h, p, b.sx, b.sy, b.sh, b.i0, i1, b.j0, j1)) return false;
+    b.bw = i1 - b.i0;
+    b.bh = j1 - b.j0;
+    b.r2cull = 4.0 * b.sh * b.sh + 3.0 * v.pwx * v.pwy; // (4 + 3 pwx pwy / h^2) h^2: the 3-D cull
+    return true;
+}
 
-// Units of one particle a warp takes in a row: the search for the particle, its box and its constants are
-// worked out once per chunk (they were two thirds of the instructions when every unit did them).
-constexpr int kExact2Chunk = 16;
+// Lines [g G, g G + nl) of one orientation: the vertex range [klo, klo + cnt) kept of each (cnt = 0: none).
+__device__ __forceinline__ void lat_group(const ExactView &v, const LatBox &b, bool vertical, int G, int g, int &nl,
+                                          int &klo, int &cnt)
+{
+    const int nlines = (vertical ? b.bw : b.bh) + 1, len = vertical ? b.bh : b.bw;
+    const int l0 = g * G;
+    nl = min(G, nlines - l0);
+    klo = cnt = 0;
+    if (nl <= 0) {
+        nl = 0;
+        return;
+    }
+    // across the lines: the pixel columns beside them, centres a0 .. a1; the one nearest to the particle
+    const double pa = vertical ? v.pwx : v.pwy, oa = vertical ? v.x_min + b.i0 * v.pwx : v.y_min + b.j0 * v.pwy;
+    const double sa = vertical ? b.sx : b.sy;
+    const int c0 = max(l0 - 1, 0), c1 = min(l0 + nl - 1, nlines - 2);
+    const double a0 = oa + (c0 + 0.5) * pa, a1 = oa + (c1 + 0.5) * pa;
+    const double dmin = sa < a0 ? a0 - sa : sa > a1 ? sa - a1 : 0.0;
+    const double c = b.r2cull - dmin * dmin;
+    if (!(c > 0.0)) return;
+    // along the lines: pixels whose centre lies within the chord, one more on either side
+    const double half = sqrt(c);
+    const double pl = vertical ? v.pwy : v.pwx, ol = vertical ? v.y_min + b.j0 * v.pwy : v.x_min + b.i0 * v.pwx;
+    const double sl = vertical ? b.sy : b.sx;
+    const double lo = floor((sl - half - ol) / pl - 0.5), hi = ceil((sl + half - ol) / pl - 0.5);
+    const int jlo = (int)fmax(lo, 0.0), jhi = (int)fmin(hi, (double)(len - 1));
+    if (jlo > jhi) return;
+    klo = jlo;
+    cnt = jhi - jlo + 2;
+}
 
-template <typename T>
-__global__ void exact2_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
-                                    unsigned long long *units, unsigned long long *lines)
+__device__ __forceinline__ int units_of(unsigned long long vertices)
+{
+    return vertices > 1 ? (int)((vertices - 2) / 31 + 1) : 0;
+}
+
+// Per particle: the number of chunks (entry n stays 0: the exclusive scan leaves the total there) and,
+// for the 2-D render, the number of lattice lines (slots of the crossing-term table).
+template <typename T, bool PROJ3>
+__global__ void exact_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
+                                   unsigned long long *chunks, unsigned long long *lines)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p > n) return;
-    unsigned long long u = 0, l = 0; // entry n stays 0: the exclusive scans leave the totals there
-    double xp, yp, hp;
-    int i0, i1, j0, j1;
-    if (p < n && exact_box(v, x, y, h, p, xp, yp, hp, i0, i1, j0, j1)) {
-        const int bw = i1 - i0, bh = j1 - j0;
-        // end points are enumerated line by line; a unit's 31 edges may straddle lines (such edges are skipped)
-        // (a warp takes kExact2Chunk consecutive units of a particle: the count is in chunks)
-        u = (unsigned long long)((2 * units_of((bw + 1) * (bh + 1)) + kExact2Chunk - 1) / kExact2Chunk);
-        l = (unsigned long long)(bw + bh + 2);
+    unsigned long long total = 0, l = 0;
+    LatBox b;
+    int units = 0;
+    if (p < n && lat_box<T, PROJ3>(v, x, y, h, p, b)) {
+        if (PROJ3) {
+            for (int o = 0; o < 2; o++) {
+                const int nlines = (o == 0 ? b.bw : b.bh) + 1, G = (nlines + kExactGroups - 1) / kExactGroups;
+                for (int g = 0; g * G < nlines; g++) {
+                    int nl, klo, cnt;
+                    lat_group(v, b, o == 0, G, g, nl, klo, cnt);
+                    total += (unsigned long long)nl * cnt;
+                }
+            }
+            units = units_of(total);
+        } else {
+            // whole lines, vertical then horizontal, each orientation cut into its own units
+            units = 2 * units_of((unsigned long long)(b.bw + 1) * (b.bh + 1));
+        }
+        l = (unsigned long long)(b.bw + b.bh + 2);
     }
-    units[p] = u;
-    lines[p] = l;
+    chunks[p] = (unsigned long long)((units + kExactChunk - 1) / kExactChunk);
+    if (!PROJ3) lines[p] = l;
 }
 
 template <typename T>
@@ -433,13 +516,13 @@ exact2_lines_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ 
     }
 }
 
-template <typename T, int NW>
+template <typename T, int NW, bool PROJ3>
 __global__ void __launch_bounds__(kExactWarps * 32, 8)
-exact2_edges_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
-                    const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
-                    const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets,
-                    const unsigned long long *__restrict__ line_off, const double2 *__restrict__ cross, double *o0,
-                    double *o1, double *o2, double *o3)
+exact_lattice_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
+                     const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
+                     const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets,
+                     const unsigned long long *__restrict__ line_off, const double2 *__restrict__ cross, double *o0,
+                     double *o1, double *o2, double *o3)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const T *wsrc[4] = {w0, w1, w2, w3};
@@ -458,45 +541,125 @@ exact2_edges_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ 
             lo = lo + (int64_t)k * step;
         }
         const int64_t p = lo;
-        double sx, sy, sh;
-        int i0, i1, j0, j1;
-        if (!exact_box(v, x, y, h, p, sx, sy, sh, i0, i1, j0, j1)) continue;
-        const int bw = i1 - i0, bh = j1 - j0;
-        const int half = units_of((bw + 1) * (bh + 1));
-        const unsigned long long lbase = line_off[p];
-        // term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (cpu_backend.py:333, :365)
+        LatBox b;
+        if (!lat_box<T, PROJ3>(v, x, y, h, p, b)) continue;
+        // 3-D: group table, lane g holds group g of either orientation; start = number of its first vertex
+        const int Gv = (b.bw + kExactGroups) / kExactGroups, Gh = (b.bh + kExactGroups) / kExactGroups;
+        int klo_v = 0, cnt_v = 0, klo_h = 0, cnt_h = 0, start_v = 0, start_h = 0, total_v = 0, total_all = 0;
+        int units;
+        if (PROJ3) {
+            int nl_v, nl_h;
+            lat_group(v, b, true, Gv, lane, nl_v, klo_v, cnt_v);
+            lat_group(v, b, false, Gh, lane, nl_h, klo_h, cnt_h);
+            start_v = nl_v * cnt_v;
+            start_h = nl_h * cnt_h;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tv = __shfl_up_sync(0xffffffffu, start_v, o), th = __shfl_up_sync(0xffffffffu, start_h, o);
+                if (lane >= o) {
+                    start_v += tv;
+                    start_h += th;
+                }
+            }
+            total_v = __shfl_sync(0xffffffffu, start_v, 31);
+            total_all = total_v + __shfl_sync(0xffffffffu, start_h, 31);
+            start_v -= nl_v * cnt_v; // exclusive
+            start_h += total_v - nl_h * cnt_h;
+            units = units_of((unsigned long long)total_all);
+        } else {
+            total_v = units_of((unsigned long long)(b.bw + 1) * (b.bh + 1)); // units per orientation
+            units = 2 * total_v;
+        }
+
+        // 2-D: term * denom = (w / h^2) * (h^2 / |pwx pwy|)  (cpu_backend.py:333, :365)
+        // 3-D: term * dfac  = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (cpu_backend.py:628-629)
         double wp[NW];
 #pragma unroll
         for (int q = 0; q < NW; q++) wp[q] = (double)__ldg(wsrc[q] + p) * v.inv_area;
-        const int c0 = (int)(u - offsets[p]) * kExact2Chunk, c1 = min(c0 + kExact2Chunk, 2 * half);
-        for (int uc = c0; uc < c1; uc++) {
-            const bool vertical = uc < half;     // first the vertical lines, then the horizontal ones
-            const int ul = vertical ? uc : uc - half;
-            // a line has `len` edges and len + 1 end points; lines are enumerated one after the other
-            const int len = vertical ? bh : bw, nlines = vertical ? bw + 1 : bh + 1;
-            const int e = ul * 31 + lane;
-            const int line = e / (len + 1), k = e - line * (len + 1);
-            const bool live = line < nlines;
-            double g = 0.0, d = 0.0, r0 = 0.0;
-            if (live) {
-                // r0: signed distance particle -> line; d: offset of the end point from the foot of the perpendicular
-                r0 = vertical ? sx - (v.x_min + (i0 + line) * v.pwx) : sy - (v.y_min + (j0 + line) * v.pwy);
-                d = vertical ? (v.y_min + (j0 + k) * v.pwy) - sy : (v.x_min + (i0 + k) * v.pwx) - sx;
-                if (r0 != 0.0) {
-                    const double2 c = __ldg(cross + lbase + (vertical ? line : bw + 1 + line));
-                    const double ar0 = fabs(r0);
-                    g = ex::half_segment(fabs(d) / ar0, ar0 / sh, c.x, c.y); // same q0 as the lines kernel
+        const unsigned long long lbase = PROJ3 ? 0ull : line_off[p];
+        const double two_h = 2.0 * b.sh;
+        const int ul0 = (int)(u - offsets[p]) * kExactChunk, ul1 = min(ul0 + kExactChunk, units);
+        for (int ul = ul0; ul < ul1; ul++) {
+            bool vertical, live, has_a, has_b, needed;
+            int line, k;
+            if (PROJ3) {
+                const int e = ul * 31 + lane;
+                vertical = e < total_v;
+                // the group holding vertex e: the last one whose start is <= e
+                int g = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) {
+                    const int cand = g + st;
+                    const int sv = __shfl_sync(0xffffffffu, start_v, cand), sh_ = __shfl_sync(0xffffffffu, start_h, cand);
+                    if ((vertical ? sv : sh_) <= e) g = cand;
+                }
+                const int gs_v = __shfl_sync(0xffffffffu, start_v, g), gs_h = __shfl_sync(0xffffffffu, start_h, g);
+                const int gk_v = __shfl_sync(0xffffffffu, klo_v, g), gk_h = __shfl_sync(0xffffffffu, klo_h, g);
+                const int gc_v = __shfl_sync(0xffffffffu, cnt_v, g), gc_h = __shfl_sync(0xffffffffu, cnt_h, g);
+                const int gstart = vertical ? gs_v : gs_h, klo = vertical ? gk_v : gk_h;
+                const int cnt = max(vertical ? gc_v : gc_h, 1);
+                const int f = e - gstart, fl = f / cnt;
+                line = g * (vertical ? Gv : Gh) + fl;
+                k = klo + (f - fl * cnt);
+                live = e < total_all;
+                const bool last = k == klo + cnt - 1; // the line's last kept vertex: no slot after it
+                const int len = vertical ? b.bh : b.bw, nlines = (vertical ? b.bw : b.bh) + 1;
+                // the four pixels around the vertex: a / b = after / before the line, rows k and k - 1 (centre
+                // offsets as functions of the pixel index alone: the two lanes that share a slot must agree)
+                const double pa = vertical ? v.pwx : v.pwy, pl = vertical ? v.pwy : v.pwx;
+                const double oa = vertical ? v.x_min - b.sx : v.y_min - b.sy, ol = vertical ? v.y_min - b.sy : v.x_min - b.sx;
+                const int ca = (vertical ? b.i0 : b.j0) + line, cl = (vertical ? b.j0 : b.i0) + k;
+                const double xa = fma(ca + 0.5, pa, oa), xb = fma(ca - 0.5, pa, oa);
+                const double y1 = fma(cl + 0.5, pl, ol), y0 = fma(cl - 0.5, pl, ol);
+                const double xa2 = xa * xa, xb2 = xb * xb, y12 = y1 * y1, y02 = y0 * y0;
+                const bool col_a = live && line < nlines - 1, col_b = live && line > 0;
+                has_a = col_a && k < len && !last && xa2 + y12 < b.r2cull;
+                has_b = col_b && k < len && !last && xb2 + y12 < b.r2cull;
+                // a vertex is evaluated only if one of the two slots that meet there feeds a pixel inside the disc
+                needed = has_a || has_b ||
+                         (k > klo && ((col_a && xa2 + y02 < b.r2cull) || (col_b && xb2 + y02 < b.r2cull)));
+            } else {
+                vertical = ul < total_v; // first the vertical lines, then the horizontal ones
+                const int len = vertical ? b.bh : b.bw, nlines = (vertical ? b.bw : b.bh) + 1;
+                const int e = (vertical ? ul : ul - total_v) * 31 + lane;
+                line = e / (len + 1);
+                k = e - line * (len + 1);
+                live = needed = line < nlines;
+                has_a = live && k < len && line < nlines - 1;
+                has_b = live && k < len && line > 0;
+            }
+            const bool mine = has_a || has_b;
+            // signed distance of the particle from the line, offset of the vertex along it
+            const double r0 = vertical ? b.sx - (v.x_min + (b.i0 + line) * v.pwx) : b.sy - (v.y_min + (b.j0 + line) * v.pwy);
+            const double d = vertical ? (v.y_min + (b.j0 + k) * v.pwy) - b.sy : (v.x_min + (b.i0 + k) * v.pwx) - b.sx;
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            if (needed && r0 != 0.0) {
+                const double ar0 = fabs(r0);
+                if (PROJ3) {
+                    t0 = ex::los_edge(r0, d, two_h, b.sh);       // side face: edge along the line of sight
+                    t1 = ex::half_outside(ar0, two_h, d, b.sh);  // side face: its top edge
+                    t2 = ex::half_outside(two_h, ar0, d, b.sh);  // top face: the edge on this line
+                } else {
+                    const double2 c = __ldg(cross + lbase + (vertical ? line : b.bw + 1 + line));
+                    t0 = ex::half_segment(fabs(d) / ar0, ar0 / b.sh, c.x, c.y); // same q0 as the lines kernel
                 }
             }
-            // the edge from this lane's end point to the next one of the same line
-            const double g_next = __shfl_down_sync(0xffffffffu, g, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
-            if (!live || lane == 31 || k >= len || r0 == 0.0) continue;
-            const double val = (r0 > 0.0 ? 1.0 : -1.0) * ex::combine_halves(g, g_next, d, d_next);
+            const double n0 = __shfl_down_sync(0xffffffffu, t0, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
+            double n1 = 0.0, n2 = 0.0;
+            if (PROJ3) {
+                n1 = __shfl_down_sync(0xffffffffu, t1, 1);
+                n2 = __shfl_down_sync(0xffffffffu, t2, 1);
+            }
+            if (!mine || lane == 31 || r0 == 0.0) continue;
+            const double sign = r0 > 0.0 ? 1.0 : -1.0;
+            // 3-D: side face + top and bottom face edges on this slot (same two pixels, same signs)
+            const double val = PROJ3 ? n0 - t0 + 2.0 * sign * (ex::combine_halves(t1, n1, d, d_next) +
+                                                               ex::combine_halves(t2, n2, d, d_next))
+                                     : sign * ex::combine_halves(t0, n0, d, d_next);
             if (val == 0.0) continue;
             // the pixel after the line gains the integral, the pixel before it loses it (cpu_backend.py:404-440)
-            const int ia = vertical ? i0 + line : i0 + k, ja = vertical ? j0 + k : j0 + line;
+            const int ia = vertical ? b.i0 + line : b.i0 + k, ja = vertical ? b.j0 + k : b.j0 + line;
             const int ib = vertical ? ia - 1 : ia, jb = vertical ? ja : ja - 1;
-            const bool has_a = line < nlines - 1, has_b = line > 0;
 #pragma unroll
             for (int q = 0; q < NW; q++) {
                 const double wv = wp[q] * val;
@@ -513,10 +676,10 @@ exact2_edges_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ 
     }
 }
 
-template <typename T, int NW>
-static int launch_exact2(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
-                         const unsigned long long *line_off, const double2 *cross, double *const *out,
-                         cudaStream_t stream)
+template <typename T, int NW, bool PROJ3>
+static int launch_lattice(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
+                          const unsigned long long *line_off, const double2 *cross, double *const *out,
+                          cudaStream_t stream)
 {
     int sms = 0;
     SPHB_CUDA(sm_count(&sms));
@@ -526,257 +689,24 @@ static int launch_exact2(const ExactView &v, const sphb_particles *p, const unsi
         w[i] = static_cast<const T *>(p->w[i]);
         o[i] = out[i];
     }
-    exact2_edges_kernel<T, NW><<<sms * 32, kExactWarps * 32, 0, stream>>>(
+    exact_lattice_kernel<T, NW, PROJ3><<<sms * 32, kExactWarps * 32, 0, stream>>>(
         v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), w[0], w[1], w[2],
         w[3], p->n, offsets, line_off, cross, o[0], o[1], o[2], o[3]);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }
 
-// ---------------------------------------------------------------------------
-// Exact 3-D projection, lattice form for the side faces.
-//
-// The column of a pixel has a top and a bottom face (equal integrals) and four side faces, each shared
-// with the neighbouring column.  Take a lattice line (x = const, say) at signed distance r0 from the
-// particle and its slot between the lattice vertices k and k + 1 (offsets d_k, d_{k+1} along the line).
-// Two things live on that slot, and both feed the pixel after the line with + and the pixel before it
-// with -:
-//   the side face in the plane of the line (surface_int with the face centred on the particle along the
-//   line of sight):   S = Z(d_{k+1}) - Z(d_k) + 2 sign(r0) combine(E_k, E_{k+1})
-//       Z(d) = line_int3d(r0, r1 = d, 2h, 2h)   the edge along the line of sight through the vertex (los_edge)
-//       E_k  = clamped half-segment of the face's top edge: line (|r0|, r1 = 2h), end point d_k
-//   the edge of the top (= bottom) faces on the line:   2 sign(r0) combine(T_k, T_{k+1})
-//       T_k  = clamped half-segment of the line (2h, r1 = |r0|), end point d_k
-// so, as in the 2-D render, everything belongs to lattice VERTICES and serves the two slots that meet
-// there: the lanes take consecutive vertices of a line, a slot is formed from a lane and its neighbour
-// (four shuffles).  Per pixel that is 2 full edge set-ups and 6 half-segments instead of 10 and 16 (and
-// round 1's 12 and 24).
-//
-// Which vertices: the reference evaluates a pixel only if its centre passes q^2 < 4 + 3 pwx pwy / h^2
-// (cpu_backend.py:675), a disc inside the box, so ~ 1 - pi/4 of the lattice is never needed.  The lines
-// of each orientation are cut into at most 32 GROUPS of G consecutive lines; a group keeps, of every line,
-// only the vertex range its widest chord of that disc can reach (widened by one pixel, so rounding cannot
-// lose a pixel the cull accepts; the cull itself is still applied per pixel).  Inside a group the
-// (line, vertex) numbering is rectangular, the groups are laid end to end, and that sequence is cut into
-// units of 32 vertices overlapping by one.  A warp takes kExact3Chunk consecutive units of one particle,
-// so the search for the particle, its box and the group table are worked out once per chunk.
-constexpr int kExact3Chunk = 16;
-constexpr int kExact3Groups = 32;
-
-struct Box3 {
-    double sx, sy, sh, r2cull;
-    int i0, j0, bw, bh;
-};
-
-// Lines [g G, g G + nl) of one orientation: the vertex range [klo, klo + cnt) kept of each (cnt = 0: none).
-__device__ __forceinline__ void exact3_group(const ExactView &v, const Box3 &b, bool vertical, int G, int g, int &nl,
-                                             int &klo, int &cnt)
+template <typename T, bool PROJ3>
+static int launch_lattice_nw(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
+                             const unsigned long long *line_off, const double2 *cross, double *const *out,
+                             cudaStream_t stream)
 {
-    const int nlines = (vertical ? b.bw : b.bh) + 1, len = vertical ? b.bh : b.bw;
-    const int l0 = g * G;
-    nl = min(G, nlines - l0);
-    klo = cnt = 0;
-    if (nl <= 0) {
-        nl = 0;
-        return;
+    switch (p->n_weights) {
+    case 1: return launch_lattice<T, 1, PROJ3>(v, p, offsets, line_off, cross, out, stream);
+    case 2: return launch_lattice<T, 2, PROJ3>(v, p, offsets, line_off, cross, out, stream);
+    case 3: return launch_lattice<T, 3, PROJ3>(v, p, offsets, line_off, cross, out, stream);
+    default: return launch_lattice<T, 4, PROJ3>(v, p, offsets, line_off, cross, out, stream);
     }
-    // across the lines: the pixel columns beside them, centres a0 .. a1; nearest one to the particle
-    const double pa = vertical ? v.pwx : v.pwy, oa = vertical ? v.x_min + b.i0 * v.pwx : v.y_min + b.j0 * v.pwy;
-    const double sa = vertical ? b.sx : b.sy;
-    const int c0 = max(l0 - 1, 0), c1 = min(l0 + nl - 1, nlines - 2);
-    const double a0 = oa + (c0 + 0.5) * pa, a1 = oa + (c1 + 0.5) * pa;
-    const double dmin = sa < a0 ? a0 - sa : sa > a1 ? sa - a1 : 0.0;
-    const double c = b.r2cull - dmin * dmin;
-    if (!(c > 0.0)) return;
-    // along the lines: pixels whose centre lies within the chord, one more on either side
-    const double half = sqrt(c);
-    const double pl = vertical ? v.pwy : v.pwx, ol = vertical ? v.y_min + b.j0 * v.pwy : v.x_min + b.i0 * v.pwx;
-    const double sl = vertical ? b.sy : b.sx;
-    const double lo = floor((sl - half - ol) / pl - 0.5), hi = ceil((sl + half - ol) / pl - 0.5);
-    const int jlo = (int)fmax(lo, 0.0), jhi = (int)fmin(hi, (double)(len - 1));
-    if (jlo > jhi) return;
-    klo = jlo;
-    cnt = jhi - jlo + 2;
-}
-
-template <typename T>
-__device__ __forceinline__ bool exact3_box(const ExactView &v, const T *x, const T *y, const T *h, int64_t p, Box3 &b)
-{
-    int i1, j1;
-    if (!exact_box(v, x, y, h, p, b.sx, b.sy, b.sh, b.i0, i1, b.j0, j1)) return false;
-    b.bw = i1 - b.i0;
-    b.bh = j1 - b.j0;
-    b.r2cull = 4.0 * b.sh * b.sh + 3.0 * v.pwx * v.pwy;   // (4 + 3 pwx pwy / h^2) h^2
-    return true;
-}
-
-__device__ __forceinline__ int chunks_of(unsigned long long vertices)
-{
-    return vertices > 1 ? (int)((((vertices - 2) / 31 + 1) + kExact3Chunk - 1) / kExact3Chunk) : 0;
-}
-
-template <typename T>
-__global__ void exact3_count_kernel(ExactView v, const T *x, const T *y, const T *h, int64_t n,
-                                    unsigned long long *chunks)
-{
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > n) return;
-    unsigned long long total = 0;
-    Box3 b;
-    if (p < n && exact3_box(v, x, y, h, p, b)) {
-        for (int o = 0; o < 2; o++) {
-            const int nlines = (o == 0 ? b.bw : b.bh) + 1, G = (nlines + kExact3Groups - 1) / kExact3Groups;
-            for (int g = 0; g * G < nlines; g++) {
-                int nl, klo, cnt;
-                exact3_group(v, b, o == 0, G, g, nl, klo, cnt);
-                total += (unsigned long long)nl * cnt;
-            }
-        }
-    }
-    chunks[p] = (unsigned long long)chunks_of(total);
-}
-
-#ifndef SPHB_EXACT3_MINB
-#define SPHB_EXACT3_MINB 8
-#endif
-
-template <typename T, int NW>
-__global__ void __launch_bounds__(kExactWarps * 32, SPHB_EXACT3_MINB)
-exact3_kernel(ExactView v, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ h,
-              const T *__restrict__ w0, const T *__restrict__ w1, const T *__restrict__ w2,
-              const T *__restrict__ w3, int64_t n, const unsigned long long *__restrict__ offsets, double *o0,
-              double *o1, double *o2, double *o3)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const T *wsrc[4] = {w0, w1, w2, w3};
-    double *outs[4] = {o0, o1, o2, o3};
-    const unsigned long long total = offsets[n];
-    const unsigned long long stride = (unsigned long long)gridDim.x * kExactWarps;
-    for (unsigned long long u = (unsigned long long)blockIdx.x * kExactWarps + warp; u < total; u += stride) {
-        int64_t lo = 0, hi = n; // largest p with offsets[p] <= u (33-way search)
-        while (hi - lo > 1) {
-            const int64_t step = (hi - lo + 32) / 33;
-            const int64_t probe = lo + (int64_t)(lane + 1) * step;
-            const bool le = probe < hi && __ldg(offsets + probe) <= u;
-            const int k = __popc(__ballot_sync(0xffffffffu, le));
-            hi = min(hi, lo + (int64_t)(k + 1) * step);
-            lo = lo + (int64_t)k * step;
-        }
-        const int64_t p = lo;
-        Box3 b;
-        if (!exact3_box(v, x, y, h, p, b)) continue;
-        // group table: lane g holds group g of either orientation, start = first vertex number of the group
-        const int Gv = (b.bw + kExact3Groups) / kExact3Groups, Gh = (b.bh + kExact3Groups) / kExact3Groups;
-        int nl_v, klo_v, cnt_v, nl_h, klo_h, cnt_h;
-        exact3_group(v, b, true, Gv, lane, nl_v, klo_v, cnt_v);
-        exact3_group(v, b, false, Gh, lane, nl_h, klo_h, cnt_h);
-        int start_v = nl_v * cnt_v, start_h = nl_h * cnt_h;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int tv = __shfl_up_sync(0xffffffffu, start_v, o), th = __shfl_up_sync(0xffffffffu, start_h, o);
-            if (lane >= o) {
-                start_v += tv;
-                start_h += th;
-            }
-        }
-        const int total_v = __shfl_sync(0xffffffffu, start_v, 31);
-        const int total_all = total_v + __shfl_sync(0xffffffffu, start_h, 31);
-        start_v -= nl_v * cnt_v;                       // exclusive
-        start_h += total_v - nl_h * cnt_h;
-
-        // term * dfac = (w / (pi h^3)) * (pi h^3 / (pwx pwy))  (cpu_backend.py:628-629)
-        double wp[NW];
-#pragma unroll
-        for (int q = 0; q < NW; q++) wp[q] = (double)__ldg(wsrc[q] + p) * v.inv_area;
-        const double two_h = 2.0 * b.sh;
-        const int units = (total_all - 2) / 31 + 1;
-        const int ul0 = (int)(u - offsets[p]) * kExact3Chunk, ul1 = min(ul0 + kExact3Chunk, units);
-        for (int ul = ul0; ul < ul1; ul++) {
-            const int e = ul * 31 + lane;
-            const bool vertical = e < total_v;
-            // the group holding vertex e: the last one whose start is <= e
-            int g = 0;
-#pragma unroll
-            for (int st = 16; st > 0; st >>= 1) {
-                const int cand = g + st;
-                const int sv = __shfl_sync(0xffffffffu, start_v, cand), sh_ = __shfl_sync(0xffffffffu, start_h, cand);
-                if ((vertical ? sv : sh_) <= e) g = cand;
-            }
-            const int gs_v = __shfl_sync(0xffffffffu, start_v, g), gs_h = __shfl_sync(0xffffffffu, start_h, g);
-            const int gk_v = __shfl_sync(0xffffffffu, klo_v, g), gk_h = __shfl_sync(0xffffffffu, klo_h, g);
-            const int gc_v = __shfl_sync(0xffffffffu, cnt_v, g), gc_h = __shfl_sync(0xffffffffu, cnt_h, g);
-            const int gstart = vertical ? gs_v : gs_h, klo = vertical ? gk_v : gk_h;
-            const int cnt = max(vertical ? gc_v : gc_h, 1);
-            const int f = e - gstart, fl = f / cnt;
-            const int line = g * (vertical ? Gv : Gh) + fl, k = klo + (f - fl * cnt);
-            const bool live = e < total_all;
-            const bool last = k == klo + cnt - 1;               // the line's last kept vertex: no slot after it
-            const int len = vertical ? b.bh : b.bw, nlines = (vertical ? b.bw : b.bh) + 1;
-            // signed distance of the particle from the line, offset of the vertex along it
-            const double r0 = vertical ? b.sx - (v.x_min + (b.i0 + line) * v.pwx) : b.sy - (v.y_min + (b.j0 + line) * v.pwy);
-            const double d = vertical ? (v.y_min + (b.j0 + k) * v.pwy) - b.sy : (v.x_min + (b.i0 + k) * v.pwx) - b.sx;
-            // the four pixels around the vertex: a / b = after / before the line, rows k and k - 1
-            // (centre offsets as functions of the pixel index alone: the two lanes that share a slot must agree)
-            const double pa = vertical ? v.pwx : v.pwy, pl = vertical ? v.pwy : v.pwx;
-            const double oa = vertical ? v.x_min - b.sx : v.y_min - b.sy, ol = vertical ? v.y_min - b.sy : v.x_min - b.sx;
-            const int ca = (vertical ? b.i0 : b.j0) + line, cl = (vertical ? b.j0 : b.i0) + k;
-            const double xa = fma(ca + 0.5, pa, oa), xb = fma(ca - 0.5, pa, oa);
-            const double y1 = fma(cl + 0.5, pl, ol), y0 = fma(cl - 0.5, pl, ol);
-            const double xa2 = xa * xa, xb2 = xb * xb, y12 = y1 * y1, y02 = y0 * y0;
-            const bool col_a = live && line < nlines - 1, col_b = live && line > 0;
-            const bool has_a = col_a && k < len && !last && xa2 + y12 < b.r2cull;
-            const bool has_b = col_b && k < len && !last && xb2 + y12 < b.r2cull;
-            const bool mine = has_a || has_b;
-            // a vertex is evaluated only if one of the two slots that meet there feeds a pixel inside the cull
-            const bool needed = mine || (k > klo && ((col_a && xa2 + y02 < b.r2cull) || (col_b && xb2 + y02 < b.r2cull)));
-            double zk = 0.0, ek = 0.0, tk = 0.0;
-            if (needed && r0 != 0.0) {
-                zk = ex::los_edge(r0, d, two_h, b.sh);                 // side face: edge along the line of sight
-                ek = ex::half_outside(fabs(r0), two_h, d, b.sh);       // side face: its top edge
-                tk = ex::half_outside(two_h, fabs(r0), d, b.sh);       // top face: the edge on this line
-            }
-            const double z_next = __shfl_down_sync(0xffffffffu, zk, 1), e_next = __shfl_down_sync(0xffffffffu, ek, 1);
-            const double t_next = __shfl_down_sync(0xffffffffu, tk, 1), d_next = __shfl_down_sync(0xffffffffu, d, 1);
-            if (!mine || lane == 31 || r0 == 0.0) continue;
-            // side face + top and bottom face edges on this slot (same two pixels, same signs)
-            const double s_val = z_next - zk + 2.0 * (r0 > 0.0 ? 1.0 : -1.0) * (ex::combine_halves(ek, e_next, d, d_next) +
-                                                                              ex::combine_halves(tk, t_next, d, d_next));
-            if (s_val == 0.0) continue;
-            const int ia = vertical ? b.i0 + line : b.i0 + k, ja = vertical ? b.j0 + k : b.j0 + line;
-            const int ib = vertical ? ia - 1 : ia, jb = vertical ? ja : ja - 1;
-#pragma unroll
-            for (int q = 0; q < NW; q++) {
-                const double wv = wp[q] * s_val;
-                if (has_a) {
-                    SPHB_ASSERT(ia >= 0 && ia < v.nx && ja >= 0 && ja < v.ny);
-                    red_add(outs[q] + (size_t)ja * v.nx + ia, wv);
-                }
-                if (has_b) {
-                    SPHB_ASSERT(ib >= 0 && ib < v.nx && jb >= 0 && jb < v.ny);
-                    red_add(outs[q] + (size_t)jb * v.nx + ib, -wv);
-                }
-            }
-        }
-    }
-}
-
-template <typename T, int NW>
-static int launch_exact3(const ExactView &v, const sphb_particles *p, const unsigned long long *offsets,
-                         double *const *out, cudaStream_t stream)
-{
-    int sms = 0;
-    SPHB_CUDA(sm_count(&sms));
-    const T *w[4] = {nullptr, nullptr, nullptr, nullptr};
-    double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < NW; i++) {
-        w[i] = static_cast<const T *>(p->w[i]);
-        o[i] = out[i];
-    }
-    exact3_kernel<T, NW><<<sms * 32, kExactWarps * 32, 0, stream>>>(
-        v, static_cast<const T *>(p->x), static_cast<const T *>(p->y), static_cast<const T *>(p->h), w[0], w[1], w[2],
-        w[3], p->n, offsets, o[0], o[1], o[2], o[3]);
-    SPHB_LAUNCH_CHECK();
-    return SPHB_OK;
 }
 
 // Page-locked landing zone of the 2-D line total, one per host thread and device.
@@ -816,19 +746,14 @@ static int exact_typed(const ExactView &v, const sphb_particles *p, bool proj3d,
     const T *x = static_cast<const T *>(p->x), *y = static_cast<const T *>(p->y), *h = static_cast<const T *>(p->h);
     if (proj3d) {
         void *scan_ws = static_cast<unsigned char *>(ws) + off_bytes;
-        exact3_count_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, offsets);
+        exact_count_kernel<T, true><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, offsets, nullptr);
         SPHB_LAUNCH_CHECK();
         SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
-        switch (p->n_weights) {
-        case 1: return launch_exact3<T, 1>(v, p, offsets, out, stream);
-        case 2: return launch_exact3<T, 2>(v, p, offsets, out, stream);
-        case 3: return launch_exact3<T, 3>(v, p, offsets, out, stream);
-        default: return launch_exact3<T, 4>(v, p, offsets, out, stream);
-        }
+        return launch_lattice_nw<T, true>(v, p, offsets, nullptr, nullptr, out, stream);
     }
     unsigned long long *line_off = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ws) + off_bytes);
     void *scan_ws = static_cast<unsigned char *>(ws) + 2 * off_bytes;
-    exact2_count_kernel<T><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, offsets, line_off);
+    exact_count_kernel<T, false><<<div_up(n + 1, 256), 256, 0, stream>>>(v, x, y, h, n, offsets, line_off);
     SPHB_LAUNCH_CHECK();
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, offsets, offsets, n + 1, stream));
     SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, line_off, line_off, n + 1, stream));
@@ -851,12 +776,7 @@ static int exact_typed(const ExactView &v, const sphb_particles *p, bool proj3d,
     exact2_lines_kernel<T><<<(int)std::min<int64_t>(div_up(n, 4), (int64_t)sms * 16), 128, 0, stream>>>(v, x, y, h, n,
                                                                                                      line_off, cross);
     SPHB_LAUNCH_CHECK();
-    switch (p->n_weights) {
-    case 1: return launch_exact2<T, 1>(v, p, offsets, line_off, cross, out, stream);
-    case 2: return launch_exact2<T, 2>(v, p, offsets, line_off, cross, out, stream);
-    case 3: return launch_exact2<T, 3>(v, p, offsets, line_off, cross, out, stream);
-    default: return launch_exact2<T, 4>(v, p, offsets, line_off, cross, out, stream);
-    }
+    return launch_lattice_nw<T, false>(v, p, offsets, line_off, cross, out, stream);
 }
 
 static int exact_impl(const sphb_particles *p, const sphb_raster *r, bool proj3d, int accumulate,
