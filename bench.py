@@ -649,10 +649,10 @@ def measure_exact(wl, cols, args, ctx, want_cpu):
                       "bbox_pixels_upper_bound": boxes * world if world > 1 else boxes},
            "roofline": {"bound": "hbm", "achieved": ab / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": ab / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "alg_bytes": ab,
-                        "kernel": "exact2_edges_kernel" if wl["key"] == "exact2d" else "exact3_kernel",
+                        "kernel": "exact_lattice_kernel<PROJ3=%s>" % ("false" if wl["key"] == "exact2d" else "true"),
                         "note": "compute-bound by construction: 10^3-10^4 double-precision operations (closed forms with "
                                 "log / atan / acos) per pixel integral; the HBM fraction is reported for uniformity"},
-           "e2e": e2e, "gpu_launches": steps * (5 if wl["key"] == "exact2d" else 2)}
+           "e2e": e2e, "gpu_launches": steps * (3 if wl["key"] == "exact2d" else 2)}  # count (+ lines) + lattice kernel
     if want_cpu:
         cpu = ctx["cpu"]
         ns = 1 << (14 if wl["key"] == "exact2d" else 12)

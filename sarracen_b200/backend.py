@@ -319,8 +319,8 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         (x, y, weight, h), mode = _shard([x, y, weight, h])
         if exact:
-            xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
-            return _images(ops.exact2d(xd, yd, hd, [wd], r), mode)[0]
+            return _images(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.exact2d(
+                c[0], c[1], c[3], [c[2]], r, out=out, accumulate=acc)), mode)[0]
         wf = resolve_weight_function(weight_function, kernel_radius)
         return _images(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
             c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc)), mode)[0]
@@ -333,8 +333,8 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         (x, y, weight_x, weight_y, h), mode = _shard([x, y, weight_x, weight_y, h])
         if exact:
-            xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
-            a, b = _images(ops.exact2d(xd, yd, hd, [wx, wy], r), mode)
+            a, b = _images(streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.exact2d(
+                c[0], c[1], c[4], [c[2], c[3]], r, out=out, accumulate=acc)), mode)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
             a, b = _images(streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(
@@ -366,8 +366,8 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         (x, y, weight, h), mode = _shard([x, y, weight, h])
         if exact:
-            xd, yd, wd, hd = _to_device([x, y, weight, h], dev)
-            return _images(ops.exact3d_proj(xd, yd, hd, [wd], r), mode)[0]
+            return _images(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.exact3d_proj(
+                c[0], c[1], c[3], [c[2]], r, out=out, accumulate=acc)), mode)[0]
         wf = resolve_weight_function(weight_function, kernel_radius)
         return _images(streamed_scatter([x, y, weight, h], dev, lambda c, out, acc: ops.scatter2d(
             c[0], c[1], c[3], [c[2]], wf, kernel_radius, 2, r, out=out, accumulate=acc)), mode)[0]
@@ -380,8 +380,8 @@ class B200Backend:
         r = ops.Raster(x_pixels, y_pixels, x_min, x_max, y_min, y_max)
         (x, y, weight_x, weight_y, h), mode = _shard([x, y, weight_x, weight_y, h])
         if exact:
-            xd, yd, wx, wy, hd = _to_device([x, y, weight_x, weight_y, h], dev)
-            a, b = _images(ops.exact3d_proj(xd, yd, hd, [wx, wy], r), mode)
+            a, b = _images(streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.exact3d_proj(
+                c[0], c[1], c[4], [c[2], c[3]], r, out=out, accumulate=acc)), mode)
         else:
             wf = resolve_weight_function(weight_function, kernel_radius)
             a, b = _images(streamed_scatter([x, y, weight_x, weight_y, h], dev, lambda c, out, acc: ops.scatter2d(

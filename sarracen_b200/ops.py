@@ -380,9 +380,20 @@ def line3d(x, y, z, h, weights, weight_function, radius, pixels, x1, x2, y1, y2,
     return out
 
 
-def _exact(fn_name, x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
+def _exact(fn_name, x, y, h, weights, raster: Raster, out=None, accumulate=False) -> List[torch.Tensor]:
     device = x.device
-    out = [torch.empty((raster.ny, raster.nx), dtype=torch.float64, device=device) for _ in weights]
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs the rasters to add to (out=)")
+        out = [torch.empty((raster.ny, raster.nx), dtype=torch.float64, device=device) for _ in weights]
+    else:
+        out = list(out)
+        for o in out:
+            _require_cuda(o, "out")
+            if o.dtype != torch.float64 or tuple(o.shape) != (raster.ny, raster.nx) or not o.is_contiguous():
+                raise ValueError("out rasters must be contiguous float64 of shape (ny, nx)")
+        if len(out) != len(weights):
+            raise ValueError("one output raster per weight column")
     part = _particles(x, y, None, h, weights)
     rast = raster.c()
     with torch.cuda.device(device):
@@ -390,7 +401,7 @@ def _exact(fn_name, x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
         need = ctypes.c_size_t(0)
         ws = _workspaces.get(str(device))
         for _attempt in range(3):   # exact2d sizes its table of line terms after a first count
-            rc = fn(ctypes.byref(part), ctypes.byref(rast), 0, _out_ptrs(out),
+            rc = fn(ctypes.byref(part), ctypes.byref(rast), 1 if accumulate else 0, _out_ptrs(out),
                     ctypes.c_void_p(ws.data_ptr()) if ws is not None else None,
                     ws.numel() if ws is not None else 0, ctypes.byref(need), _stream(device))
             if rc != _lib.SPHB_ERR_WORKSPACE:
@@ -401,14 +412,14 @@ def _exact(fn_name, x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
     return out
 
 
-def exact2d(x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
+def exact2d(x, y, h, weights, raster: Raster, out=None, accumulate=False) -> List[torch.Tensor]:
     """B4: exact pixel integrals of the 2-D cubic spline (cpu_backend.py:317-447)."""
-    return _exact("sphb_exact2d", x, y, h, weights, raster)
+    return _exact("sphb_exact2d", x, y, h, weights, raster, out, accumulate)
 
 
-def exact3d_proj(x, y, h, weights, raster: Raster) -> List[torch.Tensor]:
+def exact3d_proj(x, y, h, weights, raster: Raster, out=None, accumulate=False) -> List[torch.Tensor]:
     """B5: exact column integrals of the 3-D cubic spline (cpu_backend.py:611-720)."""
-    return _exact("sphb_exact3d_proj", x, y, h, weights, raster)
+    return _exact("sphb_exact3d_proj", x, y, h, weights, raster, out, accumulate)
 
 
 def count_contributions(x, y, h, radius, raster: Raster, z=None, z_slice=None) -> int:

@@ -157,6 +157,41 @@ def test_config5_exact_3d_projection(env):
     assert_parity(out, ref, 1e-10, "config 5 exact 3-D projection, 2^14 particles, 1024^2")
 
 
+@pytest.mark.parametrize("proj3d", [False, True])
+def test_exact_streamed_upload_matches_one_call(env, proj3d):
+    """>= 2^22 host particles reach the exact kernels in chunks that accumulate into one raster
+    (backend.streamed_scatter); same image as one device-resident call.  h ~ pixel / 3 keeps it cheap."""
+    import torch
+    from sarracen_b200 import ops
+    n = (1 << 22) + 12345
+    rng = np.random.default_rng(77)
+    pw = 1.0 / 1024
+    x, y = rng.uniform(0.0, 1.0, n), rng.uniform(0.0, 1.0, n)
+    w, h = rng.uniform(0.0, 1.0, n) / n, rng.uniform(0.2 * pw, 0.5 * pw, n)
+    k = env.s.CubicSplineKernel()
+    r = ops.Raster(1024, 1024, 0.0, 1.0, 0.0, 1.0)
+    dev = torch.device("cuda", 0)
+    xd, yd, wd, hd = (torch.from_numpy(a).to(dev) for a in (x, y, w, h))
+    if proj3d:
+        out = env.s.B200Backend.interpolate_3d_projection(x, y, w, h, k.get_column_kernel_func(1000), 2.0, 1024, 1024,
+                                                          0.0, 1.0, 0.0, 1.0, True)
+        one = ops.exact3d_proj(xd, yd, hd, [wd], r)[0].cpu().numpy()
+    else:
+        out = env.s.B200Backend.interpolate_2d_render(x, y, w, h, k.w, 2.0, 1024, 1024, 0.0, 1.0, 0.0, 1.0, True)
+        one = ops.exact2d(xd, yd, hd, [wd], r)[0].cpu().numpy()
+    assert_parity(out, one, 1e-12, "streamed exact upload vs one call")
+    # and the one call against the oracle on a sub-sample (linearity: the first 2^14 particles alone)
+    m = 1 << 14
+    sub = (ops.exact3d_proj if proj3d else ops.exact2d)(xd[:m], yd[:m], hd[:m], [wd[:m]], r)[0].cpu().numpy()
+    if proj3d:
+        ref = env.ob.interpolate_3d_projection(x[:m], y[:m], w[:m], h[:m], env.ok.column("cubic", 1000), 2.0, 1024, 1024,
+                                               0.0, 1.0, 0.0, 1.0, True)
+    else:
+        ref = env.ob.interpolate_2d_render(x[:m], y[:m], w[:m], h[:m], env.ok("cubic"), 2.0, 1024, 1024,
+                                           0.0, 1.0, 0.0, 1.0, True)
+    assert_parity(sub, ref, 1e-10, "exact, sub-pixel h, 2^14 particles vs oracle")
+
+
 # ---- size-independent properties at full size ---------------------------------------------------
 def test_config2_full_size_linearity_and_split(env):
     """2^24 particles: rendering the set in two halves and adding the images equals rendering it at once,
