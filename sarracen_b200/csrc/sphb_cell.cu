@@ -197,6 +197,55 @@ __device__ __forceinline__ void cell_column(R qxy, R dz0, R step, int zs, int sp
     }
 }
 
+// The particles `m` (lanes of the batch) of one cell and one class: voxel boxes whose x-y plane takes the
+// whole warp in one round (17 .. 32 pixels), U z-slices per lane.
+template <typename R, int NW> struct CellPrep {
+    using R2 = typename Real2<R>::type;
+    R qxy;      // in-plane q^2 of this lane's pixel (+ sqrt guard)
+    R2 zz;      // z scale and offset
+    R term[NW];
+    R *ap;      // this lane's accumulator column
+    bool on;    // lane inside the box plane
+};
+
+template <typename R, int NW>
+__device__ __forceinline__ CellPrep<R, NW> cell_prep(int s, const CellBatch<R, NW> &st, const CellAcc<R> &a, int lane)
+{
+    using R2 = typename Real2<R>::type;
+    CellPrep<R, NW> p;
+    const int4 geo = st.geo[s];
+    const int4 use = st.use[s];
+    const int wx = geo.y & 0xff, wxy = use.y & 0xff;
+    SPHB_ASSERT((geo.x & 0xff) + wx <= a.s1 && ((geo.x >> 16) + (geo.y >> 16)) * a.s2 <= a.plane && wxy <= 32);
+    const unsigned inv_wx = (unsigned)geo.w >> 8;
+    const R2 xs = st.xs[s], ys = st.ys[s], ct = st.ct[s];
+    p.zz = st.zs[s];
+    p.term[0] = ct.y;
+#pragma unroll
+    for (int k = 1; k < NW; k++) p.term[k] = st.term[k][s];
+    const int iy = (int)(((unsigned)lane * inv_wx) >> 16), ix = lane - iy * wx;
+    const R dxs = fma((R)ix, xs.x, xs.y), dys = fma((R)iy, ys.x, ys.y);
+    p.qxy = fma(dys, dys, fma(dxs, dxs, ct.x)); // ct.x carries sqrt_guard()
+    p.ap = a.acc + (use.x + iy * a.s1 + ix);
+    p.on = lane < wxy;
+    return p;
+}
+
+template <typename R, int KIND, int NW, int U>
+__device__ __forceinline__ void cell_class(unsigned m, const CellBatch<R, NW> &st, const CellAcc<R> &a, int lane,
+                                           R rad2, int plane, const LutView<R> &lv)
+{
+    // (fetching the next particle's staged values ahead of this particle's column -- a software pipeline
+    // across the __syncwarp -- was measured: 118 registers and 33.6 instead of 32.3 ms, not kept)
+    while (m) {
+        const CellPrep<R, NW> cur = cell_prep<R, NW>(__ffs(m) - 1, st, a, lane);
+        m &= m - 1;
+        if (cur.on)
+            cell_column<R, KIND, NW, U, false>(cur.qxy, cur.zz.y, cur.zz.x, 0, 1, U, rad2, cur.term, cur.ap, a.s2, plane, lv);
+        __syncwarp();
+    }
+}
+
 // ACC = false: every box of the call holds at most kTinyVolume pixels, so the accumulator is never
 // used; that variant is built without it (fewer registers, 8-warp CTAs, several CTAs per SM: the
 // direct reductions need many warps in flight, not shared memory).
@@ -276,7 +325,7 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
         const int buf = batch & 1;
         if (lane == 0 && base + 32 < end) fetch(base + 32, buf ^ 1);
         mbar_wait(bar + buf, (unsigned)(batch >> 1) & 1u);
-        int vol = 0;
+        int vol = 0, my_cell = -1, my_class = 0;
         {
             int4 geo = make_int4(0, 0, -1, 0);
             if (base + lane < end) {
@@ -330,6 +379,10 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
                     const int nit = (wz + (32 >> lpl_log) - 1) >> (5 - lpl_log); // z-passes of a lane
                     st.use[lane] = make_int4((z0 & cmz) * s2 + (y0 & cmy) * s1 + (x0 & cmx), (wx * wy) | (nit << 8),
                                              (int)(65536u / (unsigned)(wx * wy) + 1u), 0);
+                    my_cell = geo.z;
+                    // class U = 1..8: a voxel box whose plane takes the whole warp in one round (one z-slice per
+                    // pass, U = wz slices per lane); 0: everything else (images, planes of <= 16 or > 32 pixels)
+                    my_class = DIM3 && lpl_log == 5 && wx * wy <= 32 ? nit : 0;
                 }
             }
             st.geo[lane] = geo;
@@ -378,79 +431,96 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
         }
 
         // ---- one particle per pass, lanes over its box, local accumulator --------------
-        const int nb = ACC ? (int)min((int64_t)32, end - base) : 0;
-        for (int s = 0; s < nb; s++) {
-            const int4 geo = st.geo[s];
-            if (!geo.y) continue;
-            if (geo.z != a.cell) {
+        // The batch is taken apart into runs of one cell (the stream is cell-ordered: usually one or two per
+        // batch) and, inside a run, into classes of equal z-extent: each class is a tight loop over its
+        // particles with the z-column unrolled at compile time -- no per-particle dispatch (the indirect
+        // branch, the cell test and the loop control of the particle-by-particle version took a fifth of the
+        // kernel's stall samples at 4 warps per scheduler).
+        unsigned todo = ACC ? __ballot_sync(0xffffffffu, vol > 0) : 0u;
+        while (todo) {
+            const int first = __ffs(todo) - 1;
+            const int c = __shfl_sync(0xffffffffu, my_cell, first);
+            const unsigned run = todo & __ballot_sync(0xffffffffu, my_cell == c);
+            todo &= ~run;
+            if (c != a.cell) {
                 cell_flush<R, NW>(a, v, lane, outs);
-                a.cell = geo.z;
-                a.cx0 = st.bx[s] - (geo.x & 0xff);
-                a.cy0 = st.by[s] - ((geo.x >> 8) & 0xff);
-                a.cz0 = st.bz[s] - (geo.x >> 16);
+                const int gx = st.geo[first].x;
+                a.cell = c;
+                a.cx0 = st.bx[first] - (gx & 0xff);
+                a.cy0 = st.by[first] - ((gx >> 8) & 0xff);
+                a.cz0 = st.bz[first] - (gx >> 16);
             }
             a.dirty = true;
-            const int4 use = st.use[s];
-            const int wx = geo.y & 0xff, wz = geo.y >> 16;
-            const int wxy = use.y & 0xff, nit = use.y >> 8;
-            SPHB_ASSERT((geo.x & 0xff) + wx <= a.s1 && ((geo.x >> 16) + wz) * a.s2 <= a.plane);
-            const R2 xs = st.xs[s], ys = st.ys[s], ct = st.ct[s];
-            const R sx = xs.x, ox = xs.y, sy = ys.x, oy = ys.y, cq = ct.x;
-            R term[NW];
-            term[0] = ct.y;
-#pragma unroll
-            for (int k = 1; k < NW; k++) term[k] = st.term[k][s];
-            const unsigned inv_wx = (unsigned)geo.w >> 8;
             if (DIM3) {
-                // lanes: in-plane pixel lane % lpl, z-slice lane / lpl (lpl = power of two >= wx wy, at
-                // most 32; a wider plane is covered in several rounds)
-                const R2 zz = st.zs[s];
-                const R sz = zz.x, oz = zz.y;
-                const int lpl_log = geo.w & 0xff, lpl = 1 << lpl_log, sp = 32 >> lpl_log, zs = lane >> lpl_log;
-                const R dz0 = fma((R)zs, sz, oz), step = (R)sp * sz;
-                const int zstride = sp * a.s2;
-                for (int a0 = lane & (lpl - 1); a0 < wxy; a0 += lpl) {
-                    const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
-                    const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
-                    const R qxy = fma(dys, dys, fma(dxs, dxs, cq)); // cq carries sqrt_guard()
-                    R *ap = a.acc + (use.x + zs * a.s2 + iy * a.s1 + ix);
-#define SPHB_COLUMN(U, CZ) \
-    cell_column<R, KIND, NW, U, CZ>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv)
-                    if (sp == 1) {
-                        switch (nit) {
-                        case 1: SPHB_COLUMN(1, false); break;
-                        case 2: SPHB_COLUMN(2, false); break;
-                        case 3: SPHB_COLUMN(3, false); break;
-                        case 4: SPHB_COLUMN(4, false); break;
-                        case 5: SPHB_COLUMN(5, false); break;
-                        case 6: SPHB_COLUMN(6, false); break;
-                        case 7: SPHB_COLUMN(7, false); break;
-                        default: SPHB_COLUMN(8, false); break;
-                        }
-                    } else {
-                        switch (nit) {   // at least two slices per pass: at most four passes
-                        case 1: SPHB_COLUMN(1, true); break;
-                        case 2: SPHB_COLUMN(2, true); break;
-                        case 3: SPHB_COLUMN(3, true); break;
-                        default: SPHB_COLUMN(4, true); break;
-                        }
-                    }
-#undef SPHB_COLUMN
-                }
-            } else {
-                for (int a0 = lane; a0 < wxy; a0 += 32) {
-                    const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
-                    const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
-                    const R qxy = fma(dys, dys, fma(dxs, dxs, cq));
-                    if (qxy < rad2) {
-                        const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
-                        R *ap = a.acc + (use.x + iy * a.s1 + ix);
-#pragma unroll
-                        for (int k = 0; k < NW; k++) ap[k * plane] = fma(term[k], wv, ap[k * plane]);
-                    }
-                }
+#define SPHB_CLASS(U) \
+    cell_class<R, KIND, NW, U>(run & __ballot_sync(0xffffffffu, my_class == U), st, a, lane, rad2, plane, lv)
+                SPHB_CLASS(5);
+                SPHB_CLASS(4);
+                SPHB_CLASS(6);
+                SPHB_CLASS(3);
+                SPHB_CLASS(7);
+                SPHB_CLASS(2);
+                SPHB_CLASS(8);
+                SPHB_CLASS(1);
+#undef SPHB_CLASS
             }
-            __syncwarp();
+            unsigned rest = run & __ballot_sync(0xffffffffu, my_class == 0);
+            while (rest) {
+                const int s = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const int4 geo = st.geo[s];
+                const int4 use = st.use[s];
+                const int wx = geo.y & 0xff, wz = geo.y >> 16;
+                const int wxy = use.y & 0xff, nit = use.y >> 8;
+                SPHB_ASSERT((geo.x & 0xff) + wx <= a.s1 && ((geo.x >> 16) + wz) * a.s2 <= a.plane);
+                const R2 xs = st.xs[s], ys = st.ys[s], ct = st.ct[s];
+                const R sx = xs.x, ox = xs.y, sy = ys.x, oy = ys.y, cq = ct.x;
+                R term[NW];
+                term[0] = ct.y;
+#pragma unroll
+                for (int k = 1; k < NW; k++) term[k] = st.term[k][s];
+                const unsigned inv_wx = (unsigned)geo.w >> 8;
+                if (DIM3) {
+                    // lanes: in-plane pixel lane % lpl, z-slice lane / lpl (lpl = power of two >= wx wy, at
+                    // most 32; a wider plane is covered in several rounds)
+                    const R2 zz = st.zs[s];
+                    const R sz = zz.x, oz = zz.y;
+                    const int lpl_log = geo.w & 0xff, lpl = 1 << lpl_log, sp = 32 >> lpl_log, zs = lane >> lpl_log;
+                    const R dz0 = fma((R)zs, sz, oz), step = (R)sp * sz;
+                    const int zstride = sp * a.s2;
+                    for (int a0 = lane & (lpl - 1); a0 < wxy; a0 += lpl) {
+                        const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
+                        const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
+                        const R qxy = fma(dys, dys, fma(dxs, dxs, cq)); // cq carries sqrt_guard()
+                        R *ap = a.acc + (use.x + zs * a.s2 + iy * a.s1 + ix);
+#define SPHB_COLUMN(U) cell_column<R, KIND, NW, U, true>(qxy, dz0, step, zs, sp, wz, rad2, term, ap, zstride, plane, lv)
+                        switch (nit) {
+                        case 1: SPHB_COLUMN(1); break;
+                        case 2: SPHB_COLUMN(2); break;
+                        case 3: SPHB_COLUMN(3); break;
+                        case 4: SPHB_COLUMN(4); break;
+                        case 5: SPHB_COLUMN(5); break;
+                        case 6: SPHB_COLUMN(6); break;
+                        case 7: SPHB_COLUMN(7); break;
+                        default: SPHB_COLUMN(8); break;
+                        }
+#undef SPHB_COLUMN
+                    }
+                } else {
+                    for (int a0 = lane; a0 < wxy; a0 += 32) {
+                        const int iy = (int)(((unsigned)a0 * inv_wx) >> 16), ix = a0 - iy * wx;
+                        const R dxs = fma((R)ix, sx, ox), dys = fma((R)iy, sy, oy);
+                        const R qxy = fma(dys, dys, fma(dxs, dxs, cq));
+                        if (qxy < rad2) {
+                            const R wv = kernel_eval_pos<KIND, R>(qxy, lv);
+                            R *ap = a.acc + (use.x + iy * a.s1 + ix);
+#pragma unroll
+                            for (int k = 0; k < NW; k++) ap[k * plane] = fma(term[k], wv, ap[k * plane]);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
     if (ACC) cell_flush<R, NW>(a, v, lane, outs);
