@@ -693,7 +693,11 @@ def run_gpu(args):
     records, shared = {}, None
     for i, name in enumerate(names):
         wl = describe(name, args.particles or default_particles(name), args.dtype)
-        cols = generate(wl, rank, world, args.dtype, share=shared if name in ("grid", "grid_hmin") else None)
+        if args.emulate_shard > 1 and world == 1:
+            # experiments: one GPU renders the shard rank 0 of an N-rank run would get (value / N is meaningless)
+            cols = generate(wl, 0, args.emulate_shard, args.dtype)
+        else:
+            cols = generate(wl, rank, world, args.dtype, share=shared if name in ("grid", "grid_hmin") else None)
         if name in ("grid", "grid_hmin"):
             shared = cols
         sampler = ClockSampler(local) if (i == 0 and rank == 0 and not os.environ.get("BENCH_NO_CLOCKS")) else None
@@ -724,6 +728,8 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="override the TOTAL particle count of every workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiling runs)")
+    ap.add_argument("--emulate-shard", type=int, default=1,
+                    help="experiments only: render rank 0's shard of an N-rank run on one GPU")
     ap.add_argument("--cpu-port", action="store_true", help="CPU legs: use the C port even if Sarracen imports")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per cpu_baseline sample")
     args = ap.parse_args()

@@ -34,7 +34,7 @@
 namespace sphb {
 
 #ifndef SPHB_CELL_MAXW
-#define SPHB_CELL_MAXW 16
+#define SPHB_CELL_MAXW 20
 #endif
 constexpr int kCellMaxWarps = SPHB_CELL_MAXW;
 constexpr int kTinyVolume = 16; // a batch whose largest box holds <= this many pixels reduces directly
@@ -284,26 +284,27 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
     if (start >= p_hi) return;
     const int64_t end = min(start + (int64_t)kCellChunk, p_hi);
 
-    // double-buffered raw records + their mbarriers, behind the staging slots
+    // one raw record batch + its mbarrier, behind the staging slots.  The staging step empties the buffer
+    // (every lane turns its record into staging slots), so the bulk copy of the next batch is issued right
+    // after it and lands while this batch's particles are evaluated: one buffer is enough, and 2 KB less per
+    // warp is what lets 20 warps share an SM's shared memory.
     const int raw_bytes = 32 * v.rec_stride * (int)sizeof(T);
     T *const raw0 = reinterpret_cast<T *>(mine + sizeof(CellBatch<R, NW>));
-    const int raw_elems = 32 * v.rec_stride;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(mine + sizeof(CellBatch<R, NW>) + 2 * raw_bytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(mine + sizeof(CellBatch<R, NW>) + raw_bytes);
     if (lane == 0) {
         mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    auto fetch = [&](int64_t first, int buf) {   // lane 0: records [first, first + 32) of the stream
+    auto fetch = [&](int64_t first) {   // lane 0: records [first, first + 32) of the stream
         const unsigned bytes = (unsigned)(min((int64_t)32, end - first) * v.rec_stride * (int)sizeof(T));
-        mbar_expect_tx(bar + buf, bytes);
-        bulk_g2s(raw0 + buf * raw_elems, recs + (size_t)first * v.rec_stride, bytes, bar + buf);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(raw0, recs + (size_t)first * v.rec_stride, bytes, bar);
     };
-    if (lane == 0) fetch(start, 0);
+    if (lane == 0) fetch(start);
 
     CellAcc<R> a;
-    a.acc = reinterpret_cast<R *>(mine + sizeof(CellBatch<R, NW>) + 2 * raw_bytes + 16);
+    a.acc = reinterpret_cast<R *>(mine + sizeof(CellBatch<R, NW>) + raw_bytes + 16);
     a.s1 = (1 << v.cx_log) + v.halo;
     a.s2 = a.s1 * ((1 << v.cy_log) + v.halo);
     a.plane = plane;
@@ -321,15 +322,13 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
 
     int batch = 0;
     for (int64_t base = start; base < end; base += 32, batch++) {
-        // ---- next batch on its way, this one landed; every lane derives one particle ----------
-        const int buf = batch & 1;
-        if (lane == 0 && base + 32 < end) fetch(base + 32, buf ^ 1);
-        mbar_wait(bar + buf, (unsigned)(batch >> 1) & 1u);
+        // ---- this batch has landed; every lane derives one particle ----------------------------
+        mbar_wait(bar, (unsigned)batch & 1u);
         int vol = 0, my_cell = -1, my_class = 0;
         {
             int4 geo = make_int4(0, 0, -1, 0);
             if (base + lane < end) {
-                const Rec<T> pr = smem_rec(raw0 + buf * raw_elems, v.rec_stride, lane);
+                const Rec<T> pr = smem_rec(raw0, v.rec_stride, lane);
                 const double hp = (double)pr.h;
                 const double xp = (double)pr.x, yp = (double)pr.y;
                 const double rad = v.radius * hp;
@@ -391,6 +390,7 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         __syncwarp();
+        if (lane == 0 && base + 32 < end) fetch(base + 32); // the raw buffer is free again: next batch on its way
         if (vmax == 0) continue;
 
         if (!ACC || vmax <= kTinyVolume) {
@@ -539,8 +539,8 @@ static int launch_one(const View &v, const T *recs, const sphb_kernel *k, const 
     const int plane = !acc ? 0 : DIM3 ? s2 * ((1 << v.cz_log) + v.halo) : s2;
     size_t lut_bytes = 0;
     if (KIND == SPHB_COLUMN_LUT) lut_bytes = align_up(sizeof(R2) * (size_t)k->lut_samples, 16);
-    // staging slots, two raw record batches, two mbarriers, accumulator
-    const size_t warp_bytes = align_up(sizeof(CellBatch<R, NW>) + 2 * 32 * (size_t)v.rec_stride * sizeof(T) + 16 +
+    // staging slots, one raw record batch, its mbarrier, accumulator
+    const size_t warp_bytes = align_up(sizeof(CellBatch<R, NW>) + 32 * (size_t)v.rec_stride * sizeof(T) + 16 +
                                            sizeof(R) * (size_t)plane * NW, 16);
     const size_t limit = 227 * 1024;
     if (lut_bytes + warp_bytes > limit) {

@@ -432,17 +432,17 @@ static int small_edge_setting(bool dim3, bool f32)
 }
 
 // Cell size (log2) of the small-footprint path.  Images: 32 x 32 pixels (16 x 16 with three or four
-// weights in double).  Grids: 4 x 4 x 4 voxels when the particles are dense (>= 32 per such cell on
-// average) -- with 8 x 8 x 8 a warp's accumulator is 14-27 KB and only 8-13 warps fit on an SM;
-// 4 x 4 x 4 (4 KB at the 5-voxel boxes of BASELINE config 4) runs 16 register-rich warps: 53 -> 42 ms
-// there, although it flushes 8 instead of 3.4 reductions per voxel.  Sparser sets (a 1/8 shard of
-// config 4 holds 8 particles per 4^3 cell: one 512-entry flush per 8 particles would undo the
-// accumulator) use 8 x 8 x 8.
-static int cell_log(bool dim3, bool f32, int nw, int small_edge, int64_t n, size_t n_out)
+// weights in double).  Grids: 4 x 4 x 4 voxels -- a warp's accumulator is 4 KB at the 5-voxel boxes of
+// BASELINE config 4 and 20 warps share an SM (with 8 x 8 x 8 it is 14-27 KB and 8-11 warps fit: 53 against
+// 42 ms when that was measured), although it flushes 8 instead of 3.4 reductions per voxel.  Sparse sets
+// (fewer than 32 particles per 4^3 cell: a 1/8 shard of config 4 holds 8) flush too often with that;
+// their cells are twice as deep, 4 x 4 x 8 (profiles/exp_r2_cellshape.sh, 1/8 shard: 4^3 5.61, 4x4x8 5.12,
+// 4x8x8 5.13, 8x8x4 5.45, 4x4x16 5.63, 8^3 6.21 ms; full set: 4^3 30.0, 4x4x8 31.3, 8x8x4 33.8 ms).
+static int cell_log(bool dim3, bool f32, int nw, int small_edge)
 {
     const char *e = getenv("SPHB_CELL_LOG");
     if (e && *e) return std::min(std::max(atoi(e), 1), 5);
-    if (dim3) return (double)n * 64.0 >= 32.0 * (double)n_out ? 2 : 3;
+    if (dim3) return 2;
     const size_t elem = f32 ? 4 : 8;
     const size_t s = 32 + (small_edge > 0 ? small_edge - 1 : 0);
     return s * s * elem * nw <= 28 * 1024 ? 5 : 4;
@@ -543,9 +543,14 @@ static int build_view(const sphb_particles *p, const sphb_kernel *k, const sphb_
     v.norm = kernel_norm(k->kind, k->ndim);
     v.small_edge = small_edge_setting(dim3, f32);
     v.rec_stride = rec_stride_for(f32, dim3 || use_z, p->n_weights);
-    const int clog = cell_log(dim3, f32, p->n_weights, v.small_edge, p->n, (size_t)v.nx * v.ny * v.nz);
+    const int clog = cell_log(dim3, f32, p->n_weights, v.small_edge);
     v.cx_log = v.cy_log = clog;
     v.cz_log = dim3 ? clog : 0;
+    if (dim3 && (double)p->n * 64.0 < 32.0 * ((double)v.nx * v.ny * v.nz)) v.cz_log = clog + 1; // sparse set
+    if (const char *e = getenv("SPHB_CELL_ZLOG"))
+        if (*e && dim3) v.cz_log = std::min(std::max(atoi(e), 1), 5);
+    if (const char *e = getenv("SPHB_CELL_YLOG"))
+        if (*e && dim3) v.cy_log = std::min(std::max(atoi(e), 1), 5);
     v.ncx = div_up(v.nx, 1 << v.cx_log);
     v.ncy = div_up(v.ny, 1 << v.cy_log);
     v.ncz = dim3 ? div_up(v.nz, 1 << v.cz_log) : 1;
