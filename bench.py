@@ -388,7 +388,7 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
 
     def collective_only():
         if dim3:
-            parallel.combine_grid_along_z(out[0], slab)
+            parallel.reduce_along_z(out[0])      # the exchange alone, same transport, nothing to hide behind
         else:
             parallel.combine_image(out[0], dst=0)
 
@@ -462,8 +462,7 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
                     part = s.backend.streamed_scatter(
                         [cols[k] for k in order], dev, lambda c, o, acc: ops.scatter3d(
                             c[0], c[1], c[2], c[4], [c[3]], wf, wl["radius"], raster, out=o, accumulate=acc))[0]
-                    parallel.combine_grid_along_z(part, slab)
-                    host_out.copy_(slab)
+                    host_out.copy_(parallel.reduce_along_z(part))
                 else:
                     part = s.backend.streamed_scatter(
                         [cols[k] for k in order], dev, lambda c, o, acc: ops.scatter2d(
@@ -570,8 +569,13 @@ def measure(wl, cols, args, ctx, want_cpu, clock_sampler=None):
     }
     if world > 1:
         rec.update({"ms_compute": ms_compute, "ms_collective": ms_collective, "collective_hidden": hidden,
-                    "collective": "ncclReduceScatter along z per z-chunk (2 chunks) on NCCL's high-priority stream; "
-                                  "ms_collective times the monolithic reduce-scatter on its own" if dim3
+                    "collective": ("reduce-scatter along z in %d z-chunks overlapped with the staged render; transport %s; "
+                                   "ms_collective times the same exchange on its own after a finished render"
+                                   % (parallel.z_chunks(wl["nz"], world), {
+                                       "peer": "peer memory (copy-engine pushes into the owners' symmetric-memory "
+                                               "slots + sphb_sum_slots)",
+                                       "nccl": "ncclReduceScatter on NCCL's high-priority stream"}.get(
+                                       parallel.last_transport, str(parallel.last_transport)))) if dim3
                                   else "ncclReduce to rank 0"})
     if want_cpu:
         rec["cpu_baseline"] = cpu_sample(ctx["cpu"], wl, cols, budget_s=args.cpu_budget,

@@ -16,7 +16,7 @@ SPHB_OK, SPHB_ERR_ARGUMENT, SPHB_ERR_WORKSPACE, SPHB_ERR_CUDA, SPHB_ERR_TOO_MANY
 
 EXPORTS = ["sphb_version", "sphb_last_error", "sphb_column_kernel", "sphb_scatter2d", "sphb_scatter3d",
            "sphb_scatter3d_staged", "sphb_scatter_plan", "sphb_scatter_planned", "sphb_scatter_overflowed",
-           "sphb_line2d", "sphb_line3d", "sphb_exact2d", "sphb_exact3d_proj", "sphb_normalize",
+           "sphb_line2d", "sphb_line3d", "sphb_exact2d", "sphb_exact3d_proj", "sphb_normalize", "sphb_sum_slots",
            "sphb_count_contributions", "sphb_radial_index", "sphb_bin_sums"]
 
 
@@ -102,6 +102,7 @@ def load():
                                       c_vp, c_vp, c_vp]
     lib.sphb_bin_sums.argtypes = [c_int, c_vp, c_int, outs, ctypes.c_int64, c_int, outs, c_vp]
     lib.sphb_normalize.argtypes = [c_vp, c_vp, ctypes.c_int64, c_vp]
+    lib.sphb_sum_slots.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_vp]
     lib.sphb_count_contributions.argtypes = [P, c_dbl, R, c_int, c_dbl, c_vp, c_vp]
     for name in EXPORTS:
         if name != "sphb_last_error":

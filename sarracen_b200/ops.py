@@ -447,3 +447,20 @@ def normalize_(num: torch.Tensor, den: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.load().sphb_normalize(ctypes.c_void_p(num.data_ptr()), ctypes.c_void_p(den.data_ptr()),
                                               num.numel(), _stream(num.device)))
     return num
+
+
+def sum_slots_(dst: torch.Tensor, own: torch.Tensor, slots: torch.Tensor, skip: int) -> torch.Tensor:
+    """dst = own + sum over the rows s != skip of `slots` (n_slots, n): the receive side of the peer-memory
+    exchange along z (sarracen_b200.parallel).  `slots` may be a view into peer-mapped (symmetric) memory."""
+    for t, name in ((dst, "dst"), (own, "own"), (slots, "slots")):
+        _require_cuda(t, name)
+        if t.dtype != torch.float64 or not t.is_contiguous():
+            raise ValueError("sum_slots_ needs contiguous float64 tensors")
+    n = dst.numel()
+    if own.numel() != n or slots.dim() != 2 or slots.shape[1] != n:
+        raise ValueError("sum_slots_: dst and own of n elements, slots of shape (n_slots, n)")
+    with torch.cuda.device(dst.device):
+        _lib.check(_lib.load().sphb_sum_slots(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(own.data_ptr()),
+                                              ctypes.c_void_p(slots.data_ptr()), int(slots.shape[0]), n, int(skip), n,
+                                              _stream(dst.device)))
+    return dst

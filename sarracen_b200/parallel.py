@@ -106,7 +106,10 @@ def combine_grid_along_z(grid: torch.Tensor, slab: torch.Tensor, group=None) -> 
     return slab
 
 
-DEFAULT_CHUNKS = 2
+# z-chunks of the overlapped exchange.  The copy-engine transport does not compete with the render for SMs, so
+# finer chunks only shorten the exposed tail (2 chunks were the optimum of the NCCL transport: 27.1 against
+# 28.2 ms with 4 at 2 GPUs, its kernel displaces render CTAs each time).
+DEFAULT_CHUNKS = 4
 
 
 def z_chunks(nz: int, world: int, chunks: Optional[int] = None) -> int:
@@ -135,19 +138,103 @@ def owned_planes(nz: int, rank: int, world: int, chunks: Optional[int] = None) -
     return [k * (nz // c) + rank * b + i for k in range(c) for i in range(b)]
 
 
+# ---- exchange over peer memory -------------------------------------------------------------------
+# NCCL's reduce-scatter is a kernel: next to a render that fills every SM it waits for SM slots and then
+# holds them, so little of it hides behind the render (measured: 17-37 % at 2 and 8 GPUs).  The transport
+# below moves the partial planes with the COPY ENGINES instead: every rank owns receive slots in symmetric
+# (peer-mapped) memory (`torch.distributed._symmetric_memory`), the owner of a finished z-chunk's planes is
+# sent each rank's partial planes by plain device-to-device copies over NVLink -- no SM involved -- and one
+# small kernel of this library (`sphb_sum_slots`) adds the G - 1 received partials to the rank's own.  Two
+# device-side barriers per exchange (slots free / copies landed) come from the symmetric-memory handle.
+_peer_cache = {}
+_peer_failed = False
+last_transport = None   # 'peer' or 'nccl': what the most recent exchange along z used (reported by bench.py)
+
+
+class _PeerSlots:
+    def __init__(self, group, dev, numel):
+        import torch.distributed._symmetric_memory as symm
+        self.numel = numel
+        self.buf = symm.empty(numel, dtype=torch.float64, device=dev)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+
+
+def _peer_slots(group, dev, numel) -> Optional[_PeerSlots]:
+    """Symmetric receive slots of at least `numel` doubles on every rank (collective: all ranks of the
+    group call it with the same size), or None where symmetric memory is not available."""
+    global _peer_failed
+    if _peer_failed:
+        return None
+    key = (id(group) if group is not None else 0, dev.index)
+    slots = _peer_cache.get(key)
+    if slots is None or slots.numel < numel:
+        try:
+            slots = _peer_cache[key] = _PeerSlots(group, dev, numel)
+        except Exception as e:   # no P2P mapping on this machine / build: NCCL carries the exchange
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({e!r}); the z-exchange uses NCCL reduce_scatter")
+            _peer_failed = True
+            return None
+    return slots
+
+
+TRANSPORTS = ("peer", "nccl")
+
+
+def _exchange_peer(peer, out, mine, rank, world, c, per, b, slot, events=None):
+    """Peer-memory exchange of the partial grids `out` (one per weight) into `mine`; `events[k]` (if
+    given) marks chunk k of `out` final on the current stream, otherwise the whole of `out` is final."""
+    global last_transport
+    last_transport = "peer"
+    dev = out[0].device
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    hdl = peer.hdl
+    if events is None:
+        side.wait_stream(main)
+    with torch.cuda.stream(side):
+        # every rank is past the sums of the previous exchange: the slots may be overwritten
+        hdl.barrier(channel=0)
+        for k in range(c):
+            if events is not None:
+                side.wait_event(events[k])
+            for step in range(1, world):
+                q = (rank + step) % world
+                for w, o in enumerate(out):
+                    dst = hdl.get_buffer(q, (slot,), torch.float64, ((w * c + k) * world + rank) * slot)
+                    dst.copy_(o[k * per + q * b:k * per + (q + 1) * b].reshape(-1), non_blocking=True)
+            hdl.barrier(channel=1)   # the copies of chunk k have landed on every rank
+            for w, (o, m) in enumerate(zip(out, mine)):
+                recv = peer.buf[(w * c + k) * world * slot:(w * c + k + 1) * world * slot].view(world, slot)
+                _ops().sum_slots_(m[k * b:(k + 1) * b], o[k * per + rank * b:k * per + (rank + 1) * b], recv, rank)
+    main.wait_stream(side)
+    return mine
+
+
+def _ops():
+    from . import ops
+    return ops
+
+
 def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=None, group=None,
-                      chunks: Optional[int] = None, overlap: bool = True) -> List[torch.Tensor]:
+                      chunks: Optional[int] = None, overlap: bool = True,
+                      transport: Optional[str] = None) -> List[torch.Tensor]:
     """Voxel grid of THIS rank's particle shard, summed over the ranks along z: returns, per weight,
     a (len(owned_planes), ny, nx) tensor holding the planes owned_planes(nz, rank, G, chunks).
 
     The render is issued in C z-chunk stages (`ops.scatter3d(stage_planes=...)`); as soon as chunk c
-    is final its `reduce_scatter` starts on NCCL's stream and overlaps the render of chunks c+1..;
-    only the last chunk's exchange (1 / C of the volume) is exposed.  Every reduce-scatter uses all
-    links at once, so the total exchange time is that of the monolithic collective.  `out` are
-    full-size float64 work grids (allocated if omitted)."""
+    is final its exchange starts on a side stream and overlaps the render of chunks c+1..; only the last
+    chunk's exchange (1 / C of the volume) is exposed.  transport='peer' (default where symmetric memory
+    works): copy-engine pushes into the owners' receive slots + `sphb_sum_slots`; 'nccl': one
+    `reduce_scatter` per chunk on NCCL's stream.  `out` are full-size float64 work grids (allocated if
+    omitted)."""
     from . import ops
     world, rank = _world(group), _rank(group)
     nz = raster.nz
+    if transport is None:
+        transport = "peer" if (overlap and world > 1 and x.is_cuda) else "nccl"
+    if transport not in TRANSPORTS:
+        raise ValueError(f"transport must be one of {TRANSPORTS}")
     c = z_chunks(nz, world, chunks)
     if world == 1:
         return ops.scatter3d(x, y, z, h, weights, weight_function, radius, raster, out=out)
@@ -159,6 +246,26 @@ def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=
     nw = len(weights)
     mine = [torch.empty((c * b,) + (raster.ny, raster.nx), dtype=torch.float64, device=dev) for _ in range(nw)]
     works = []
+    slot = b * raster.ny * raster.nx                       # doubles one rank sends one owner per chunk and weight
+    peer = _peer_slots(group, dev, nw * c * world * slot) if (transport == "peer" and overlap) else None
+    if peer is not None:
+        main = torch.cuda.current_stream(dev)
+        events = [torch.cuda.Event() for _ in range(c)]
+        done = set()
+
+        def on_stage(k):
+            # called by ops.scatter3d right after the kernels of stage k have been enqueued
+            events[k].record(main)
+            done.add(k)
+
+        out = ops.scatter3d(x, y, z, h, weights, weight_function, radius, raster, out=out,
+                            stage_planes=[(k + 1) * per for k in range(c)], on_stage=on_stage)
+        for k in range(c):
+            if k not in done:   # a render that could not be staged (split particle batches): final only now
+                events[k].record(main)
+        return _exchange_peer(peer, out, mine, rank, world, c, per, b, slot, events)
+    global last_transport
+    last_transport = "nccl"
     if not overlap or c == 1:
         out = ops.scatter3d(x, y, z, h, weights, weight_function, radius, raster, out=out)
         for k in range(c):
@@ -192,7 +299,8 @@ def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=
     return mine
 
 
-def reduce_along_z(grid: torch.Tensor, group=None, chunks: Optional[int] = None) -> torch.Tensor:
+def reduce_along_z(grid: torch.Tensor, group=None, chunks: Optional[int] = None,
+                   transport: Optional[str] = None) -> torch.Tensor:
     """Sum a FINISHED (nz, ny, nx) partial grid along z; returns the planes
     owned_planes(nz, rank, G, chunks) of the sum (same layout as scatter3d_sharded, no overlap)."""
     world, rank = _world(group), _rank(group)
@@ -200,6 +308,13 @@ def reduce_along_z(grid: torch.Tensor, group=None, chunks: Optional[int] = None)
     if world == 1:
         return grid
     c = z_chunks(nz, world, chunks)
+    if c > 0 and grid.is_cuda and transport in (None, "peer") and grid.dtype == torch.float64 and grid.is_contiguous():
+        per, b = nz // c, nz // (c * world)
+        slot = b * grid.shape[1] * grid.shape[2]
+        peer = _peer_slots(group, grid.device, c * world * slot)
+        if peer is not None:
+            mine = torch.empty((c * b,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
+            return _exchange_peer(peer, [grid], [mine], rank, world, c, per, b, slot)[0]
     if c == 0 or not grid.is_cuda:
         # unequal slabs (or gloo, which has no reduce_scatter): one in-place reduce per owner
         if c == 0:

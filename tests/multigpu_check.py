@@ -67,9 +67,21 @@ errs.append(relmax(slab2, full3[zl:zh]))
 # a grid whose small particles take the cell path and whose large ones the tile path, 64 planes per rank
 r3b = ops.Raster(64, 64, 0, 1, 0, 1, 64 * world, 0, 1)
 full3b = ops.scatter3d(xd, yd, zd, hd, [wd], c.w, 2.0, r3b)[0]
-for ch in (4, 1):      # block-cyclic planes (4 z-chunks, overlapped) and contiguous slabs
-    slab3 = scatter3d_sharded(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3b, chunks=ch)[0]
-    errs.append(relmax(slab3, full3b[owned_planes(64 * world, rank, world, ch)]))
+used = []
+for tr in ("peer", "nccl"):       # copy-engine pushes through symmetric memory / NCCL reduce-scatter
+    for ch in (4, 1):             # block-cyclic planes (4 z-chunks, overlapped) and contiguous slabs
+        slab3 = scatter3d_sharded(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3b, chunks=ch,
+                                  transport=tr)[0]
+        used.append(parallel.last_transport)
+        errs.append(relmax(slab3, full3b[owned_planes(64 * world, rank, world, ch)]))
+    # two weights in one exchange, and the exchange of a finished grid
+    a3, b3 = scatter3d_sharded(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi], hd[lo:hi]], c.w, 2.0, r3b,
+                               transport=tr)
+    fa, fb = ops.scatter3d(xd, yd, zd, hd, [wd, hd], c.w, 2.0, r3b)
+    own = owned_planes(64 * world, rank, world)
+    errs += [relmax(a3, fa[own]), relmax(b3, fb[own])]
+    gp = ops.scatter3d(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3b)[0]
+    errs.append(relmax(parallel.reduce_along_z(gp, transport=tr), full3b[own]))
 assert owned_planes(64 * world, rank, world, 1) == list(range(*slab_range(64 * world, rank, world)))
 e = torch.tensor(errs, device=dev, dtype=torch.float64)
 dist.all_reduce(e, op=dist.ReduceOp.MAX)
@@ -118,7 +130,7 @@ if rank == 0:
     eo = float(np.abs(part.cpu().numpy() - ref).max() / np.abs(ref).max())
     print(f"world={world} image: sharded vs single {e2:.2e}, vs oracle {eo:.2e}; grid slabs vs single "
           f"(unequal slabs overlapped / sequential, reduce-scatter, 4 z-chunks, contiguous) {[f'{v:.1e}' for v in e.tolist()]}; "
-          f"backend API in multi-GPU mode vs single {ea.max().item():.2e}")
+          f"backend API in multi-GPU mode vs single {ea.max().item():.2e}; transports used {sorted(set(used))}")
     assert e2 < 1e-12 and eo < 1e-10 and e.max().item() < 1e-12 and ea.max().item() < 1e-12
     print("multi-GPU check ok")
 dist.destroy_process_group()
