@@ -106,10 +106,11 @@ def combine_grid_along_z(grid: torch.Tensor, slab: torch.Tensor, group=None) -> 
     return slab
 
 
-# z-chunks of the overlapped exchange.  The copy-engine transport does not compete with the render for SMs, so
-# finer chunks only shorten the exposed tail (2 chunks were the optimum of the NCCL transport: 27.1 against
-# 28.2 ms with 4 at 2 GPUs, its kernel displaces render CTAs each time).
-DEFAULT_CHUNKS = 4
+# z-chunks of the overlapped exchange.  The stages of a staged render overlap each other's tails (two internal
+# streams, sphb_scatter3d_staged) and the copy-engine transport does not compete with the render for SMs, so
+# finer chunks only shorten the exposed tail: config 4 on 2 GPUs, render alone 20.14 ms, with the exchange
+# 20.82 (4 chunks) / 20.65 ms (8 chunks); the exchange on its own takes 1.1 ms (profiles/diag_peer_overlap.py).
+DEFAULT_CHUNKS = 8
 
 
 def z_chunks(nz: int, world: int, chunks: Optional[int] = None) -> int:
@@ -368,7 +369,7 @@ def enable(group=None, images: str = "all", grids: str = "all", chunks: Optional
                       z, then all_gather), or
             'slab' -- every rank receives only the planes owned_planes(nz, rank, G, chunks) (no
                       gather: the form `north_star` names; the return shape is (nz / G, ny, nx)).
-    chunks: z-chunks of the overlapped reduce-scatter (default 4; 1 = contiguous slabs)."""
+    chunks: z-chunks of the overlapped exchange (default 8; 1 = contiguous slabs)."""
     global _mode
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("torch.distributed is not initialised")
