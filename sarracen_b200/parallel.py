@@ -24,6 +24,7 @@ render if its few CTAs get onto the SMs ahead of the queued render CTAs.  `enabl
 `B200Backend` methods (and with them `backend='gpu'` of Sarracen's own front-end) to this mode:
 every rank passes the SAME full columns, renders its shard and receives the combined result.
 """
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -117,7 +118,7 @@ def z_chunks(nz: int, world: int, chunks: Optional[int] = None) -> int:
     """Number of z-chunks the reduction along z is cut into: `chunks` (default DEFAULT_CHUNKS)
     reduced until every chunk splits evenly over the ranks; 0 if not even one chunk does (then
     the ranks own unequal contiguous slabs, see owned_planes)."""
-    c = DEFAULT_CHUNKS if chunks is None else int(chunks)
+    c = int(os.environ.get("SPHB_Z_CHUNKS") or DEFAULT_CHUNKS) if chunks is None else int(chunks)
     c = max(1, c)
     while c > 1 and nz % (c * world):
         c -= 1
@@ -193,17 +194,32 @@ def _exchange_peer(peer, out, mine, rank, world, c, per, b, slot, events=None):
     hdl = peer.hdl
     if events is None:
         side.wait_stream(main)
+    lanes = _copy_lanes(dev, min(PEER_COPY_LANES, world - 1))
     with torch.cuda.stream(side):
         # every rank is past the sums of the previous exchange: the slots may be overwritten
         hdl.barrier(channel=0)
+        free = torch.cuda.Event()
+        free.record(side)
         for k in range(c):
             if events is not None:
                 side.wait_event(events[k])
-            for step in range(1, world):
-                q = (rank + step) % world
-                for w, o in enumerate(out):
-                    dst = hdl.get_buffer(q, (slot,), torch.float64, ((w * c + k) * world + rank) * slot)
-                    dst.copy_(o[k * per + q * b:k * per + (q + 1) * b].reshape(-1), non_blocking=True)
+            # the pushes to the G - 1 owners go out on several streams: one copy engine each
+            for j, lane in enumerate(lanes):
+                if k == 0:
+                    lane.wait_event(free)
+                if events is not None:
+                    lane.wait_event(events[k])
+                elif k == 0:
+                    lane.wait_stream(main)
+                with torch.cuda.stream(lane):
+                    for step in range(1 + j, world, len(lanes)):
+                        q = (rank + step) % world
+                        for w, o in enumerate(out):
+                            dst = hdl.get_buffer(q, (slot,), torch.float64, ((w * c + k) * world + rank) * slot)
+                            dst.copy_(o[k * per + q * b:k * per + (q + 1) * b].reshape(-1), non_blocking=True)
+                    sent = torch.cuda.Event()
+                    sent.record(lane)
+                side.wait_event(sent)
             hdl.barrier(channel=1)   # the copies of chunk k have landed on every rank
             for w, (o, m) in enumerate(zip(out, mine)):
                 recv = peer.buf[(w * c + k) * world * slot:(w * c + k + 1) * world * slot].view(world, slot)
@@ -233,7 +249,7 @@ def scatter3d_sharded(x, y, z, h, weights, weight_function, radius, raster, out=
     world, rank = _world(group), _rank(group)
     nz = raster.nz
     if transport is None:
-        transport = "peer" if (overlap and world > 1 and x.is_cuda) else "nccl"
+        transport = os.environ.get("SPHB_Z_TRANSPORT") or ("peer" if (overlap and world > 1 and x.is_cuda) else "nccl")
     if transport not in TRANSPORTS:
         raise ValueError(f"transport must be one of {TRANSPORTS}")
     c = z_chunks(nz, world, chunks)
@@ -309,6 +325,7 @@ def reduce_along_z(grid: torch.Tensor, group=None, chunks: Optional[int] = None,
     if world == 1:
         return grid
     c = z_chunks(nz, world, chunks)
+    transport = transport or os.environ.get("SPHB_Z_TRANSPORT")
     if c > 0 and grid.is_cuda and transport in (None, "peer") and grid.dtype == torch.float64 and grid.is_contiguous():
         per, b = nz // c, nz // (c * world)
         slot = b * grid.shape[1] * grid.shape[2]
@@ -340,6 +357,17 @@ def reduce_along_z(grid: torch.Tensor, group=None, chunks: Optional[int] = None,
 
 
 _side_streams = {}
+_copy_lane_cache = {}
+# streams the pushes of one chunk are spread over.  One: at 8 GPUs four lanes made the exchange on its own
+# slower (2.07 -> 2.70 ms) and the overlapped step no faster (6.99 / 6.98 ms), profiles/exp_r2_transport8.sh
+PEER_COPY_LANES = 1
+
+
+def _copy_lanes(dev, n: int):
+    lanes = _copy_lane_cache.setdefault(dev.index, [])
+    while len(lanes) < n:
+        lanes.append(torch.cuda.Stream(dev, priority=-1))
+    return lanes[:n]
 
 
 def _side_stream(dev) -> torch.cuda.Stream:
