@@ -178,6 +178,19 @@ template <int KIND, typename R> __device__ __forceinline__ R kernel_shape(R q)
     }
 }
 
+// The same from q and q^2 when the caller has both (it formed q^2 first): the cubic's inner branch is
+// 1 + q^2 (0.75 q - 1.5) -- the exact q^2 instead of the rounded square of its root, one multiply less.
+template <int KIND, typename R> __device__ __forceinline__ R kernel_shape2(R q, R q2)
+{
+    if (KIND == SPHB_CUBIC) {
+        const R a = fma(q, R(-0.62996052494743658), R(1.25992104989487316));
+        const R w = a * a * a;
+        const R w1 = fma(q2, fma(R(0.75), q, R(-1.5)), R(1));
+        return q2 < R(1) ? w1 : w;
+    }
+    return kernel_shape<KIND>(q);
+}
+
 // Column-table lookup.  The reference evaluates T[i] + f (T[i+1] - T[i]) with i = floor(t),
 // f = t - i, t = q (S - 1) / R (sarracen/kernels/base_kernel.py:88-110 via np.interp).  On each
 // segment that is the straight line A_i + B_i q with B_i = (T[i+1] - T[i]) (S - 1) / R and
@@ -228,7 +241,7 @@ __device__ __forceinline__ R kernel_eval_pos(R q2, const LutView<R> &lut)
     if (is_lut<KIND>()) {
         return lut_eval<KIND, R>(q, lut);
     } else {
-        return kernel_shape<KIND>(q);
+        return kernel_shape2<KIND>(q, q2);
     }
 }
 
@@ -242,7 +255,7 @@ __device__ __forceinline__ R kernel_eval_unguarded(R q2, R rad2, const LutView<R
     if (is_lut<KIND>()) {
         return lut_eval<KIND, R>(q, lut);
     } else {
-        R w = kernel_shape<KIND>(q);
+        R w = kernel_shape2<KIND>(q, q2);
         return q2 < rad2 ? w : R(0);
     }
 }
