@@ -237,8 +237,8 @@ int sphb_normalize(double *num, const double *den, int64_t n, sphb_stream stream
 /* Receive side of the multi-GPU exchange along z (no reference counterpart: the reference is one process;
  * SURVEY 8(e)).  dst[i] = own[i] + sum over slots s != skip of slots[s * slot_stride + i], i < n.  `slots`
  * are this rank's receive buffers -- peer-mapped device memory the other ranks' copy engines have written
- * their partial z-planes into -- `own` this rank's partial planes.  Pointers 16-byte aligned, slot_stride
- * even.  Asynchronous. */
+ * their partial z-planes into -- `own` this rank's partial planes.  16-byte accesses when the pointers are 16-byte aligned
+ * and slot_stride is even, scalar otherwise.  Asynchronous. */
 int sphb_sum_slots(double *dst, const double *own, const double *slots, int n_slots, int64_t slot_stride,
                    int skip, int64_t n, sphb_stream stream);
 

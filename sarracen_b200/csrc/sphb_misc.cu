@@ -357,13 +357,14 @@ __global__ void normalize_kernel(double *num, const double *den, int64_t n)
 // The slots are this rank's receive buffers in peer-mapped memory: the other ranks' copy engines have
 // written their partial z-planes there (sarracen_b200/parallel.py), this kernel is the reduction of the
 // reduce-scatter.  Two doubles per thread (16-byte accesses), grid-stride.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 sum_slots_kernel(double *__restrict__ dst, const double *__restrict__ own, const double *__restrict__ slots,
                  int n_slots, int64_t stride, int skip, int64_t n)
 {
     const int64_t step = (int64_t)gridDim.x * blockDim.x * 2;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += step) {
-        if (i + 1 < n) {
+        if (VEC && i + 1 < n) {
             double2 a = *reinterpret_cast<const double2 *>(own + i);
             for (int s = 0; s < n_slots; s++) {
                 if (s == skip) continue;
@@ -373,10 +374,12 @@ sum_slots_kernel(double *__restrict__ dst, const double *__restrict__ own, const
             }
             *reinterpret_cast<double2 *>(dst + i) = a;
         } else {
-            double a = own[i];
-            for (int s = 0; s < n_slots; s++)
-                if (s != skip) a += slots[(size_t)s * stride + i];
-            dst[i] = a;
+            for (int64_t j = i; j < min(i + 2, n); j++) {
+                double a = own[j];
+                for (int s = 0; s < n_slots; s++)
+                    if (s != skip) a += slots[(size_t)s * stride + j];
+                dst[j] = a;
+            }
         }
     }
 }
@@ -475,16 +478,22 @@ extern "C" int sphb_normalize(double *num, const double *den, int64_t n, sphb_st
 extern "C" int sphb_sum_slots(double *dst, const double *own, const double *slots, int n_slots, int64_t slot_stride,
                               int skip, int64_t n, sphb_stream stream)
 {
-    if (!dst || !own || n < 0 || n_slots < 0 || (n_slots > 0 && !slots) || slot_stride < 0 || (slot_stride & 1) ||
-        ((uintptr_t)dst & 15) || ((uintptr_t)own & 15) || ((uintptr_t)slots & 15)) {
-        set_error("sum_slots: null, misaligned (16 bytes) or negative argument");
+    if (!dst || !own || n < 0 || n_slots < 0 || (n_slots > 0 && !slots) || slot_stride < 0) {
+        set_error("sum_slots: null or negative argument");
         return SPHB_ERR_ARGUMENT;
     }
+    // 16-byte accesses when everything is aligned for them (the usual case: whole z-planes), scalar otherwise
+    const bool vec = !(slot_stride & 1) && !((uintptr_t)dst & 15) && !((uintptr_t)own & 15) && !((uintptr_t)slots & 15);
     if (n == 0) return SPHB_OK;
     int sms = 0;
     SPHB_CUDA(sm_count(&sms));
     const int grid = (int)std::min<int64_t>(div_up(n, 512), (int64_t)sms * 8);
-    sum_slots_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, own, slots, n_slots, slot_stride, skip, n);
+    if (vec)
+        sum_slots_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, own, slots, n_slots,
+                                                                                  slot_stride, skip, n);
+    else
+        sum_slots_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, own, slots, n_slots,
+                                                                                   slot_stride, skip, n);
     SPHB_LAUNCH_CHECK();
     return SPHB_OK;
 }

@@ -82,6 +82,12 @@ for tr in ("peer", "nccl"):       # copy-engine pushes through symmetric memory 
     errs += [relmax(a3, fa[own]), relmax(b3, fb[own])]
     gp = ops.scatter3d(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3b)[0]
     errs.append(relmax(parallel.reduce_along_z(gp, transport=tr), full3b[own]))
+# one plane of an odd number of pixels per rank and chunk: the receive slots are not 16-byte multiples
+r3c = ops.Raster(33, 35, 0, 1, 0, 1, 8 * world, 0, 1)
+full3c = ops.scatter3d(xd, yd, zd, hd, [wd], c.w, 2.0, r3c)[0]
+slab3c = scatter3d_sharded(xd[lo:hi], yd[lo:hi], zd[lo:hi], hd[lo:hi], [wd[lo:hi]], c.w, 2.0, r3c, chunks=8,
+                           transport="peer")[0]
+errs.append(relmax(slab3c, full3c[owned_planes(8 * world, rank, world, 8)]))
 assert owned_planes(64 * world, rank, world, 1) == list(range(*slab_range(64 * world, rank, world)))
 e = torch.tensor(errs, device=dev, dtype=torch.float64)
 dist.all_reduce(e, op=dist.ReduceOp.MAX)

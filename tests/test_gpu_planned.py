@@ -97,3 +97,24 @@ def test_stale_plan_is_flagged_not_fatal(env):
     assert bool(torch.isfinite(out[0]).all())
     ref = ops.scatter2d(*full)[0]                      # the library still works afterwards
     assert float(ref.sum()) > 0
+
+
+def test_sum_slots_receive_side():
+    """sphb_sum_slots (receive side of the multi-GPU exchange): dst = own + sum of the slots except `skip`,
+    odd and even lengths, against torch."""
+    import torch
+    from sarracen_b200 import ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for n in (1, 2, 999, 4098, (1 << 20) + 1):
+        for n_slots, skip in ((1, 0), (2, 1), (8, 3)):
+            own = torch.rand(n, generator=g, dtype=torch.float64).to(dev)
+            slots = torch.rand(n_slots, n, generator=g, dtype=torch.float64).to(dev)
+            dst = torch.full((n,), -1.0, dtype=torch.float64, device=dev)
+            ops.sum_slots_(dst, own, slots, skip)
+            keep = [s for s in range(n_slots) if s != skip]
+            ref = own + (slots[keep].sum(dim=0) if keep else 0.0)
+            assert torch.allclose(dst, ref, rtol=1e-14, atol=0.0)
+    with pytest.raises(ValueError):
+        ops.sum_slots_(torch.zeros(4, dtype=torch.float64, device=dev), torch.zeros(4, dtype=torch.float64, device=dev),
+                       torch.zeros(2, 5, dtype=torch.float64, device=dev), 0)
