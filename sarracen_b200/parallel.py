@@ -3,26 +3,29 @@
 The scatter is a sum over particles, so it shards by particle with no data-path collective
 until the end: rank r renders the contiguous index range [r N / G, (r+1) N / G)
 -- the partition the reference's CPU backend gives its threads (cpu_backend.py:258-260) -- into
-a full-size partial raster, then the partial rasters are summed over NVLink / NVSwitch with NCCL:
+a full-size partial raster, then the partial rasters are summed over NVLink / NVSwitch:
 
-  images        one `reduce` to a root rank (or `all_reduce` when every rank wants the picture);
+  images        one NCCL `reduce` to a root rank (or `all_reduce` when every rank wants the picture);
                 the two components of a `_vec` call, or value + normalisation grid, travel packed
                 in ONE collective;
-  voxel grids   reduce-scatter along z, cut into C z-chunks.  The render of a voxel grid is issued
+  voxel grids   a reduce-scatter along z, cut into C z-chunks.  The render of a voxel grid is issued
                 chunk by chunk (`ops.scatter3d(..., stage_planes=...)`: the sorted work lists are
-                z-major, so chunk c is final as soon as stage c has run), and the reduce-scatter of
-                chunk c runs on NCCL's stream while chunks c+1.. are still being rendered
-                (`scatter3d_sharded`).  Rank r then owns planes [r b, (r+1) b) of every chunk
-                (`owned_planes`: block-cyclic along z; C = 1 gives contiguous slabs).  The
-                monolithic form, one `reduce_scatter_tensor` after the whole render, is
-                `combine_grid_along_z`.
+                z-major, so chunk c is final as soon as stage c has run), and the exchange of chunk c
+                runs while chunks c+1.. are still being rendered (`scatter3d_sharded`).  Rank r then
+                owns planes [r b, (r+1) b) of every chunk (`owned_planes`: block-cyclic along z;
+                C = 1 gives contiguous slabs).  Two transports: 'peer' (default) -- the copy engines
+                push the partial planes into the owners' symmetric-memory slots and `sphb_sum_slots`
+                adds them up, no SM taken from the render -- and 'nccl', one `reduce_scatter` per
+                chunk on NCCL's stream.  `reduce_along_z` is the same exchange for a finished grid,
+                `combine_grid_along_z` the monolithic NCCL form into contiguous slabs.
 
 One process per GPU, `torch.distributed` for the plumbing.  Initialise the NCCL group with a
 high-priority stream (`opts = dist.ProcessGroupNCCL.Options(); opts.is_high_priority_stream = True;
-dist.init_process_group("nccl", pg_options=opts)`): the reduction of a finished slab only overlaps the
-render if its few CTAs get onto the SMs ahead of the queued render CTAs.  `enable()` switches the nine
-`B200Backend` methods (and with them `backend='gpu'` of Sarracen's own front-end) to this mode:
-every rank passes the SAME full columns, renders its shard and receives the combined result.
+dist.init_process_group("nccl", pg_options=opts)`): with the 'nccl' transport the reduction of a
+finished chunk only overlaps the render if its few CTAs get onto the SMs ahead of the queued render
+CTAs.  `enable()` switches the nine `B200Backend` methods (and with them `backend='gpu'` of Sarracen's
+own front-end) to this mode: every rank passes the SAME full columns, renders its shard and receives
+the combined result.
 """
 import os
 from typing import List, Optional, Sequence, Tuple
