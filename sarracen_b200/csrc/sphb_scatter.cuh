@@ -160,7 +160,10 @@ inline int tile2y(bool f32, int n_weights) { return (!f32 && n_weights >= 3) ? k
 
 // Cells of the small-footprint path: 32 x 32 pixels (images), 8 x 8 x 8 voxels (grids).
 constexpr int kCell2 = 32, kCell3 = 8;
-constexpr int kCellChunk = 512; // cell-ordered particles per warp work unit
+#ifndef SPHB_CELL_CHUNK
+#define SPHB_CELL_CHUNK 512
+#endif
+constexpr int kCellChunk = SPHB_CELL_CHUNK; // cell-ordered particles per warp work unit
 
 // sphb_render.cu: tile kernel over sorted pairs [range[0], range[1]) (range == nullptr: all n_pairs).
 int launch_render(const View &v, bool f32, int kind, int nw, const void *recs, const sphb_kernel *k,
