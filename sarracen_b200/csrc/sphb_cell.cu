@@ -189,7 +189,7 @@ __device__ __forceinline__ void cell_column(R qxy, R dz0, R step, int zs, int sp
 #pragma unroll
     for (int u = 0; u < U; u++) {
         // CHECKZ = false: one z-slice per pass (sp = 1), the U passes are exactly the wz slices
-        if ((!CHECKZ || zs + u * sp < wz) && q2[u] < rad2) {
+        if ((!CHECKZ || zs + u * sp < wz) && lt_pos(q2[u], rad2)) {
             R *p = ap + u * zstride;
 #pragma unroll
             for (int k = 0; k < NW; k++) p[k * plane] = fma(term[k], wv[u], p[k * plane]);

@@ -178,6 +178,14 @@ template <int KIND, typename R> __device__ __forceinline__ R kernel_shape(R q)
     }
 }
 
+// a < b for POSITIVE finite numbers, off the FP64 pipe: positive doubles order like their bit patterns, so the
+// compare is two integer instructions on the ALU pipe instead of a DSETP on the (half-rate, contended) FP64 pipe.
+__device__ __forceinline__ bool lt_pos(double a, double b)
+{
+    return __double_as_longlong(a) < __double_as_longlong(b);
+}
+__device__ __forceinline__ bool lt_pos(float a, float b) { return a < b; }
+
 // The same from q and q^2 when the caller has both (it formed q^2 first): the cubic's inner branch is
 // 1 + q^2 (0.75 q - 1.5) -- the exact q^2 instead of the rounded square of its root, one multiply less.
 template <int KIND, typename R> __device__ __forceinline__ R kernel_shape2(R q, R q2)
@@ -186,7 +194,7 @@ template <int KIND, typename R> __device__ __forceinline__ R kernel_shape2(R q, 
         const R a = fma(q, R(-0.62996052494743658), R(1.25992104989487316));
         const R w = a * a * a;
         const R w1 = fma(q2, fma(R(0.75), q, R(-1.5)), R(1));
-        return q2 < R(1) ? w1 : w;
+        return lt_pos(q2, R(1)) ? w1 : w;
     }
     return kernel_shape<KIND>(q);
 }
@@ -256,7 +264,7 @@ __device__ __forceinline__ R kernel_eval_unguarded(R q2, R rad2, const LutView<R
         return lut_eval<KIND, R>(q, lut);
     } else {
         R w = kernel_shape2<KIND>(q, q2);
-        return q2 < rad2 ? w : R(0);
+        return lt_pos(q2, rad2) ? w : R(0);
     }
 }
 
