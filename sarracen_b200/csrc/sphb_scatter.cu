@@ -215,7 +215,7 @@ emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0,
     }
     Box b[kEmitPer];
     bool seen[kEmitPer], small[kEmitPer];
-    uint32_t key[kEmitPer], slot[kEmitPer], start[kEmitPer];
+    uint32_t key[kEmitPer], slot[kEmitPer];
     unsigned peers[kEmitPer];
 #pragma unroll
     for (int k = 0; k < kEmitPer; k++) {
@@ -228,18 +228,17 @@ emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0,
     for (int k = 0; k < kEmitPer; k++) {
         peers[k] = __match_any_sync(0xffffffffu, key[k]);
         slot[k] = 0;
-        start[k] = 0;
         if (small[k]) {
+            // (the cursors were initialised with the scanned cell starts: the atomic returns the position)
             if (lane == __ffs(peers[k]) - 1 && dbg_mode != 1)
                 slot[k] = atomicAdd(cell_cursor + key[k], (uint32_t)__popc(peers[k]));
-            start[k] = __ldg(cell_start + key[k]);
         }
     }
 #pragma unroll
     for (int k = 0; k < kEmitPer; k++) {
         slot[k] = __shfl_sync(0xffffffffu, slot[k], __ffs(peers[k]) - 1);
         if (small[k]) {
-            int64_t pos = (int64_t)start[k] + slot[k] + __popc(peers[k] & ((1u << lane) - 1u));
+            int64_t pos = (int64_t)slot[k] + __popc(peers[k] & ((1u << lane) - 1u));
             if (dbg_mode == 1) pos = (int64_t)(((uint64_t)(base + 256 * k) * 2654435761ull) % (uint64_t)n_small);
             if (dbg_mode == 3) pos = (base + 256 * k) % n_small;
             if (pos >= n_small) {   // only with a stale plan: drop and report
@@ -678,6 +677,10 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
                                                                                         cell_start, totals);
         SPHB_LAUNCH_CHECK();
         SPHB_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_tmp, cell_start, cell_start, n_cells + 1, stream));
+        // the cursors start at the cell starts: the emit kernel's one atomic per particle then returns the final
+        // position, with no second random read of cell_start
+        SPHB_CUDA(cudaMemcpyAsync(cell_cursor, cell_start, (size_t)n_cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                  stream));
         if (timed) SPHB_CUDA(cudaEventRecord(ev[5], stream));
         return SPHB_OK;
     };
