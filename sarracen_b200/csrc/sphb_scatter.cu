@@ -189,11 +189,19 @@ constexpr uint32_t kOwnPairs = 16;
 
 // Particles per thread of the emit kernel: their column loads, and then their cell-cursor atomics,
 // are issued back to back, so that several global round trips are in flight per thread (with
-// one particle per thread the kernel sat at 15 % issue utilisation waiting for them).
-constexpr int kEmitPer = 4;
+// one particle per thread the kernel sat at 15 % issue utilisation waiting for them).  Measured on the hmin
+// variant of config 4 (per thread x CTAs per SM): 4 x 3 (80 registers) 6.15 ms, 4 x 4 (64, spills) 6.69,
+// 2 x 4 (64, no spills) 5.96, 2 x 5 (48) 6.08, 8 x 2 (128) 7.12.
+#ifndef SPHB_EMIT_PER
+#define SPHB_EMIT_PER 2
+#endif
+#ifndef SPHB_EMIT_MINB
+#define SPHB_EMIT_MINB 4
+#endif
+constexpr int kEmitPer = SPHB_EMIT_PER;
 
 template <typename T>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, SPHB_EMIT_MINB)
 emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0, const T *w1, const T *w2,
             const T *w3, int nw, int64_t n, const uint32_t *cell_start, uint32_t *cell_cursor,
             unsigned long long *totals, uint32_t *keys, uint32_t *vals, T *recs_large, T *recs_small,
