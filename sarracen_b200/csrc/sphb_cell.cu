@@ -324,6 +324,67 @@ cell_kernel(View v, const T *__restrict__ recs, const double *__restrict__ lut, 
     for (int64_t base = start; base < end; base += 32, batch++) {
         // ---- this batch has landed; every lane derives one particle ----------------------------
         mbar_wait(bar, (unsigned)batch & 1u);
+        if (!ACC) {
+            // ---- every box of the call holds <= kTinyVolume pixels: each lane walks the few pixels of ITS
+            // particle straight from registers into the raster -- no staging slots, no shuffles (the sub-group
+            // scheme below, which this instantiation used before, spent 31 warp instructions per particle on
+            // re-reading the slots; this is ~10)
+            if (base + lane < end) {
+                const Rec<T> pr = smem_rec(raw0, v.rec_stride, lane);
+                const double hp = (double)pr.h;
+                const double xp = (double)pr.x, yp = (double)pr.y;
+                const double rad = v.radius * hp;
+                const double hinv = 1.0 / hp, hinv2 = hinv * hinv;
+                int x0, x1, y0, y1, z0 = 0, z1 = 1;
+                pixel_range(xp, rad, v.x_min, v.inv_pwx, v.nx, x0, x1);
+                pixel_range(yp, rad, v.y_min, v.inv_pwy, v.ny, y0, y1);
+                const R sx = (R)(v.pwx * hinv), sy = (R)(v.pwy * hinv);
+                const R ox = (R)(-((xp - v.x_min) * v.inv_pwx - 0.5 - x0) * (v.pwx * hinv));
+                const R oy = (R)(-((yp - v.y_min) * v.inv_pwy - 0.5 - y0) * (v.pwy * hinv));
+                R sz = R(0), oz = R(0);
+                double cc = 0.0;
+                if (DIM3) {
+                    const double zp = (double)pr.z;
+                    pixel_range(zp, rad, v.z_min, v.inv_pwz, v.nz, z0, z1);
+                    sz = (R)(v.pwz * hinv);
+                    oz = (R)(-((zp - v.z_min) * v.inv_pwz - 0.5 - z0) * (v.pwz * hinv));
+                } else if (v.use_z) {
+                    const double dz = v.z_slice - (double)pr.z;
+                    cc = dz * dz * hinv2;
+                }
+                const double scale = v.norm * (v.ndim == 2 ? hinv2 : hinv2 * hinv);
+                R term[NW];
+#pragma unroll
+                for (int k = 0; k < NW; k++) term[k] = (R)((double)pr.w[k] * scale);
+                const R cq = (R)cc + sqrt_guard(R(0));
+                const int wx = x1 - x0, wy = y1 - y0, wz = z1 - z0;
+                // a box beyond the tiny volume can only come with a stale plan (sphb_scatter_planned): dropped
+                if (wx > 0 && wy > 0 && wz > 0 && wx * wy * wz <= kTinyVolume) {
+                    for (int iz = 0; iz < wz; iz++) {
+                        const R dzs = fma((R)iz, sz, oz);
+                        const R qz = fma(dzs, dzs, cq);
+                        for (int iy = 0; iy < wy; iy++) {
+                            const R dys = fma((R)iy, sy, oy);
+                            const R qyz = fma(dys, dys, qz);
+                            const size_t row = ((size_t)(z0 + iz) * v.ny + (size_t)(y0 + iy)) * v.nx + (size_t)x0;
+                            for (int ix = 0; ix < wx; ix++) {
+                                const R dxs = fma((R)ix, sx, ox);
+                                const R q2 = fma(dxs, dxs, qyz);
+                                if (q2 < rad2) {
+                                    const R wv = kernel_eval_pos<KIND, R>(q2, lv);
+                                    SPHB_ASSERT(row + ix < v.n_out);
+#pragma unroll
+                                    for (int k = 0; k < NW; k++) red_add(outs[k] + row + ix, (double)(term[k] * wv));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && base + 32 < end) fetch(base + 32); // the raw buffer is free again
+            continue;
+        }
         int vol = 0, my_cell = -1, my_class = 0;
         {
             int4 geo = make_int4(0, 0, -1, 0);
