@@ -147,9 +147,13 @@ int sphb_line3d(const sphb_particles *p, const sphb_kernel *k, int pixels, doubl
 /* Same, rendered in `n_stages` z-slab stages for the multi-GPU reduction along z
  * (SURVEY 8(e)): stage s finishes every z-plane below stage_planes[s] (ascending; the last
  * stage finishes the grid whatever its entry says), and right after the kernels of stage s have
- * been enqueued on `stream` the library calls on_stage(user, s) on the calling thread -- the
- * caller records an event there and starts reducing that slab on another stream while the later
- * stages render.  n_stages = 1 with on_stage = NULL is sphb_scatter3d. */
+ * been enqueued the library calls on_stage(user, s) on the calling thread -- the caller records an
+ * event on `stream` there and starts reducing that slab on another stream while the later stages
+ * render.  The kernels of consecutive stages run on two library-owned streams, forked from `stream`
+ * and joined to it before each callback (so that the tail of one stage overlaps the head of the
+ * next): work the caller enqueues on `stream` in or after the callback of stage s is ordered after
+ * the stages 0..s and may overlap the later ones.  n_stages = 1 with on_stage = NULL is
+ * sphb_scatter3d. */
 typedef void (*sphb_stage_fn)(void *user, int stage);
 int sphb_scatter3d_staged(const sphb_particles *p, const sphb_kernel *k, const sphb_raster *r, int accumulate,
                           double *const *out, void *ws, size_t ws_bytes, size_t *ws_needed, sphb_stats *stats,

@@ -4,28 +4,32 @@
 // pixels; binning it per tile, staging it per tile and scanning it per warp costs far more than
 // its few kernel evaluations, and one global reduction per contribution is bound by the
 // reduction rate of the SM (1.29 cycles per lane).  Such particles are therefore counting-sorted
-// by the CELL that holds the origin of their box (32 x 32 pixels / 8 x 8 x 8 voxels; smaller
-// with several weight columns) -- the emit kernel writes their packed records in cell order --
-// and rendered here with a LOCAL ACCUMULATOR:
+// by the CELL that holds the origin of their box (32 x 32 pixels / 4 x 4 x 4 voxels, 4 x 4 x 8 for
+// sparse sets) -- the emit kernel writes their packed records in cell order -- and rendered here
+// with a LOCAL ACCUMULATOR:
 //
 //   * a warp takes kCellChunk consecutive records of that stream, 32 at a time.  The stream is
 //     contiguous, so a batch is ONE 1-D TMA bulk copy (cp.async.bulk global -> shared, completion
-//     on an mbarrier; SASS UBLKCP) issued by lane 0 a batch ahead: batch k+1 lands while batch k is
-//     evaluated.  Every lane derives one particle's box, scales and terms from the staged record
-//     and parks them in the warp's staging slots;
+//     on an mbarrier; SASS UBLKCP).  Every lane derives one particle's box, scales and terms from
+//     the staged record and parks them in the warp's staging slots; that empties the raw buffer,
+//     so lane 0 issues the bulk copy of the next batch right then and it lands while this batch is
+//     evaluated (one buffer per warp);
 //   * the warp owns a private shared-memory accumulator that covers one cell plus the halo a
-//     box can reach beyond it ((cell + halo)^d values per weight).  Particles are walked one at
-//     a time with the lanes laid over the box -- in-plane pixels across lanes (several z-slices
-//     at once for narrow boxes), a loop over z -- and accumulated with plain
-//     load / fma / store: the accumulator is exclusive to the warp, lanes of one particle
-//     touch distinct pixels, so no atomics are needed;
+//     box can reach beyond it ((cell + halo)^d values per weight).  The batch is taken apart into
+//     runs of one cell and, inside a run, classes of equal z-extent; each class is a tight loop
+//     over its particles, one particle per pass with the lanes laid over the box plane and the
+//     z-column unrolled at compile time, accumulated with plain load / fma / store: the
+//     accumulator is exclusive to the warp, lanes of one particle touch distinct pixels, so no
+//     atomics are needed.  Images and narrow / wide box planes take a generic per-particle path;
 //   * when the stream moves on to another cell (or the chunk ends) the non-zero part of the
 //     accumulator is added to the float64 raster with red.global.add.f64, coalesced along x,
-//     and cleared: global atomics only at cell boundaries -- 3.4 per particle instead of 57.6
-//     for BASELINE config 4;
+//     and cleared: global atomics only at cell boundaries -- 8 per voxel instead of 57.6 per
+//     particle for BASELINE config 4;
 //   * a batch whose boxes all hold at most 16 pixels (h <~ pixel: 4 contributions per particle)
 //     skips the accumulator: sub-groups of lanes take one particle each and reduce straight
-//     into the raster, which costs less than walking such particles one per warp pass.
+//     into the raster.  When EVERY box of the call is that small the accumulator-free
+//     instantiation runs instead, in which each lane walks the pixels of its own particle
+//     straight from registers.
 //
 // Replaces the pixel loop of CPUBackend._fast_2d (cpu_backend.py:263-308) and the per-slice loop
 // of CPUBackend.interpolate_3d_grid (:193-220) for small footprints.
@@ -42,7 +46,7 @@ constexpr int kTinyVolume = 16; // a batch whose largest box holds <= this many 
 // ---- TMA: 1-D bulk copies global -> shared, completion on an mbarrier -------------------------
 // The cell-ordered records of a warp's chunk are one contiguous stream, so the next batch of 32
 // records (1-2 KB) is fetched by ONE cp.async.bulk issued by lane 0 (SASS: UBLKCP) while the warp
-// works on the current batch; the lanes then read their record from shared memory.
+// evaluates the current batch; the lanes then read their record from shared memory.
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
