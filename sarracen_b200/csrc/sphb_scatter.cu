@@ -203,7 +203,7 @@ constexpr int kEmitPer = SPHB_EMIT_PER;
 template <typename T>
 __global__ void __launch_bounds__(256, SPHB_EMIT_MINB)
 emit_kernel(View v, const T *x, const T *y, const T *z, const T *h, const T *w0, const T *w1, const T *w2,
-            const T *w3, int nw, int64_t n, const uint32_t *cell_start, uint32_t *cell_cursor,
+            const T *w3, int nw, int64_t n, uint32_t *cell_cursor,
             unsigned long long *totals, uint32_t *keys, uint32_t *vals, T *recs_large, T *recs_small,
             int64_t n_pairs, int64_t n_small, int dbg_mode)
 {
@@ -771,7 +771,7 @@ static int scatter_impl(const sphb_particles *p, const sphb_kernel *k, const sph
         SPHB_CUDA(cudaMemsetAsync(keys_a, 0xff, (size_t)n_pairs * sizeof(uint32_t), stream));
     emit_kernel<T><<<div_up(n, 256 * kEmitPer), 256, 0, stream>>>(
         v, x, y, z, h, static_cast<const T *>(p->w[0]), static_cast<const T *>(p->w[1]),
-        static_cast<const T *>(p->w[2]), static_cast<const T *>(p->w[3]), p->n_weights, n, cell_start, cell_cursor,
+        static_cast<const T *>(p->w[2]), static_cast<const T *>(p->w[3]), p->n_weights, n, cell_cursor,
         totals, keys_a, vals_a, recs_large, recs_small, n_pairs, n_small,
         getenv("SPHB_EMIT_MODE") ? atoi(getenv("SPHB_EMIT_MODE")) : 0);
     SPHB_LAUNCH_CHECK();
