@@ -3,7 +3,7 @@
 particles/sec for interpolate_3d_proj & interpolate_3d_grid at 1/2/4/8 B200, % of HBM roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload proj|grid|grid_hmin]
-                    [--sub grid,grid_hmin|none] [--dtype f64|f32] [--impl reference]
+                    [--sub grid,grid_hmin,exact2d,exact3d|none] [--dtype f64|f32] [--impl reference]
 
 A "step" is one pass of the hot path over one FIXED synthetic particle set:
 
@@ -26,9 +26,10 @@ HBM; `e2e` times the reference-facing call `B200Backend.interpolate_3d_projectio
 PAGEABLE host NumPy arrays (what Sarracen's front-end passes), host<->device copies inside the
 timed region.  With N GPUs the SAME particle set is sharded by contiguous index range (strong
 scaling: total work fixed), every rank renders its shard into a full-size partial raster and the
-partial rasters are combined inside the timed region: NCCL reduce to rank 0 (images) or NCCL
-reduce-scatter along z, issued per z-chunk and overlapped with the render of the following chunks
-(voxel grids, sarracen_b200/parallel.py).  `ms_collective` is the exchange timed on its own, `ms_compute` the
+partial rasters are combined inside the timed region: NCCL reduce to rank 0 (images) or a
+reduce-scatter along z, issued per z-chunk over peer memory (copy-engine pushes + sphb_sum_slots; NCCL
+reduce_scatter where symmetric memory is unavailable) and overlapped with the render of the following
+chunks (voxel grids, sarracen_b200/parallel.py).  `ms_collective` is the exchange timed on its own, `ms_compute` the
 step without it; `collective_hidden` = (ms_compute + ms_collective - ms_per_step) / ms_collective.
 
 `--impl reference` times the reference's own CPU implementation of the headline workload on the
