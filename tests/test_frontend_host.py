@@ -126,3 +126,22 @@ def test_upload_chunk_schedule_and_host_column_views():
     assert backend._common_dtype([cols[4], cols[4]]) == torch.float32
     assert backend._host_columns([a, np.array(["x"] * 6)]) is None     # not numeric
     assert backend._host_columns([a, np.arange(5.0)]) is None          # ragged
+
+
+def test_bench_workloads_are_rank_count_independent():
+    """bench.py's fixed particle sets: any rank count generates the same set (independently seeded blocks),
+    and the exact workloads keep BASELINE config 5's shape (h log-uniform in [pw/20, 20 pw], centres inside)."""
+    import bench
+    for name, n in (("proj", 1 << 16), ("grid", 1 << 16), ("exact2d", 1 << 15), ("exact3d", 1 << 15)):
+        wl = bench.describe(name, n, "f64")
+        whole = bench.generate(wl, 0, 1, "f64")
+        parts = [bench.generate(wl, r, 4, "f64") for r in range(4)]
+        for key, col in whole.items():
+            np.testing.assert_array_equal(np.concatenate([p[key] for p in parts]), col)
+        assert whole["x"].shape[0] == n
+    wl = bench.describe("exact2d", 1 << 15, "f64")
+    c = bench.generate(wl, 0, 1, "f64")
+    pw = 1.0 / 1024
+    assert c["h"].min() >= pw / 20 and c["h"].max() <= 20 * pw
+    assert c["x"].min() >= 0.0 and c["x"].max() <= 1.0 and set(c) == {"x", "y", "h", "w"}
+    assert bench.default_particles("exact3d") == 1 << 23 and bench.default_particles("grid") == 1 << 27

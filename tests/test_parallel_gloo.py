@@ -79,6 +79,28 @@ def test_shard_ranges_cover_everything():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
 
 
+def test_block_cyclic_plane_ownership(monkeypatch):
+    """owned_planes / z_chunks: every plane has exactly one owner for any chunking that divides evenly,
+    the default is DEFAULT_CHUNKS reduced until it does, SPHB_Z_CHUNKS overrides it."""
+    from sarracen_b200 import parallel
+    from sarracen_b200.parallel import owned_planes, slab_range, z_chunks
+    monkeypatch.delenv("SPHB_Z_CHUNKS", raising=False)
+    assert parallel.DEFAULT_CHUNKS == 8 and parallel.TRANSPORTS == ("peer", "nccl")
+    assert z_chunks(512, 8) == 8 and z_chunks(512, 8, 2) == 2 and z_chunks(64, 8) == 8 and z_chunks(48, 8) == 6
+    assert z_chunks(24, 8) == 3 and z_chunks(8, 8) == 1 and z_chunks(35, 8) == 0 and z_chunks(7, 2) == 0
+    for nz, world, chunks in ((512, 8, None), (512, 2, 4), (64, 4, 8), (48, 8, None), (35, 8, None), (7, 2, 3), (6, 2, 1)):
+        planes = [owned_planes(nz, r, world, chunks) for r in range(world)]
+        assert sorted(p for pl in planes for p in pl) == list(range(nz))
+        c = z_chunks(nz, world, chunks)
+        if c == 0:
+            assert planes == [list(range(*slab_range(nz, r, world))) for r in range(world)]
+        else:
+            b = nz // (c * world)
+            assert all(pl[:b] == list(range(r * b, (r + 1) * b)) for r, pl in enumerate(planes))
+    monkeypatch.setenv("SPHB_Z_CHUNKS", "2")
+    assert z_chunks(512, 8) == 2 and z_chunks(512, 8, 4) == 4
+
+
 def test_two_rank_combine_matches_single_rank():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
